@@ -1,0 +1,214 @@
+"""ctypes binding of libbm25cu.so (include/bm25cu.h). There is no CPU fallback: if the shared library is
+missing, or a call fails, this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_PKG, "libbm25cu.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+METHOD_CODES = {"robertson": 0, "lucene": 1, "atire": 2, "bm25l": 3, "bm25+": 4}
+
+EXPORTED_SYMBOLS = [
+    "bm25cu_last_error", "bm25cu_version", "bm25cu_device_count", "bm25cu_index_upload", "bm25cu_build_begin",
+    "bm25cu_build_df_device", "bm25cu_build_df_get", "bm25cu_build_df_set", "bm25cu_build_finish",
+    "bm25cu_build_free", "bm25cu_index_build", "bm25cu_index_sizes", "bm25cu_index_download", "bm25cu_retrieve",
+    "bm25cu_retrieve_device", "bm25cu_scores_dense", "bm25cu_topk_dense", "bm25cu_topk_merge",
+    "bm25cu_topk_merge_device", "bm25cu_index_free",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("kernel_ms", C.c_float), ("fast_kernel_ms", C.c_float), ("total_ms", C.c_float),
+        ("posting_bytes", C.c_int64), ("algorithmic_bytes", C.c_int64),
+        ("n_fast", C.c_int32), ("n_general", C.c_int32), ("launches", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build_extension(verbose: bool = False) -> str:
+    """Compile libbm25cu.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libbm25cu.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    if verbose:
+        print(res.stdout[-2000:])
+    return SO_PATH
+
+
+def lib():
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(SO_PATH):
+                raise ImportError(
+                    f"{SO_PATH} is missing: the cuda backend has no CPU fallback. Build it with "
+                    "`make -C bm25s_b200/csrc` (or `python -c 'import __graft_entry__ as g; g.build()'`)."
+                )
+            L = C.CDLL(SO_PATH)
+            L.bm25cu_last_error.restype = C.c_char_p
+            for name in EXPORTED_SYMBOLS:
+                if name != "bm25cu_last_error":
+                    getattr(L, name).restype = C.c_int
+            _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    msg = lib().bm25cu_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int):
+    """Status -> exception mapping of the ABI: 1 -> ValueError, anything else non-zero -> RuntimeError."""
+    if status == 0:
+        return
+    msg = last_error()
+    if status == 1:
+        raise ValueError(msg)
+    if status == 4:
+        raise MemoryError(msg)
+    raise RuntimeError(f"libbm25cu status {status}: {msg}")
+
+
+def ptr(a, ctype):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    check(lib().bm25cu_device_count(C.byref(n)))
+    return int(n.value)
+
+
+class DeviceIndex:
+    """Owns one bm25cu_index handle (one doc-range shard on one device)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self._lock = threading.Lock()  # a handle is not thread-safe (include/bm25cu.h)
+        nnz, nv, nd, lo, hn = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib().bm25cu_index_sizes(self._h, C.byref(nnz), C.byref(nv), C.byref(nd), C.byref(lo), C.byref(hn)))
+        self.nnz, self.n_vocab, self.n_docs, self.doc_lo, self.has_nonocc = nnz.value, nv.value, nd.value, lo.value, bool(hn.value)
+
+    @classmethod
+    def upload(cls, data, indices, indptr, n_docs, nonocc=None, device=0, doc_lo=0, doc_hi=None):
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        nonocc = None if nonocc is None else np.ascontiguousarray(nonocc, dtype=np.float32)
+        doc_hi = n_docs if doc_hi is None else doc_hi
+        h = C.c_void_p()
+        check(lib().bm25cu_index_upload(ptr(data, C.c_float), ptr(indices, C.c_int32), ptr(indptr, C.c_int64),
+                                        C.c_int64(len(data)), C.c_int32(len(indptr) - 1), C.c_int32(n_docs),
+                                        ptr(nonocc, C.c_float), C.c_int32(device), C.c_int32(doc_lo), C.c_int32(doc_hi),
+                                        C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def build(cls, tokens, doc_ptr, n_vocab, method, idf_method, k1, b, delta, device=0):
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        doc_ptr = np.ascontiguousarray(doc_ptr, dtype=np.int64)
+        h = C.c_void_p()
+        check(lib().bm25cu_index_build(ptr(tokens, C.c_int32), ptr(doc_ptr, C.c_int64), C.c_int32(len(doc_ptr) - 1),
+                                       C.c_int32(n_vocab), C.c_int32(METHOD_CODES[method]),
+                                       C.c_int32(METHOD_CODES[idf_method]), C.c_double(k1), C.c_double(b),
+                                       C.c_double(delta), C.c_int32(device), C.c_int32(0), C.byref(h)))
+        return cls(h)
+
+    def download(self):
+        data = np.empty(self.nnz, np.float32)
+        indices = np.empty(self.nnz, np.int32)
+        indptr = np.empty(self.n_vocab + 1, np.int64)
+        nonocc = np.empty(self.n_vocab, np.float32) if self.has_nonocc else None
+        check(lib().bm25cu_index_download(self._h, ptr(data, C.c_float), ptr(indices, C.c_int32),
+                                          ptr(indptr, C.c_int64), ptr(nonocc, C.c_float)))
+        return data, indices, indptr, nonocc
+
+    def retrieve(self, q_tokens, q_ptr, k, shift=None, mask=None, with_stats=False):
+        q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
+        q_ptr = np.ascontiguousarray(q_ptr, dtype=np.int64)
+        nq = len(q_ptr) - 1
+        shift = None if shift is None else np.ascontiguousarray(shift, dtype=np.float32)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.float64)
+        ids = np.empty((nq, k), np.int32)
+        scores = np.empty((nq, k), np.float32)
+        st = Stats()
+        with self._lock:
+            check(lib().bm25cu_retrieve(self._h, ptr(q_tokens, C.c_int32), ptr(q_ptr, C.c_int64), C.c_int32(nq),
+                                        C.c_int32(k), C.c_int32(1), ptr(shift, C.c_float), ptr(mask, C.c_double),
+                                        ptr(ids, C.c_int32), ptr(scores, C.c_float), C.byref(st)))
+        return (ids, scores, st.as_dict()) if with_stats else (ids, scores)
+
+    def retrieve_device(self, q_tokens_ptr, q_ptr_ptr, n_queries, n_query_tokens, k, out_ids_ptr, out_scores_ptr,
+                        shift_ptr=None, mask_ptr=None):
+        """All pointers are raw device addresses (e.g. torch.Tensor.data_ptr()) on this handle's device."""
+        st = Stats()
+        with self._lock:
+            check(lib().bm25cu_retrieve_device(self._h, C.c_void_p(q_tokens_ptr), C.c_void_p(q_ptr_ptr),
+                                               C.c_int32(n_queries), C.c_int64(n_query_tokens), C.c_int32(k),
+                                               C.c_void_p(shift_ptr), C.c_void_p(mask_ptr), C.c_void_p(out_ids_ptr),
+                                               C.c_void_p(out_scores_ptr), C.byref(st)))
+        return st.as_dict()
+
+    def scores_dense(self, q_tokens, shift=None, mask=None):
+        q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.float64)
+        out = np.empty(self.n_docs, np.float32)
+        with self._lock:
+            check(lib().bm25cu_scores_dense(self._h, ptr(q_tokens, C.c_int32), C.c_int32(len(q_tokens)),
+                                            C.c_int32(shift is not None), C.c_float(0.0 if shift is None else float(shift)),
+                                            ptr(mask, C.c_double), ptr(out, C.c_float)))
+        return out
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.bm25cu_index_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def topk_dense(scores: np.ndarray, k: int, device: int = 0):
+    scores = np.ascontiguousarray(scores)
+    if scores.dtype == np.float64:
+        is64, ct = 1, C.c_double
+    else:
+        scores = scores.astype(np.float32, copy=False)
+        is64, ct = 0, C.c_float
+    ids = np.empty(k, np.int64)
+    out = np.empty(k, scores.dtype)
+    check(lib().bm25cu_topk_dense(ptr(scores, ct), C.c_int32(is64), C.c_int64(scores.shape[0]), C.c_int32(k),
+                                  C.c_int32(1), ptr(ids, C.c_int64), ptr(out, ct), C.c_int32(device)))
+    return out, ids
+
+
+def topk_merge(ids: np.ndarray, scores: np.ndarray, device: int = 0):
+    """ids/scores: [n_parts, n_queries, k] -> merged [n_queries, k]."""
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    n_parts, nq, k = ids.shape
+    oi = np.empty((nq, k), np.int32)
+    os_ = np.empty((nq, k), np.float32)
+    check(lib().bm25cu_topk_merge(ptr(ids, C.c_int32), ptr(scores, C.c_float), C.c_int32(n_parts), C.c_int32(nq),
+                                  C.c_int32(k), ptr(oi, C.c_int32), ptr(os_, C.c_float), C.c_int32(device)))
+    return oi, os_

@@ -1,0 +1,146 @@
+// Shared internals of libbm25cu.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/bm25cu.h"
+
+namespace bm25cu {
+
+void set_error(const std::string &msg);
+
+#define BM25CU_CHECK(expr)                                                                        \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            char _buf[512];                                                                       \
+            snprintf(_buf, sizeof(_buf), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,            \
+                     cudaGetErrorString(_e));                                                     \
+            bm25cu::set_error(_buf);                                                              \
+            return (_e == cudaErrorMemoryAllocation) ? BM25CU_ENOMEM : BM25CU_ECUDA;              \
+        }                                                                                         \
+    } while (0)
+
+#define BM25CU_REQUIRE(cond, msg)      \
+    do {                               \
+        if (!(cond)) {                 \
+            bm25cu::set_error(msg);    \
+            return BM25CU_EINVAL;      \
+        }                              \
+    } while (0)
+
+// A growable device / pinned-host buffer owned by a handle.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return BM25CU_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        BM25CU_CHECK(cudaMalloc(&p, want));
+        cap = want;
+        return BM25CU_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return BM25CU_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        BM25CU_CHECK(cudaMallocHost(&p, want));
+        cap = want;
+        return BM25CU_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+constexpr int kPadElems = 64;  // every posting array is over-allocated by this many elements (bulk-copy tails)
+
+}  // namespace bm25cu
+
+// One doc-range shard of the CSC score matrix, resident in HBM (layout: DESIGN.md "Data layout").
+struct bm25cu_index {
+    int device = 0;
+    int32_t n_vocab = 0;
+    int32_t n_docs = 0;    // documents in this shard (local ids 0..n_docs-1)
+    int32_t doc_base = 0;  // global id of local doc 0
+    int64_t nnz = 0;
+    float *d_data = nullptr;       // f32[nnz + pad]  scores, column (token) major, rows ascending
+    int32_t *d_indices = nullptr;  // i32[nnz + pad]  local doc ids
+    int64_t *d_indptr = nullptr;   // i64[n_vocab + 1]
+    float *d_nonocc = nullptr;     // f32[n_vocab] or null (kept for download only)
+    bool nonneg = true;            // all data >= 0 and finite: the fused streaming kernel is exact
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // per-call workspaces
+    bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,
+        d_spill, d_order;
+    bm25cu::PinBuf h_in, h_out;
+    int general_rows = 0;
+};
+
+namespace bm25cu {
+
+// ---- kernels / launchers implemented across the .cu files ------------------------------------------------
+struct RetrieveArgs {
+    const int32_t *q_tokens;  // device
+    const int64_t *q_ptr;     // device
+    int32_t n_queries;
+    int32_t k;
+    const float *shift;  // device or null
+    const double *mask;  // device or null
+    int32_t *out_ids;    // device [n_queries * k]
+    float *out_scores;   // device
+};
+
+// control block in device memory (zeroed before every call)
+struct Ctrl {
+    unsigned int fast_next;      // work-queue cursor of the fused kernel
+    unsigned int general_count;  // number of queries routed to the general kernel
+    unsigned int general_next;
+    unsigned int error;          // bit 0: token id out of range
+    unsigned long long posting_count;
+    unsigned int pad[2];
+};
+
+int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_general_list,
+                         int *launches);
+int launch_retrieve_general(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl,
+                            const unsigned int *d_general_list, int *launches);
+int launch_scores_dense(bm25cu_index *ix, const int32_t *d_q, int32_t n_tokens, int has_shift, float shift,
+                        const double *d_mask, float *d_out);
+int topk_dense_device(const void *d_scores, int is_f64, int64_t n, int32_t k, int64_t *d_out_ids, void *d_out_scores,
+                      cudaStream_t stream);
+int topk_merge_device(const int32_t *ids, const float *scores, int32_t n_parts, int32_t n_queries, int32_t k,
+                      int32_t *out_ids, float *out_scores, cudaStream_t stream);
+int finalize_index(bm25cu_index *ix);          // device attributes, events, non-negativity scan
+int alloc_postings(bm25cu_index *ix, int64_t nnz);  // d_data / d_indices with bulk-copy padding
+
+}  // namespace bm25cu

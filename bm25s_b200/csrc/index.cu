@@ -1,0 +1,247 @@
+// Index residency: upload of the reference's CSC arrays (bm25s/__init__.py:432-438, :1121-1127) into HBM,
+// doc-range shard extraction on the device, download, free.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace bm25cu {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+// per column: [first posting with doc >= doc_lo, first posting with doc >= doc_hi)
+__global__ void shard_bounds_kernel(const int32_t *__restrict__ indices, const int64_t *__restrict__ indptr,
+                                    int32_t n_vocab, int32_t doc_lo, int32_t doc_hi, int64_t *start, int64_t *count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_vocab) return;
+    const int64_t s = indptr[t], e = indptr[t + 1];
+    int64_t lo = s, hi = e;
+    while (lo < hi) {
+        int64_t m = (lo + hi) >> 1;
+        if (indices[m] < doc_lo) lo = m + 1; else hi = m;
+    }
+    const int64_t a = lo;
+    hi = e;
+    while (lo < hi) {
+        int64_t m = (lo + hi) >> 1;
+        if (indices[m] < doc_hi) lo = m + 1; else hi = m;
+    }
+    start[t] = a;
+    count[t] = lo - a;
+}
+
+// one warp per column copies its in-shard slice, rebasing doc ids to shard-local ids
+__global__ void shard_copy_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices,
+                                  const int64_t *__restrict__ start, const int64_t *__restrict__ new_indptr,
+                                  int32_t n_vocab, int32_t doc_lo, float *out_data, int32_t *out_indices) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_vocab) return;
+    const int64_t src = start[warp], dst = new_indptr[warp], cnt = new_indptr[warp + 1] - dst;
+    for (int64_t i = lane; i < cnt; i += 32) {
+        out_data[dst + i] = data[src + i];
+        out_indices[dst + i] = indices[src + i] - doc_lo;
+    }
+}
+
+// flags[0] |= 1 if any score is negative, NaN or infinite
+__global__ void check_nonneg_kernel(const float *__restrict__ data, int64_t nnz, unsigned int *flags) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = data[i];
+        bad |= !(v >= 0.0f && v < __int_as_float(0x7f800000));
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+}
+
+int finalize_index(bm25cu_index *ix) {
+    cudaDeviceProp prop;
+    BM25CU_CHECK(cudaGetDeviceProperties(&prop, ix->device));
+    ix->sm_count = prop.multiProcessorCount;
+    ix->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    for (int i = 0; i < 6; ++i) BM25CU_CHECK(cudaEventCreate(&ix->ev[i]));
+    unsigned int *d_flag = nullptr;
+    BM25CU_CHECK(cudaMalloc(&d_flag, sizeof(unsigned int)));
+    BM25CU_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(unsigned int), ix->stream));
+    if (ix->nnz > 0) {
+        check_nonneg_kernel<<<ix->sm_count * 4, 256, 0, ix->stream>>>(ix->d_data, ix->nnz, d_flag);
+        BM25CU_CHECK(cudaGetLastError());
+    }
+    unsigned int flag = 0;
+    BM25CU_CHECK(cudaMemcpyAsync(&flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost, ix->stream));
+    BM25CU_CHECK(cudaStreamSynchronize(ix->stream));
+    cudaFree(d_flag);
+    ix->nonneg = (flag == 0);
+    return BM25CU_OK;
+}
+
+int alloc_postings(bm25cu_index *ix, int64_t nnz) {
+    BM25CU_CHECK(cudaMalloc(&ix->d_data, (size_t)(nnz + kPadElems) * sizeof(float)));
+    BM25CU_CHECK(cudaMalloc(&ix->d_indices, (size_t)(nnz + kPadElems) * sizeof(int32_t)));
+    BM25CU_CHECK(cudaMemsetAsync(ix->d_data + nnz, 0, kPadElems * sizeof(float), ix->stream));
+    BM25CU_CHECK(cudaMemsetAsync(ix->d_indices + nnz, 0x7f, kPadElems * sizeof(int32_t), ix->stream));
+    return BM25CU_OK;
+}
+
+static void destroy(bm25cu_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    cudaFree(ix->d_data);
+    cudaFree(ix->d_indices);
+    cudaFree(ix->d_indptr);
+    cudaFree(ix->d_nonocc);
+    bm25cu::DevBuf *bufs[] = {&ix->d_qtok, &ix->d_qptr, &ix->d_shift, &ix->d_mask, &ix->d_out_ids, &ix->d_out_scores,
+                              &ix->d_ctrl, &ix->d_general_list, &ix->d_scratch, &ix->d_spill, &ix->d_order};
+    for (auto *b : bufs) b->release();
+    ix->h_in.release();
+    ix->h_out.release();
+    for (int i = 0; i < 6; ++i)
+        if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+}  // namespace bm25cu
+
+using namespace bm25cu;
+
+extern "C" {
+
+const char *bm25cu_last_error(void) { return g_last_error.c_str(); }
+int bm25cu_version(void) { return 100; }
+
+int bm25cu_device_count(int32_t *n) {
+    BM25CU_REQUIRE(n != nullptr, "bm25cu_device_count: null output");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    *n = c;
+    return BM25CU_OK;
+}
+
+int bm25cu_index_upload(const float *data, const int32_t *indices, const int64_t *indptr, int64_t nnz,
+                        int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
+                        int32_t doc_hi, bm25cu_index **out) {
+    BM25CU_REQUIRE(out != nullptr, "bm25cu_index_upload: null output handle");
+    *out = nullptr;
+    BM25CU_REQUIRE(nnz >= 0 && n_vocab >= 0 && n_docs >= 0, "bm25cu_index_upload: negative size");
+    BM25CU_REQUIRE(indptr != nullptr, "bm25cu_index_upload: null indptr");
+    BM25CU_REQUIRE(nnz == 0 || (data != nullptr && indices != nullptr), "bm25cu_index_upload: null data/indices");
+    BM25CU_REQUIRE(0 <= doc_lo && doc_lo <= doc_hi && doc_hi <= n_docs, "bm25cu_index_upload: bad doc range");
+    BM25CU_REQUIRE(indptr[0] == 0 && indptr[n_vocab] == nnz, "bm25cu_index_upload: indptr does not span [0, nnz]");
+    BM25CU_CHECK(cudaSetDevice(device));
+    bm25cu_index *ix = new bm25cu_index();
+    ix->device = device;
+    ix->n_vocab = n_vocab;
+    ix->n_docs = doc_hi - doc_lo;
+    ix->doc_base = doc_lo;
+    int rc = BM25CU_OK;
+    auto fail = [&](int code) { destroy(ix); return code; };
+#define TRY(expr)                                                       \
+    do {                                                                \
+        cudaError_t _e = (expr);                                        \
+        if (_e != cudaSuccess) {                                        \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+            return fail(_e == cudaErrorMemoryAllocation ? BM25CU_ENOMEM : BM25CU_ECUDA); \
+        }                                                               \
+    } while (0)
+    TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    TRY(cudaMalloc(&ix->d_indptr, (size_t)(n_vocab + 1) * sizeof(int64_t)));
+    if (nonocc) {
+        TRY(cudaMalloc(&ix->d_nonocc, (size_t)(n_vocab > 0 ? n_vocab : 1) * sizeof(float)));
+        TRY(cudaMemcpyAsync(ix->d_nonocc, nonocc, (size_t)n_vocab * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    }
+    const bool whole = (doc_lo == 0 && doc_hi == n_docs);
+    if (whole) {
+        ix->nnz = nnz;
+        if ((rc = alloc_postings(ix, nnz))) return fail(rc);
+        TRY(cudaMemcpyAsync(ix->d_indptr, indptr, (size_t)(n_vocab + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+        if (nnz) {
+            TRY(cudaMemcpyAsync(ix->d_data, data, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+            TRY(cudaMemcpyAsync(ix->d_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ix->stream));
+        }
+    } else {
+        // stage the full matrix on the device, cut out the doc range there
+        float *f_data = nullptr;
+        int32_t *f_indices = nullptr;
+        int64_t *f_indptr = nullptr, *d_start = nullptr, *d_count = nullptr, *d_tmp = nullptr;
+        auto cleanup = [&]() { cudaFree(f_data); cudaFree(f_indices); cudaFree(f_indptr); cudaFree(d_start); cudaFree(d_count); cudaFree(d_tmp); };
+#define TRY2(expr)                                                      \
+    do {                                                                \
+        cudaError_t _e = (expr);                                        \
+        if (_e != cudaSuccess) {                                        \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+            cleanup();                                                  \
+            return fail(_e == cudaErrorMemoryAllocation ? BM25CU_ENOMEM : BM25CU_ECUDA); \
+        }                                                               \
+    } while (0)
+        TRY2(cudaMalloc(&f_data, (size_t)(nnz + 1) * sizeof(float)));
+        TRY2(cudaMalloc(&f_indices, (size_t)(nnz + 1) * sizeof(int32_t)));
+        TRY2(cudaMalloc(&f_indptr, (size_t)(n_vocab + 1) * sizeof(int64_t)));
+        TRY2(cudaMalloc(&d_start, (size_t)(n_vocab + 1) * sizeof(int64_t)));
+        TRY2(cudaMalloc(&d_count, (size_t)(n_vocab + 1) * sizeof(int64_t)));
+        TRY2(cudaMalloc(&d_tmp, scan_tmp_elems(n_vocab) * sizeof(long long)));
+        TRY2(cudaMemcpyAsync(f_indptr, indptr, (size_t)(n_vocab + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+        if (nnz) {
+            TRY2(cudaMemcpyAsync(f_data, data, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+            TRY2(cudaMemcpyAsync(f_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ix->stream));
+        }
+        if (n_vocab > 0) {
+            shard_bounds_kernel<<<(n_vocab + 255) / 256, 256, 0, ix->stream>>>(f_indices, f_indptr, n_vocab, doc_lo, doc_hi, d_start, d_count);
+            TRY2(cudaGetLastError());
+        }
+        TRY2(exclusive_scan<long long>((const long long *)d_count, n_vocab, (long long *)ix->d_indptr, (long long *)d_tmp, ix->stream));
+        int64_t new_nnz = 0;
+        TRY2(cudaMemcpyAsync(&new_nnz, ix->d_indptr + n_vocab, sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+        TRY2(cudaStreamSynchronize(ix->stream));
+        ix->nnz = new_nnz;
+        if ((rc = alloc_postings(ix, new_nnz))) { cleanup(); return fail(rc); }
+        if (n_vocab > 0 && new_nnz > 0) {
+            const int64_t threads = (int64_t)n_vocab * 32;
+            shard_copy_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ix->stream>>>(f_data, f_indices, d_start, ix->d_indptr, n_vocab, doc_lo, ix->d_data, ix->d_indices);
+            TRY2(cudaGetLastError());
+        }
+        TRY2(cudaStreamSynchronize(ix->stream));
+        cleanup();
+#undef TRY2
+    }
+    TRY(cudaStreamSynchronize(ix->stream));
+#undef TRY
+    if ((rc = finalize_index(ix))) return fail(rc);
+    *out = ix;
+    return BM25CU_OK;
+}
+
+int bm25cu_index_sizes(const bm25cu_index *ix, int64_t *nnz, int32_t *n_vocab, int32_t *n_docs_local,
+                       int32_t *doc_lo, int32_t *has_nonocc) {
+    BM25CU_REQUIRE(ix != nullptr, "bm25cu_index_sizes: null handle");
+    if (nnz) *nnz = ix->nnz;
+    if (n_vocab) *n_vocab = ix->n_vocab;
+    if (n_docs_local) *n_docs_local = ix->n_docs;
+    if (doc_lo) *doc_lo = ix->doc_base;
+    if (has_nonocc) *has_nonocc = ix->d_nonocc != nullptr;
+    return BM25CU_OK;
+}
+
+int bm25cu_index_download(const bm25cu_index *ix, float *data, int32_t *indices, int64_t *indptr, float *nonocc) {
+    BM25CU_REQUIRE(ix != nullptr, "bm25cu_index_download: null handle");
+    BM25CU_CHECK(cudaSetDevice(ix->device));
+    if (data && ix->nnz) BM25CU_CHECK(cudaMemcpy(data, ix->d_data, (size_t)ix->nnz * sizeof(float), cudaMemcpyDeviceToHost));
+    if (indices && ix->nnz) BM25CU_CHECK(cudaMemcpy(indices, ix->d_indices, (size_t)ix->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (indptr) BM25CU_CHECK(cudaMemcpy(indptr, ix->d_indptr, (size_t)(ix->n_vocab + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (nonocc) {
+        BM25CU_REQUIRE(ix->d_nonocc != nullptr, "bm25cu_index_download: index has no nonoccurrence array");
+        BM25CU_CHECK(cudaMemcpy(nonocc, ix->d_nonocc, (size_t)ix->n_vocab * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return BM25CU_OK;
+}
+
+int bm25cu_index_free(bm25cu_index *ix) {
+    destroy(ix);
+    return BM25CU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / the BM25 class) against the golden fixtures made
+from the reference and against the oracles on seeded inputs. Integer/index results bit-exact (ids as sets within
+runs of equal score); float32 scores bit-exact (tolerance 0) on the query path."""
+import os
+
+import numpy as np
+import pytest
+
+from _check import check_topk_rows, lists_from_flat, load_golden
+from oracle import c_oracle as CO
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+METHODS = O.METHODS
+
+
+def key(m):
+    return m.replace("+", "plus")
+
+
+def _dev(g, m, **kw):
+    from bm25s_b200 import DeviceIndex
+
+    nonocc = g[f"{key(m)}_nonocc"] if f"{key(m)}_nonocc" in g else None
+    N = len(g["corpus_ptr"]) - 1
+    return DeviceIndex.upload(g[f"{key(m)}_data"], g[f"{key(m)}_indices"], g[f"{key(m)}_indptr"], N, nonocc=nonocc, **kw), nonocc, N
+
+
+def _shifts(nonocc, queries):
+    return None if nonocc is None else np.array([O.query_shift(nonocc, q) for q in queries], np.float32)
+
+
+@pytest.mark.parametrize("name", ["synth_small", "synth_medium"])
+@pytest.mark.parametrize("force_general", [0, 1])
+def test_retrieve_matches_reference_fixture(name, force_general, monkeypatch):
+    monkeypatch.setenv("BM25CU_FORCE_GENERAL", str(force_general))
+    g = load_golden(name)
+    queries = lists_from_flat(g["query_tokens"], g["query_ptr"])
+    k = int(g["k"])
+    for m in METHODS:
+        dev, nonocc, N = _dev(g, m)
+        data, indices, indptr = g[f"{key(m)}_data"], g[f"{key(m)}_indices"], g[f"{key(m)}_indptr"]
+        sh = _shifts(nonocc, queries)
+        ids, sc, st = dev.retrieve(g["query_tokens"], g["query_ptr"], k, shift=sh, with_stats=True)
+        dense_fn = lambda qi: O.get_scores(data, indptr, indices, N, queries[qi], nonocc)  # noqa: E731
+        check_topk_rows(ids, sc, g[f"{key(m)}_ids"], g[f"{key(m)}_scores"], dense_fn, what=f"{name} {m} general={force_general}")
+        assert st["n_general"] == (len(queries) if force_general else 0)
+        assert st["posting_bytes"] == 8 * sum(int(indptr[t + 1] - indptr[t]) for q in queries for t in q)
+        # weight masks (numpy order: mask, then shift): 0/1 float32 and arbitrary float64
+        for mk in ("mask01", "maskf64"):
+            ids, sc = dev.retrieve(g["query_tokens"], g["query_ptr"], k, shift=sh, mask=g[mk])
+            np.testing.assert_array_equal(sc, g[f"{key(m)}_scores_{mk}"])
+            dfn = lambda qi: O.get_scores(data, indptr, indices, N, queries[qi], nonocc, g[mk])  # noqa: E731
+            check_topk_rows(ids, sc, ids, g[f"{key(m)}_scores_{mk}"], dfn, what=f"{name} {m} {mk}")
+        dev.close()
+
+
+@pytest.mark.parametrize("name", ["readme_corpus", "synth_small"])
+def test_dense_scores_bit_exact(name):
+    g = load_golden(name)
+    for m in METHODS:
+        dev, nonocc, N = _dev(g, m)
+        if name == "readme_corpus":
+            q = g["query_ids"]
+            sh = None if nonocc is None else O.query_shift(nonocc, q)
+            np.testing.assert_array_equal(dev.scores_dense(q, shift=sh), g[f"{key(m)}_dense"])
+            for mk, mask in (("f32", np.array([1, 0, 0, 1], np.float32)), ("i32", np.array([1, 0, 0, 1], np.int32)),
+                             ("bool", np.array([1, 0, 0, 1], np.bool_))):
+                np.testing.assert_array_equal(dev.scores_dense(q, shift=sh, mask=mask.astype(np.float64)),
+                                              g[f"{key(m)}_dense_mask_{mk}"])
+        else:
+            queries = lists_from_flat(g["query_tokens"], g["query_ptr"])
+            for qi in range(g[f"{key(m)}_dense"].shape[0]):
+                sh = None if nonocc is None else O.query_shift(nonocc, queries[qi])
+                np.testing.assert_array_equal(dev.scores_dense(queries[qi], shift=sh), g[f"{key(m)}_dense"][qi])
+                np.testing.assert_array_equal(dev.scores_dense(queries[qi], shift=sh, mask=g["maskf64"]),
+                                              g[f"{key(m)}_dense_maskf64"][qi])
+        dev.close()
+
+
+def test_known_answer_csc():
+    """tests/core/test_scoring.py:26-98 through the ABI."""
+    from bm25s_b200 import DeviceIndex
+
+    dev = DeviceIndex.upload(np.array([1.0, 2.0], np.float32), np.array([0, 1], np.int32), np.array([0, 1, 2], np.int64), 3)
+    np.testing.assert_array_equal(dev.scores_dense([0, 1]), [1.0, 2.0, 0.0])
+    np.testing.assert_array_equal(dev.scores_dense([]), [0.0, 0.0, 0.0])
+    ids, sc = dev.retrieve([0, 1], [0, 2], 3)
+    np.testing.assert_array_equal(ids, [[1, 0, 2]])
+    np.testing.assert_array_equal(sc, [[2.0, 1.0, 0.0]])
+    dev2 = DeviceIndex.upload(np.array([1.5, 2.5], np.float32), np.array([0, 0], np.int32), np.array([0, 1, 2], np.int64), 2)
+    np.testing.assert_array_equal(dev2.scores_dense([0, 1]), [4.0, 0.0])
+    ids, sc = dev2.retrieve([0, 1], [0, 2], 2)
+    np.testing.assert_array_equal(ids, [[0, 1]])
+    np.testing.assert_array_equal(sc, [[4.0, 0.0]])
+    with pytest.raises(ValueError, match="maximum token ID"):
+        dev2.retrieve([0, 2], [0, 2], 1)
+
+
+def test_topk_dense_reference_vectors():
+    """tests/core/test_topk.py:16-59 and tests/core/test_selection.py:34-58 on the GPU selector."""
+    from bm25s_b200 import selection
+
+    g = load_golden("known_answers")
+    s, i = selection.topk(g["topk_scores_in"], 5)
+    np.testing.assert_array_equal(s, g["topk_s"])
+    np.testing.assert_array_equal(i, g["topk_i"])
+    assert i.dtype == np.int64 and s.dtype == np.float64
+    s, i = selection.topk(np.array([3.0, 1.0, 4.0, 2.0], np.float32), k=2)
+    np.testing.assert_array_equal(s, [4.0, 3.0])
+    np.testing.assert_array_equal(i, [2, 0])
+    rng = np.random.default_rng(3)
+    for n, k in ((1, 1), (33, 33), (5000, 100), (200_000, 1000), (70_000, 5000)):
+        x = rng.standard_normal(n).astype(np.float32)
+        x[rng.integers(0, n, n // 3)] = 0.0  # many ties at a common value
+        s, i = selection.topk(x, k)
+        ref = np.sort(x)[-k:][::-1]
+        np.testing.assert_array_equal(s, ref)
+        np.testing.assert_array_equal(x[i], s)
+        assert len(set(i.tolist())) == k
+
+
+def _random_csc(rng, n_docs, n_vocab, nnz_per_col_max, with_zero=False):
+    cols = []
+    for t in range(n_vocab):
+        df = int(rng.integers(0, min(nnz_per_col_max, n_docs) + 1))
+        cols.append(np.sort(rng.choice(n_docs, size=df, replace=False)).astype(np.int32))
+    indptr = np.zeros(n_vocab + 1, np.int64)
+    np.cumsum([len(c) for c in cols], out=indptr[1:])
+    indices = np.concatenate(cols) if indptr[-1] else np.zeros(0, np.int32)
+    data = (rng.random(len(indices)) * 3).astype(np.float32)
+    if with_zero and len(data):
+        data[rng.integers(0, len(data), len(data) // 10)] = 0.0
+    return data, indices.astype(np.int32), indptr
+
+
+def test_edge_cases_small():
+    """Empty queries, k = 0..N, repeated tokens, > 64 tokens (general path), all-zero columns, fewer than k matches."""
+    from bm25s_b200 import DeviceIndex
+
+    rng = np.random.default_rng(5)
+    n_docs, n_vocab = 37, 90
+    data, indices, indptr = _random_csc(rng, n_docs, n_vocab, 20, with_zero=True)
+    dev = DeviceIndex.upload(data, indices, indptr, n_docs)
+    queries = [[], [3], [3, 3, 3], [5, 7, 5, 9, 5], list(range(80)), [int(x) for x in rng.integers(0, n_vocab, 70)],
+               [11, 12], [], [int(x) for x in rng.integers(0, n_vocab, 64)]]
+    ptr = np.zeros(len(queries) + 1, np.int64)
+    np.cumsum([len(q) for q in queries], out=ptr[1:])
+    flat = np.array([t for q in queries for t in q], np.int32)
+    for k in (0, 1, 2, 5, 36, 37):
+        ids, sc, st = dev.retrieve(flat, ptr, k, with_stats=True)
+        assert ids.shape == (len(queries), k)
+        if k == 0:
+            continue
+        assert st["n_general"] == 2  # the two queries longer than 64 tokens
+        rid, rsc = O.retrieve(data, indptr, indices, n_docs, queries, k)
+        dense_fn = lambda qi: O.score_dense(data, indptr, indices, n_docs, queries[qi])  # noqa: E731
+        check_topk_rows(ids, sc, rid, rsc, dense_fn, what=f"edge k={k}")
+    # a shard with fewer documents than k pads with id -1 / -inf
+    dev.close()
+
+
+@pytest.mark.parametrize("k", [1, 10, 100, 1000])
+def test_random_corpus_vs_c_oracle(k):
+    """Zipf corpus with heavy columns: windows, contested documents, candidate-buffer compaction, k up to 1000."""
+    from bm25s_b200 import DeviceIndex, synth
+
+    n_docs, n_vocab = 120_000, 20_000
+    corp = synth.make_corpus(n_docs, 30, n_vocab, seed=7)
+    data, indices, indptr, nonocc = O.build_index(corp.to_lists(), n_vocab, "bm25+")
+    qs = synth.make_queries(64, n_vocab, seed=8)
+    # make some queries heavy: the most frequent tokens, repeated tokens
+    extra = [[0, 1, 2], [0, 0], [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11], [5]]
+    queries = qs.to_lists() + extra
+    ptr = np.zeros(len(queries) + 1, np.int64)
+    np.cumsum([len(q) for q in queries], out=ptr[1:])
+    flat = np.array([t for q in queries for t in q], np.int32)
+    sh = np.array([O.query_shift(nonocc, q) for q in queries], np.float32)
+    dev = DeviceIndex.upload(data, indices, indptr, n_docs, nonocc=nonocc)
+    ids, sc, st = dev.retrieve(flat, ptr, k, shift=sh, with_stats=True)
+    assert st["n_general"] == 0
+    rid, rsc = CO.retrieve(data, indices, indptr, n_docs, flat, ptr, k, shift=sh)
+    dense_fn = lambda qi: CO.scores_dense(data, indices, indptr, n_docs, queries[qi], shift=sh[qi])  # noqa: E731
+    check_topk_rows(ids, sc, rid, rsc, dense_fn if k <= 100 else None, what=f"random k={k}")
+    # small stage / tag settings force many windows and the same answer
+    for env in ({"BM25CU_STAGE": "2048", "BM25CU_TAG": "4096"}, {"BM25CU_THREADS": "256", "BM25CU_CTAS_PER_SM": "2"}):
+        old = {kk: os.environ.get(kk) for kk in env}
+        os.environ.update(env)
+        try:
+            ids2, sc2 = dev.retrieve(flat, ptr, k, shift=sh)
+        finally:
+            for kk, v in old.items():
+                if v is None:
+                    os.environ.pop(kk, None)
+                else:
+                    os.environ[kk] = v
+        np.testing.assert_array_equal(sc2, sc)
+        np.testing.assert_array_equal(ids2, ids)  # deterministic tie rule: identical ids whatever the tiling
+    dev.close()
+
+
+def test_doc_range_shards_merge_to_unsharded():
+    """shard by contiguous doc range, local top-k per shard, merge == unsharded result."""
+    from bm25s_b200 import DeviceIndex, topk_merge
+
+    g = load_golden("synth_medium")
+    m = "bm25l"
+    queries = lists_from_flat(g["query_tokens"], g["query_ptr"])
+    nonocc = g[f"{key(m)}_nonocc"]
+    N, k = len(g["corpus_ptr"]) - 1, int(g["k"])
+    sh = _shifts(nonocc, queries)
+    full, _, _ = _dev(g, m)
+    ids_full, sc_full = full.retrieve(g["query_tokens"], g["query_ptr"], k, shift=sh)
+    for parts in (2, 3, 8):
+        bounds = [N * p // parts for p in range(parts + 1)]
+        pi, ps = [], []
+        for p in range(parts):
+            d, _, _ = _dev(g, m, doc_lo=bounds[p], doc_hi=bounds[p + 1])
+            assert d.n_docs == bounds[p + 1] - bounds[p] and d.doc_lo == bounds[p]
+            i, s = d.retrieve(g["query_tokens"], g["query_ptr"], k, shift=sh)
+            pi.append(i)
+            ps.append(s)
+            d.close()
+        mi, ms = topk_merge(np.stack(pi), np.stack(ps))
+        np.testing.assert_array_equal(ms, sc_full)
+        np.testing.assert_array_equal(mi, ids_full)
+    # shard download returns the shard-local CSC
+    d, _, _ = _dev(g, m, doc_lo=100, doc_hi=1100)
+    data, indices, indptr, no = d.download()
+    full_idx = g[f"{key(m)}_indices"]
+    sel = (full_idx >= 100) & (full_idx < 1100)
+    np.testing.assert_array_equal(indices, full_idx[sel] - 100)
+    np.testing.assert_array_equal(data, g[f"{key(m)}_data"][sel])
+    np.testing.assert_array_equal(no, nonocc)
+    full.close()
