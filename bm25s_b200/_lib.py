@@ -16,7 +16,7 @@ CSRC = os.path.join(_PKG, "csrc")
 METHOD_CODES = {"robertson": 0, "lucene": 1, "atire": 2, "bm25l": 3, "bm25+": 4}
 
 EXPORTED_SYMBOLS = [
-    "bm25cu_last_error", "bm25cu_version", "bm25cu_device_count", "bm25cu_index_upload", "bm25cu_build_begin",
+    "bm25cu_last_error", "bm25cu_version", "bm25cu_device_count", "bm25cu_index_upload", "bm25cu_index_upload_device", "bm25cu_index_set_stream", "bm25cu_build_begin",
     "bm25cu_build_df_device", "bm25cu_build_df_get", "bm25cu_build_df_set", "bm25cu_build_finish",
     "bm25cu_build_free", "bm25cu_index_build", "bm25cu_index_sizes", "bm25cu_index_download", "bm25cu_retrieve",
     "bm25cu_retrieve_device", "bm25cu_scores_dense", "bm25cu_topk_dense", "bm25cu_topk_merge",
@@ -119,6 +119,21 @@ class DeviceIndex:
                                         ptr(nonocc, C.c_float), C.c_int32(device), C.c_int32(doc_lo), C.c_int32(doc_hi),
                                         C.byref(h)))
         return cls(h)
+
+    @classmethod
+    def upload_device(cls, data_ptr, indices_ptr, indptr_ptr, nnz, n_vocab, n_docs, nonocc_ptr=None, device=0, doc_lo=0,
+                      doc_hi=None):
+        """CSC arrays already on the device (raw addresses, e.g. torch.Tensor.data_ptr()); copied device-to-device."""
+        doc_hi = n_docs if doc_hi is None else doc_hi
+        h = C.c_void_p()
+        check(lib().bm25cu_index_upload_device(C.c_void_p(data_ptr), C.c_void_p(indices_ptr), C.c_void_p(indptr_ptr),
+                                               C.c_int64(nnz), C.c_int32(n_vocab), C.c_int32(n_docs),
+                                               C.c_void_p(nonocc_ptr), C.c_int32(device), C.c_int32(doc_lo),
+                                               C.c_int32(doc_hi), C.byref(h)))
+        return cls(h)
+
+    def set_stream(self, stream_handle: int):
+        check(lib().bm25cu_index_set_stream(self._h, C.c_void_p(stream_handle)))
 
     @classmethod
     def build(cls, tokens, doc_ptr, n_vocab, method, idf_method, k1, b, delta, device=0):

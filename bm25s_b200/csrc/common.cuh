@@ -98,6 +98,7 @@ struct bm25cu_index {
     int sm_count = 148;
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;
+    bool owns_stream = true;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,

@@ -97,7 +97,7 @@ static void destroy(bm25cu_index *ix) {
     ix->h_out.release();
     for (int i = 0; i < 6; ++i)
         if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
-    if (ix->stream) cudaStreamDestroy(ix->stream);
+    if (ix->stream && ix->owns_stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
 
@@ -122,16 +122,17 @@ int bm25cu_device_count(int32_t *n) {
     return BM25CU_OK;
 }
 
-int bm25cu_index_upload(const float *data, const int32_t *indices, const int64_t *indptr, int64_t nnz,
-                        int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
-                        int32_t doc_hi, bm25cu_index **out) {
+static int upload_impl(const float *data, const int32_t *indices, const int64_t *indptr, int64_t nnz,
+                       int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
+                       int32_t doc_hi, bool src_on_device, bm25cu_index **out) {
     BM25CU_REQUIRE(out != nullptr, "bm25cu_index_upload: null output handle");
     *out = nullptr;
     BM25CU_REQUIRE(nnz >= 0 && n_vocab >= 0 && n_docs >= 0, "bm25cu_index_upload: negative size");
     BM25CU_REQUIRE(indptr != nullptr, "bm25cu_index_upload: null indptr");
     BM25CU_REQUIRE(nnz == 0 || (data != nullptr && indices != nullptr), "bm25cu_index_upload: null data/indices");
     BM25CU_REQUIRE(0 <= doc_lo && doc_lo <= doc_hi && doc_hi <= n_docs, "bm25cu_index_upload: bad doc range");
-    BM25CU_REQUIRE(indptr[0] == 0 && indptr[n_vocab] == nnz, "bm25cu_index_upload: indptr does not span [0, nnz]");
+    if (!src_on_device)
+        BM25CU_REQUIRE(indptr[0] == 0 && indptr[n_vocab] == nnz, "bm25cu_index_upload: indptr does not span [0, nnz]");
     BM25CU_CHECK(cudaSetDevice(device));
     bm25cu_index *ix = new bm25cu_index();
     ix->device = device;
@@ -152,16 +153,16 @@ int bm25cu_index_upload(const float *data, const int32_t *indices, const int64_t
     TRY(cudaMalloc(&ix->d_indptr, (size_t)(n_vocab + 1) * sizeof(int64_t)));
     if (nonocc) {
         TRY(cudaMalloc(&ix->d_nonocc, (size_t)(n_vocab > 0 ? n_vocab : 1) * sizeof(float)));
-        TRY(cudaMemcpyAsync(ix->d_nonocc, nonocc, (size_t)n_vocab * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+        TRY(cudaMemcpyAsync(ix->d_nonocc, nonocc, (size_t)n_vocab * sizeof(float), cudaMemcpyDefault, ix->stream));
     }
     const bool whole = (doc_lo == 0 && doc_hi == n_docs);
     if (whole) {
         ix->nnz = nnz;
         if ((rc = alloc_postings(ix, nnz))) return fail(rc);
-        TRY(cudaMemcpyAsync(ix->d_indptr, indptr, (size_t)(n_vocab + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+        TRY(cudaMemcpyAsync(ix->d_indptr, indptr, (size_t)(n_vocab + 1) * sizeof(int64_t), cudaMemcpyDefault, ix->stream));
         if (nnz) {
-            TRY(cudaMemcpyAsync(ix->d_data, data, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-            TRY(cudaMemcpyAsync(ix->d_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ix->stream));
+            TRY(cudaMemcpyAsync(ix->d_data, data, (size_t)nnz * sizeof(float), cudaMemcpyDefault, ix->stream));
+            TRY(cudaMemcpyAsync(ix->d_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault, ix->stream));
         }
     } else {
         // stage the full matrix on the device, cut out the doc range there
@@ -184,10 +185,10 @@ int bm25cu_index_upload(const float *data, const int32_t *indices, const int64_t
         TRY2(cudaMalloc(&d_start, (size_t)(n_vocab + 1) * sizeof(int64_t)));
         TRY2(cudaMalloc(&d_count, (size_t)(n_vocab + 1) * sizeof(int64_t)));
         TRY2(cudaMalloc(&d_tmp, scan_tmp_elems(n_vocab) * sizeof(long long)));
-        TRY2(cudaMemcpyAsync(f_indptr, indptr, (size_t)(n_vocab + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+        TRY2(cudaMemcpyAsync(f_indptr, indptr, (size_t)(n_vocab + 1) * sizeof(int64_t), cudaMemcpyDefault, ix->stream));
         if (nnz) {
-            TRY2(cudaMemcpyAsync(f_data, data, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-            TRY2(cudaMemcpyAsync(f_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ix->stream));
+            TRY2(cudaMemcpyAsync(f_data, data, (size_t)nnz * sizeof(float), cudaMemcpyDefault, ix->stream));
+            TRY2(cudaMemcpyAsync(f_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault, ix->stream));
         }
         if (n_vocab > 0) {
             shard_bounds_kernel<<<(n_vocab + 255) / 256, 256, 0, ix->stream>>>(f_indices, f_indptr, n_vocab, doc_lo, doc_hi, d_start, d_count);
@@ -212,6 +213,28 @@ int bm25cu_index_upload(const float *data, const int32_t *indices, const int64_t
 #undef TRY
     if ((rc = finalize_index(ix))) return fail(rc);
     *out = ix;
+    return BM25CU_OK;
+}
+
+int bm25cu_index_upload(const float *data, const int32_t *indices, const int64_t *indptr, int64_t nnz,
+                        int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
+                        int32_t doc_hi, bm25cu_index **out) {
+    return upload_impl(data, indices, indptr, nnz, n_vocab, n_docs, nonocc, device, doc_lo, doc_hi, false, out);
+}
+
+int bm25cu_index_upload_device(const float *data, const int32_t *indices, const int64_t *indptr, int64_t nnz,
+                               int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
+                               int32_t doc_hi, bm25cu_index **out) {
+    return upload_impl(data, indices, indptr, nnz, n_vocab, n_docs, nonocc, device, doc_lo, doc_hi, true, out);
+}
+
+int bm25cu_index_set_stream(bm25cu_index *ix, void *stream) {
+    BM25CU_REQUIRE(ix != nullptr, "bm25cu_index_set_stream: null handle");
+    BM25CU_CHECK(cudaSetDevice(ix->device));
+    BM25CU_CHECK(cudaStreamSynchronize(ix->stream));
+    if (ix->owns_stream && ix->stream) cudaStreamDestroy(ix->stream);
+    ix->stream = (cudaStream_t)stream;
+    ix->owns_stream = false;
     return BM25CU_OK;
 }
 

@@ -104,3 +104,62 @@ def make_queries_torch(n_queries: int, n_vocab: int, seed: int = 1, mean_extra: 
     x = torch.exp(u * math.log(n_vocab + s) + (1.0 - u) * math.log(s)) - s
     tokens = x.floor_().clamp_(0, n_vocab - 1).to(torch.int32)
     return tokens, ptr
+
+
+def csc_from_tokens_torch(tokens, ptr, n_vocab: int, method: str = "lucene", k1: float = 1.5, b: float = 0.75,
+                          delta: float = 0.5):
+    """Benchmark/test plumbing: CSC score matrix of a flat corpus with torch ops on the corpus' device (one 64-bit
+    sort). Same formulae as bm25s/scoring.py (float64 math, one float32 rounding); `torch.log` may differ from libm
+    in the last float64 ulp, so use the library's GPU builder (bm25cu_index_build) where bit-parity matters.
+    Returns (data f32, indices i32, indptr i64, nonocc f32 | None) tensors."""
+    import torch
+
+    n_docs = ptr.numel() - 1
+    lens = ptr[1:] - ptr[:-1]
+    doc = torch.repeat_interleave(torch.arange(n_docs, device=tokens.device, dtype=torch.int64), lens)
+    key = tokens.to(torch.int64) * n_docs + doc
+    del doc
+    key, _ = torch.sort(key)
+    ukey, tf = torch.unique_consecutive(key, return_counts=True)
+    del key
+    tok = torch.div(ukey, n_docs, rounding_mode="floor")
+    d = ukey - tok * n_docs
+    del ukey
+    df = torch.bincount(tok, minlength=n_vocab)
+    indptr = torch.zeros(n_vocab + 1, dtype=torch.int64, device=tokens.device)
+    torch.cumsum(df, 0, out=indptr[1:])
+    N = float(n_docs)
+    dff = df.to(torch.float64)
+    if method == "robertson":
+        idf = torch.log(torch.clamp((N - dff + 0.5) / (dff + 0.5), min=1.0))
+    elif method == "lucene":
+        idf = torch.log(1 + (N - dff + 0.5) / (dff + 0.5))
+    elif method == "atire":
+        idf = torch.log(N / dff)
+    elif method == "bm25l":
+        idf = torch.log((N + 1) / (dff + 0.5))
+    elif method == "bm25+":
+        idf = torch.log((N + 1) / dff)
+    else:
+        raise ValueError(method)
+    idf = torch.where(df > 0, idf, torch.zeros_like(idf))
+    l_avg = lens.to(torch.float64).mean()
+    l_d = lens.to(torch.float64)[d]
+    tff = tf.to(torch.float64)
+    norm = 1 - b + b * l_d / l_avg
+    nonocc = None
+    if method in ("robertson", "lucene"):
+        tfc = tff / (k1 * norm + tff)
+    elif method == "atire":
+        tfc = (tff * (k1 + 1)) / (tff + k1 * norm)
+    elif method == "bm25l":
+        c = tff / norm
+        tfc = ((k1 + 1) * (c + delta)) / (k1 + c + delta)
+        nonocc = (idf * (((k1 + 1) * delta) / (k1 + delta))).to(torch.float32)
+    else:
+        tfc = ((k1 + 1) * tff) / (k1 * norm + tff) + delta
+        nonocc = (idf * delta).to(torch.float32)
+    score = idf.to(torch.float32).to(torch.float64)[tok] * tfc
+    if nonocc is not None:
+        score = score - nonocc.to(torch.float64)[tok]
+    return score.to(torch.float32), d.to(torch.int32), indptr, nonocc

@@ -65,6 +65,15 @@ int bm25cu_index_upload(const float *data, const int32_t *indices, const int64_t
                         int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
                         int32_t doc_hi, bm25cu_index **out);
 
+/* Same, but data / indices / indptr / nonocc are DEVICE pointers on `device` (tensor interop; copied device to device). */
+int bm25cu_index_upload_device(const float *data, const int32_t *indices, const int64_t *indptr, int64_t nnz,
+                               int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
+                               int32_t doc_hi, bm25cu_index **out);
+
+/* Run the handle's device work on a caller-owned CUDA stream (cudaStream_t, e.g. torch's current stream) so that
+ * the caller can bracket calls with its own events. Pass the stream's raw handle. */
+int bm25cu_index_set_stream(bm25cu_index *ix, void *stream);
+
 /*
  * Build the index on the GPU from flat token ids - replaces BM25.build_index_from_ids
  * (bm25s/__init__.py:326-438; scoring.py:28-57 df, :60-73 idf, :76-112 nonoccurrence, :115-159 tfc,
