@@ -62,6 +62,14 @@ int finish_stats(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, i
 
 extern "C" {
 
+// debug: copy the phase counters of the last retrieve call (32 x uint64); zeros unless built with -DBM25CU_PROFILE
+int bm25cu_debug_prof(bm25cu_index *ix, unsigned long long *out) {
+    BM25CU_REQUIRE(ix && out && ix->d_ctrl.p, "bm25cu_debug_prof: no retrieve call yet");
+    BM25CU_CHECK(cudaSetDevice(ix->device));
+    BM25CU_CHECK(cudaMemcpy(out, ix->d_ctrl.as<Ctrl>()->prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return BM25CU_OK;
+}
+
 int bm25cu_retrieve(bm25cu_index *ix, const int32_t *q_tokens, const int64_t *q_ptr, int32_t n_queries, int32_t k,
                     int32_t sorted, const float *shift_per_query, const double *weight_mask, int32_t *out_ids,
                     float *out_scores, bm25cu_stats *stats) {

@@ -94,6 +94,7 @@ struct bm25cu_index {
     int32_t *d_indices = nullptr;  // i32[nnz + pad]  local doc ids
     int64_t *d_indptr = nullptr;   // i64[n_vocab + 1]
     float *d_nonocc = nullptr;     // f32[n_vocab] or null (kept for download only)
+    float *d_colmax = nullptr;     // f32[n_vocab] largest score of every column (upper bounds for pruning)
     bool nonneg = true;            // all data >= 0 and finite: the fused streaming kernel is exact
     int sm_count = 148;
     int max_smem_optin = 0;
@@ -129,6 +130,7 @@ struct Ctrl {
     unsigned int error;          // bit 0: token id out of range
     unsigned long long posting_count;
     unsigned int pad[2];
+    unsigned long long prof[32];  // phase cycle counters / event counts of the fused kernel (BM25CU_PROFILE builds)
 };
 
 int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_general_list,

@@ -53,6 +53,20 @@ __global__ void check_nonneg_kernel(const float *__restrict__ data, int64_t nnz,
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
 }
 
+// colmax[t] = max of column t (0 for an empty column); one warp per column
+__global__ void column_max_kernel(const float *__restrict__ data, const int64_t *__restrict__ indptr, int32_t n_vocab,
+                                  float *colmax) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_vocab) return;
+    const int64_t s = indptr[warp], e = indptr[warp + 1];
+    float m = 0.0f;
+    for (int64_t i = s + lane; i < e; i += 32) m = fmaxf(m, data[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) colmax[warp] = m;
+}
+
 int finalize_index(bm25cu_index *ix) {
     cudaDeviceProp prop;
     BM25CU_CHECK(cudaGetDeviceProperties(&prop, ix->device));
@@ -64,6 +78,12 @@ int finalize_index(bm25cu_index *ix) {
     BM25CU_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(unsigned int), ix->stream));
     if (ix->nnz > 0) {
         check_nonneg_kernel<<<ix->sm_count * 4, 256, 0, ix->stream>>>(ix->d_data, ix->nnz, d_flag);
+        BM25CU_CHECK(cudaGetLastError());
+    }
+    BM25CU_CHECK(cudaMalloc(&ix->d_colmax, (size_t)(ix->n_vocab > 0 ? ix->n_vocab : 1) * sizeof(float)));
+    if (ix->n_vocab > 0) {
+        const int64_t threads = (int64_t)ix->n_vocab * 32;
+        column_max_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ix->stream>>>(ix->d_data, ix->d_indptr, ix->n_vocab, ix->d_colmax);
         BM25CU_CHECK(cudaGetLastError());
     }
     unsigned int flag = 0;
@@ -90,6 +110,7 @@ static void destroy(bm25cu_index *ix) {
     cudaFree(ix->d_indices);
     cudaFree(ix->d_indptr);
     cudaFree(ix->d_nonocc);
+    cudaFree(ix->d_colmax);
     bm25cu::DevBuf *bufs[] = {&ix->d_qtok, &ix->d_qptr, &ix->d_shift, &ix->d_mask, &ix->d_out_ids, &ix->d_out_scores,
                               &ix->d_ctrl, &ix->d_general_list, &ix->d_scratch, &ix->d_spill, &ix->d_order};
     for (auto *b : bufs) b->release();

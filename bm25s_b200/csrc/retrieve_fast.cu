@@ -29,14 +29,27 @@
 
 namespace bm25cu {
 
-constexpr int kMaxTok = 64;    // token slots per query on this path (tag byte: slot, or 0x80 | slot)
+#ifdef BM25CU_PROFILE
+#define PROF_DECL long long _pt = clock64(); unsigned long long _pc[32] = {0}
+#define PROF(i) do { long long _n = clock64(); _pc[i] += (unsigned long long)(_n - _pt); _pt = _n; } while (0)
+#define PROF_CNT(i, v) do { _pc[i] += (unsigned long long)(v); } while (0)
+#define PROF_FLUSH(cond) do { if (cond) for (int _i = 0; _i < 32; ++_i) if (_pc[_i]) atomicAdd(&p.ctrl->prof[_i], _pc[_i]); } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_CNT(i, v)
+#define PROF_FLUSH(cond)
+#endif
+
+constexpr int kMaxTok = 32;    // token slots per query on this path (tag byte: slot, 0x80 | slot, or 0xFF = clean)
 constexpr int kMinCap = 16;    // minimum staged postings per token per window (multiple of 4)
-constexpr int kPartCap = 4096; // floats of scratch for the contested-document partial scores
+constexpr unsigned char kClean = 0xFF;
 
 struct FastParams {
     const float *data;
     const int32_t *indices;
     const int64_t *indptr;
+    const float *colmax;
     int32_t n_docs, n_vocab, doc_base;
     RetrieveArgs a;
     Ctrl *ctrl;
@@ -45,9 +58,11 @@ struct FastParams {
     int stagecap;  // postings per stage buffer
     int cbcap;     // candidate entries (power of two, >= 2 * next_pow2(k))
     int rcap;      // contested-doc list entries
+    int partcap;   // floats of scratch for the contested-document partial scores
     unsigned long long *spill;  // per-CTA global overflow of the candidate buffer
     int spillcap;
     int route_all_general;
+    int prune;     // 0: every token is "essential" (no threshold pruning), 1: essential / non-essential split
 };
 
 // ---------------------------------------------------------------- PTX wrappers (mbarrier + bulk async copy)
@@ -90,15 +105,24 @@ struct SmemHdr {
     uint64_t bar_free[2];   // consumers are done with stage b      (producer waits)
     long long t_cur[kMaxTok];
     long long t_end[kMaxTok];
+    long long w_goff[2][kMaxTok];  // global posting index of the token's first posting in the window
     int t_cap[kMaxTok];
-    int t_off[kMaxTok];      // element offset of the token's region inside a stage buffer
-    int t_skip[2][kMaxTok];  // leading elements to skip (16-byte alignment of the global source)
-    int t_n[2][kMaxTok];     // valid staged postings
-    int w_cnt[2][kMaxTok];   // postings of the token inside the window of stage b
-    int w_off[2][kMaxTok];   // t_off + t_skip of stage b
-    int w_base[2];           // first document of the window
-    int w_last[2];           // 1 if this is the query's last window
-    int w_total[2];          // postings in the window
+    int t_off[kMaxTok];       // element offset of the token's region inside a stage buffer
+    float t_max[kMaxTok];     // largest score of the token's column
+    float t_rest[kMaxTok];    // upper bound of what the OTHER query tokens can add to a document
+    float t_nebound[kMaxTok]; // upper bound of a document hit only by this token and tokens with smaller maxima
+    int t_skip[2][kMaxTok];   // leading elements to skip (16-byte alignment of the global source)
+    int t_n[2][kMaxTok];      // valid staged postings
+    int w_ne[2][kMaxTok];     // 1: token is non-essential in this window (scores not staged)
+    int w_cnt[2][kMaxTok];    // postings of the token inside the window of stage b
+    int w_off[2][kMaxTok];    // t_off + t_skip of stage b
+    int w_preE[2][kMaxTok], w_endE[2][kMaxTok];    // flattened index space of the essential postings
+    int w_preN[2][kMaxTok], w_endN[2][kMaxTok];    // flattened index space of the non-essential postings
+    int w_base[2];            // first document of the window
+    int w_last[2];            // 1 if this is the query's last window
+    int w_ME[2], w_MN[2];     // essential / non-essential postings in the window
+    int w_nE[2];              // essential tokens with postings in the window
+    unsigned int w_kept[2];   // essential postings that survived the upper-bound filter (consumers count)
     unsigned int q_slot;
     unsigned int cb_cnt;
     unsigned int r_cnt;
@@ -115,10 +139,11 @@ __device__ __forceinline__ int cand_doc(unsigned long long c) { return (int)~(un
 template <int NT>
 struct Fast {
     static constexpr int CNT = NT - 32;  // consumer threads
+    static constexpr int NW = CNT / 32;  // consumer warps
     SmemHdr *h;
     unsigned long long *cb;   // [cbcap]
     int *rlist;               // [rcap]
-    float *part;              // [kPartCap]
+    float *part;              // [partcap]
     int *sdocs;               // [2][stagecap]
     float *sscores;           // [2][stagecap]
     unsigned char *tag;       // [tagcap]
@@ -133,7 +158,7 @@ struct Fast {
         rlist = reinterpret_cast<int *>(smem + o);
         o += (size_t)p.rcap * 4;
         part = reinterpret_cast<float *>(smem + o);
-        o += (size_t)kPartCap * 4;
+        o += (size_t)p.partcap * 4;
         o = (o + 15) & ~size_t(15);
         sdocs = reinterpret_cast<int *>(smem + o);
         o += (size_t)2 * p.stagecap * 4;
@@ -144,7 +169,7 @@ struct Fast {
     }
     static size_t fixed_smem(const FastParams &p) {
         size_t o = (sizeof(SmemHdr) + 15) & ~size_t(15);
-        o += (size_t)p.cbcap * 8 + (size_t)p.rcap * 4 + (size_t)kPartCap * 4;
+        o += (size_t)p.cbcap * 8 + (size_t)p.rcap * 4 + (size_t)p.partcap * 4;
         o = (o + 15) & ~size_t(15);
         o += (size_t)4 * p.stagecap * 4;
         return o;
@@ -196,7 +221,7 @@ struct Fast {
             if (sp_done >= spilled) {
                 if (id == 0) {
                     h->cb_cnt = keep;
-                    if (keep == (unsigned)k) h->theta = cand_score(cb[k - 1]);
+                    if (keep == (unsigned)k) h->theta = fmaxf(h->theta, cand_score(cb[k - 1]));
                 }
                 bsync<CONS>();
                 return;
@@ -217,24 +242,30 @@ struct Fast {
         }
     }
 
-    // producer: stage the next window of every live token into buffer b
+    // producer: stage the next window of every live token into buffer b. A token is non-essential when even a
+    // document containing it and every token with a smaller column maximum cannot reach the current threshold:
+    // only its document ids are staged then.
     __device__ void issue_loads(int b, int T) {
         const int lane = threadIdx.x & 31;
-        for (int t = lane; t < T; t += 32) {
+        const float theta_p = *reinterpret_cast<volatile float *>(&h->theta);
+        if (lane < T) {
+            const int t = lane;
             const long long cur = h->t_cur[t], rem = h->t_end[t] - cur;
+            const int ne = (p.prune && h->t_nebound[t] < theta_p) ? 1 : 0;
             int n = 0, a = 0;
             if (rem > 0) {
                 a = (int)(cur & 3);
                 const int cap = h->t_cap[t];
                 n = (int)min((long long)(cap - a), rem);
                 const uint32_t bytes = (uint32_t)(((a + n + 3) & ~3) * 4);
-                mbar_expect_tx(&h->bar_data[b], 2 * bytes);
+                mbar_expect_tx(&h->bar_data[b], ne ? bytes : 2 * bytes);
                 const size_t so = (size_t)b * p.stagecap + h->t_off[t];
                 bulk_g2s(sdocs + so, p.indices + (cur - a), bytes, &h->bar_data[b]);
-                bulk_g2s(sscores + so, p.data + (cur - a), bytes, &h->bar_data[b]);
+                if (!ne) bulk_g2s(sscores + so, p.data + (cur - a), bytes, &h->bar_data[b]);
             }
             h->t_skip[b][t] = a;
             h->t_n[b][t] = n;
+            h->w_ne[b][t] = ne;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&h->bar_data[b]);
@@ -259,6 +290,15 @@ struct Fast {
         return lo + __popc(__ballot_sync(0xffffffffu, pr));
     }
 
+    __device__ __forceinline__ int warp_excl_scan(int v, int &total) {
+        const int lane = threadIdx.x & 31;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        total = __shfl_sync(0xffffffffu, x, 31);
+        return x - v;
+    }
+
     // ------------------------------------------------------------------------------------------ producer warp
     __device__ void producer(int T, uint32_t &ph_data0, uint32_t &ph_data1, uint32_t &ph_free0, uint32_t &ph_free1) {
         const int lane = threadIdx.x & 31;
@@ -268,24 +308,18 @@ struct Fast {
             if (b == 0) { mbar_wait(&h->bar_data[0], ph_data0); ph_data0 ^= 1; }
             else { mbar_wait(&h->bar_data[1], ph_data1); ph_data1 ^= 1; }
             const int *bd = sdocs + (size_t)b * p.stagecap;
-            // per lane: tokens lane and lane + 32
-            int n0 = 0, n1 = 0, off0 = 0, off1 = 0, first = 0x7fffffff, e = 0x7fffffff, last0 = -1, last1 = -1;
+            int n0 = 0, off0 = 0, first = 0x7fffffff, e = 0x7fffffff, last0 = -1, ne = 0;
+            long long cur = 0, tend = 0;
             if (lane < T) {
                 n0 = h->t_n[b][lane];
                 off0 = h->t_off[lane] + h->t_skip[b][lane];
+                ne = h->w_ne[b][lane];
+                cur = h->t_cur[lane];
+                tend = h->t_end[lane];
                 if (n0 > 0) {
                     first = bd[off0];
                     last0 = bd[off0 + n0 - 1];
-                    if (h->t_cur[lane] + n0 < h->t_end[lane]) e = last0 + 1;
-                }
-            }
-            if (lane + 32 < T) {
-                n1 = h->t_n[b][lane + 32];
-                off1 = h->t_off[lane + 32] + h->t_skip[b][lane + 32];
-                if (n1 > 0) {
-                    first = min(first, bd[off1]);
-                    last1 = bd[off1 + n1 - 1];
-                    if (h->t_cur[lane + 32] + n1 < h->t_end[lane + 32]) e = min(e, last1 + 1);
+                    if (cur + n0 < tend) e = last0 + 1;
                 }
             }
 #pragma unroll
@@ -297,7 +331,6 @@ struct Fast {
             const int cap_end = (base > 0x7fffffff - p.tagcap) ? 0x7fffffff : base + p.tagcap;
             const int wend = min(e, cap_end);
             int c0 = (n0 > 0 && last0 < wend) ? n0 : 0;
-            int c1 = (n1 > 0 && last1 < wend) ? n1 : 0;
             // tokens whose staged postings reach beyond the window end need a search (rare)
             unsigned int need0 = __ballot_sync(0xffffffffu, n0 > 0 && last0 >= wend);
             while (need0) {
@@ -307,37 +340,30 @@ struct Fast {
                 const int c = warp_count_below(bd + so, sn, wend);
                 if (lane == src) c0 = c;
             }
-            unsigned int need1 = __ballot_sync(0xffffffffu, n1 > 0 && last1 >= wend);
-            while (need1) {
-                const int src = __ffs(need1) - 1;
-                need1 &= need1 - 1;
-                const int so = __shfl_sync(0xffffffffu, off1, src), sn = __shfl_sync(0xffffffffu, n1, src);
-                const int c = warp_count_below(bd + so, sn, wend);
-                if (lane == src) c1 = c;
-            }
+            int ME, MN;
+            const int wE = ne ? 0 : c0, wN = ne ? c0 : 0;
+            const int preE = warp_excl_scan(wE, ME), preN = warp_excl_scan(wN, MN);
+            const int nE = __popc(__ballot_sync(0xffffffffu, wE > 0));
             bool more = false;
             if (lane < T) {
                 h->w_cnt[b][lane] = c0;
                 h->w_off[b][lane] = off0;
-                const long long nc = h->t_cur[lane] + c0;
-                h->t_cur[lane] = nc;
-                more |= nc < h->t_end[lane];
+                h->w_goff[b][lane] = cur;
+                h->w_preE[b][lane] = preE;
+                h->w_endE[b][lane] = preE + wE;
+                h->w_preN[b][lane] = preN;
+                h->w_endN[b][lane] = preN + wN;
+                h->t_cur[lane] = cur + c0;
+                more = (cur + c0) < tend;
             }
-            if (lane + 32 < T) {
-                h->w_cnt[b][lane + 32] = c1;
-                h->w_off[b][lane + 32] = off1;
-                const long long nc = h->t_cur[lane + 32] + c1;
-                h->t_cur[lane + 32] = nc;
-                more |= nc < h->t_end[lane + 32];
-            }
-            int tot = c0 + c1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
             const bool any_more = __any_sync(0xffffffffu, more);
             if (lane == 0) {
                 h->w_base[b] = base;
                 h->w_last[b] = any_more ? 0 : 1;
-                h->w_total[b] = tot;
+                h->w_ME[b] = ME;
+                h->w_MN[b] = MN;
+                h->w_nE[b] = nE;
+                h->w_kept[b] = 0;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&h->bar_meta[b]);  // release: metadata visible to the consumers
@@ -350,8 +376,7 @@ struct Fast {
             issue_loads(b ^ 1, T);
             b ^= 1;
         }
-        // consume the release of the stages not waited for above (keeps barrier parities in step across queries)
-        // windows nwin-2 (if any) and nwin-1 are still unconsumed
+        // consume the releases not waited for above (keeps the barrier parities in step across queries)
         if (nwin >= 2) {
             const int bb = (nwin - 2) & 1;
             if (bb == 0) { mbar_wait(&h->bar_free[0], ph_free0); ph_free0 ^= 1; }
@@ -364,22 +389,47 @@ struct Fast {
         }
     }
 
+    // Visit the flattened positions [lo, hi) of one index space (pre/end per token slot) with the whole warp:
+    // body(t, f, j) is called by the lane that owns position f; `off[t] - pre[t] + f` is the staged element.
+    // j counts the warp's iterations (one bit of the per-thread masks), identical on every replay.
+    template <typename Body>
+    __device__ __forceinline__ void for_range(const int *pre, const int *end, int lo, int hi, Body body) {
+        const int lane = threadIdx.x & 31;
+        int t = 0, j = 0, f = lo;
+        while (f < hi) {
+            while (f >= end[t]) ++t;  // warp-uniform
+            const int seg_hi = min(end[t], hi);
+            const int pre_t = pre[t];
+            for (; f < seg_hi; f += 32, ++j) {
+                const int ff = f + lane;
+                if (ff < seg_hi) body(t, ff - pre_t, j);
+            }
+            f = seg_hi;
+        }
+    }
+
     // ------------------------------------------------------------------------------------------ consumer warps
     __device__ void consumer(int T, int k, uint32_t &ph_meta0, uint32_t &ph_meta1) {
         const int ctid = threadIdx.x - 32;
+        const int cw = ctid >> 5, lane = ctid & 31;
         const int trigger = p.cbcap / 2;
         float theta = 0.0f;
         int b = 0;
         bool first_window = true;
+        PROF_DECL;
         for (;;) {
+            PROF(0);
             if (b == 0) { mbar_wait(&h->bar_meta[0], ph_meta0); ph_meta0 ^= 1; }
             else { mbar_wait(&h->bar_meta[1], ph_meta1); ph_meta1 ^= 1; }
+            PROF(1);
+            PROF_CNT(16, 1);
             const int *bd = sdocs + (size_t)b * p.stagecap;
             const float *bs = sscores + (size_t)b * p.stagecap;
             const int base = h->w_base[b];
             const int last = h->w_last[b];
             const int *wcnt = h->w_cnt[b];
             const int *woff = h->w_off[b];
+            const int ME = h->w_ME[b], MN = h->w_MN[b];
 
             if (first_window) {
                 // Seed theta: the k-th largest score among the staged postings of the token with the most postings in
@@ -397,87 +447,146 @@ struct Fast {
                     const unsigned int bits = (unsigned int)(cb[k - 1] >> 32);
                     theta = bits > 0u ? __uint_as_float(bits - 1u) : 0.0f;  // next float below the k-th sampled score
                     bsync<true>();
+                    if (ctid == 0) h->theta = theta;
                 }
             }
 
-            // ---- P1: every posting claims its document's tag byte
-            for (int t = 0; t < T; ++t) {
-                const int c = wcnt[t];
-                const int *docs = bd + woff[t];
-#pragma unroll 4
-                for (int i = ctid; i < c; i += CNT) tag[docs[i] - base] = (unsigned char)t;
-            }
-            bsync<true>();
-            // ---- P2: postings that lost the claim mark the document as contested
-            for (int t = 0; t < T; ++t) {
-                const int c = wcnt[t];
-                const int *docs = bd + woff[t];
-#pragma unroll 4
-                for (int i = ctid; i < c; i += CNT) {
-                    const int o = docs[i] - base;
-                    if (tag[o] != (unsigned char)t) tag[o] = (unsigned char)(0x80 | t);
+            PROF(2);
+            PROF_CNT(17, ME); PROF_CNT(18, MN);
+            // this warp's slice of the two flattened index spaces (32-bit: postings per window * warps < 2^31)
+            const int eLo = (int)((unsigned)ME * (unsigned)cw / (unsigned)NW), eHi = (int)((unsigned)ME * (unsigned)(cw + 1) / (unsigned)NW);
+            const int nLo = (int)((unsigned)MN * (unsigned)cw / (unsigned)NW), nHi = (int)((unsigned)MN * (unsigned)(cw + 1) / (unsigned)NW);
+            const int *preE = h->w_preE[b], *endE = h->w_endE[b], *preN = h->w_preN[b], *endN = h->w_endN[b];
+            unsigned long long keptE = 0ull, hitN = 0ull;
+
+            // ---- P1: essential postings that can still reach the threshold claim their document's tag byte.
+            //      A posting (d, s) of token t is dropped when s + (sum of the other tokens' column maxima) <= theta:
+            //      no document containing it can enter the top-k.
+            for_range(preE, endE, eLo, eHi, [&](int t, int i, int j) {
+                const int o = woff[t] + i;
+                const float s = bs[o];
+                const float ub = __fmul_ru(__fadd_ru(s, h->t_rest[t]), 1.00002f);
+                if (ub > theta) {
+                    tag[bd[o] - base] = (unsigned char)t;
+                    keptE |= 1ull << j;
                 }
+            });
+            {
+                int kc = __popcll(keptE);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) kc += __shfl_xor_sync(0xffffffffu, kc, o);
+                if (lane == 0 && kc > 0) atomicAdd(&h->w_kept[b], (unsigned)kc);
             }
+            PROF(3);
             bsync<true>();
-            // ---- P3: uncontested owners score directly; the surviving marker owns the contested document
-            for (int t = 0; t < T; ++t) {
-                const int c = wcnt[t];
-                const int *docs = bd + woff[t];
-                const float *sc = bs + woff[t];
-#pragma unroll 4
-                for (int i = ctid; i < c; i += CNT) {
-                    const int d = docs[i];
-                    const unsigned char x = tag[d - base];
-                    if (x == (unsigned char)t) {
-                        const float s = sc[i];
-                        if (s > theta) emit(s, d);
-                    } else if (x == (unsigned char)(0x80 | t)) {
-                        const unsigned int r = atomicAdd(&h->r_cnt, 1u);
-                        if (r < (unsigned)p.rcap) rlist[r] = d;
-                    }
-                }
-            }
-            bsync<true>();
-            // ---- P4: contested documents are summed in query-token order (the reference's float32 order).
-            //      a) one thread per (document, token): binary search of the token's window postings
-            //      b) one thread per document: ordered sum of the partial scores found
-            const int R = min((int)h->r_cnt, p.rcap);
-            if (R > 0) {
-                const int chunk_docs = max(1, kPartCap / T);
-                for (int r0 = 0; r0 < R; r0 += chunk_docs) {
-                    const int nd = min(chunk_docs, R - r0);
-                    const int pairs = nd * T;
-                    for (int j = ctid; j < pairs; j += CNT) {
-                        const int r = j / T, t = j - r * T;
-                        const int d = rlist[r0 + r];
-                        const int c = wcnt[t];
-                        float v = -1.0f;
-                        if (c > 0) {
-                            const int *dt = bd + woff[t];
-                            int lo = 0, hi = c;
-                            while (lo < hi) { const int m = (lo + hi) >> 1; if (dt[m] < d) lo = m + 1; else hi = m; }
-                            if (lo < c && dt[lo] == d) v = bs[woff[t] + lo];
+            PROF(4);
+            const bool active = h->w_kept[b] > 0;
+            PROF_CNT(19, active ? 1 : 0); PROF_CNT(20, h->w_kept[b]);  // no surviving essential posting: nothing in this window can score
+            if (active) {
+                // ---- P2: essential postings that lost the claim mark the document as contested; non-essential
+                //      postings probe the tag and mark documents that some essential posting claimed
+                if (h->w_nE[b] >= 2 && keptE) {
+                    for_range(preE, endE, eLo, eHi, [&](int t, int i, int j) {
+                        if ((keptE >> j) & 1ull) {
+                            const int o = bd[woff[t] + i] - base;
+                            if (tag[o] != (unsigned char)t) tag[o] = (unsigned char)(0x80 | t);
                         }
-                        part[j] = v;
+                    });
+                }
+                for_range(preN, endN, nLo, nHi, [&](int t, int i, int j) {
+                    const int o = bd[woff[t] + i] - base;
+                    if (tag[o] != kClean) {
+                        tag[o] = (unsigned char)(0x80 | t);
+                        hitN |= 1ull << j;
                     }
-                    bsync<true>();
-                    for (int r = ctid; r < nd; r += CNT) {
-                        float sum = 0.0f;
-                        const float *pv = part + r * T;
-                        for (int t = 0; t < T; ++t) { const float v = pv[t]; if (v >= 0.0f) sum = __fadd_rn(sum, v); }
-                        if (sum > theta) emit(sum, rlist[r0 + r]);
+                });
+                PROF(5);
+                bsync<true>();
+                PROF(6);
+                // ---- P3: uncontested owners score directly; the surviving marker owns the contested document
+                if (keptE) {
+                    for_range(preE, endE, eLo, eHi, [&](int t, int i, int j) {
+                        if ((keptE >> j) & 1ull) {
+                            const int o = woff[t] + i;
+                            const int d = bd[o];
+                            const unsigned char x = tag[d - base];
+                            if (x == (unsigned char)t) {
+                                const float s = bs[o];
+                                if (s > theta) emit(s, d);
+                            } else if (x == (unsigned char)(0x80 | t)) {
+                                const unsigned int r = atomicAdd(&h->r_cnt, 1u);
+                                if (r < (unsigned)p.rcap) rlist[r] = d;
+                            }
+                        }
+                    });
+                }
+                if (hitN) {
+                    for_range(preN, endN, nLo, nHi, [&](int t, int i, int j) {
+                        if ((hitN >> j) & 1ull) {
+                            const int d = bd[woff[t] + i];
+                            if (tag[d - base] == (unsigned char)(0x80 | t)) {
+                                const unsigned int r = atomicAdd(&h->r_cnt, 1u);
+                                if (r < (unsigned)p.rcap) rlist[r] = d;
+                            }
+                        }
+                    });
+                }
+                PROF(7);
+                bsync<true>();
+                PROF(8);
+                // ---- P5: the essential postings clean the tags they claimed (tags are all-clean between windows)
+                if (keptE) {
+                    for_range(preE, endE, eLo, eHi, [&](int t, int i, int j) {
+                        if ((keptE >> j) & 1ull) tag[bd[woff[t] + i] - base] = kClean;
+                    });
+                }
+                // ---- P4: contested documents are summed in query-token order (the reference's float32 order).
+                //      a) one thread per (document, token): binary search of the token's window postings
+                //      b) one thread per document: ordered sum of the partial scores found
+                const int R = min((int)h->r_cnt, p.rcap);
+                PROF(9);
+                PROF_CNT(21, R);
+                if (R > 0) {
+                    const int chunk_docs = max(1, p.partcap / T);
+                    for (int r0 = 0; r0 < R; r0 += chunk_docs) {
+                        const int nd = min(chunk_docs, R - r0);
+                        const int pairs = nd * T;
+                        for (int jj = ctid; jj < pairs; jj += CNT) {
+                            const int r = jj / T, t = jj - r * T;
+                            const int d = rlist[r0 + r];
+                            const int c = wcnt[t];
+                            float v = -1.0f;
+                            if (c > 0) {
+                                const int *dt = bd + woff[t];
+                                int lo = 0, hi = c;
+                                while (lo < hi) { const int m = (lo + hi) >> 1; if (dt[m] < d) lo = m + 1; else hi = m; }
+                                if (lo < c && dt[lo] == d)
+                                    v = h->w_ne[b][t] ? p.data[h->w_goff[b][t] + lo] : bs[woff[t] + lo];
+                            }
+                            part[jj] = v;
+                        }
+                        bsync<true>();
+                        for (int r = ctid; r < nd; r += CNT) {
+                            float sum = 0.0f;
+                            const float *pv = part + r * T;
+                            for (int t = 0; t < T; ++t) { const float v = pv[t]; if (v >= 0.0f) sum = __fadd_rn(sum, v); }
+                            if (sum > theta) emit(sum, rlist[r0 + r]);
+                        }
+                        bsync<true>();
                     }
+                } else {
                     bsync<true>();
                 }
-            } else {
-                bsync<true>();
             }
+            PROF(10);
             // all consumers are done with stage b and the tags of this window
             if (ctid == 0) { h->r_cnt = 0; mbar_arrive(&h->bar_free[b]); }
-            if (h->cb_cnt >= (unsigned)trigger) { compact<true>(k, ctid, CNT); theta = fmaxf(theta, h->theta); }
+            if (h->cb_cnt >= (unsigned)trigger) { compact<true>(k, ctid, CNT); theta = fmaxf(theta, h->theta); PROF_CNT(22, 1); }
+            PROF(11);
             if (last) break;
             b ^= 1;
         }
+        PROF_FLUSH(ctid == 0);
     }
 
     __device__ void run() {
@@ -487,10 +596,13 @@ struct Fast {
             for (int i = 0; i < 2; ++i) { mbar_init(&h->bar_data[i], 1); mbar_init(&h->bar_meta[i], 1); mbar_init(&h->bar_free[i], 1); }
             fence_mbar_init();
         }
+        for (int i = tid * 16; i < p.tagcap; i += NT * 16) *reinterpret_cast<uint4 *>(tag + i) = make_uint4(~0u, ~0u, ~0u, ~0u);
         __syncthreads();
         uint32_t ph_data0 = 0, ph_data1 = 0, ph_free0 = 0, ph_free1 = 0, ph_meta0 = 0, ph_meta1 = 0;
 
+        PROF_DECL;
         for (;;) {
+            PROF(12);
             if (tid == 0) h->q_slot = atomicAdd(&p.ctrl->fast_next, 1u);
             __syncthreads();
             const unsigned int slot = h->q_slot;
@@ -507,32 +619,43 @@ struct Fast {
             if (tid < T) {
                 const int tok = p.a.q_tokens[qs + tid];
                 long long beg = 0, end = 0;
+                float mx = 0.0f;
                 if ((unsigned)tok >= (unsigned)p.n_vocab) atomicOr(&p.ctrl->error, 1u);
-                else { beg = p.indptr[tok]; end = p.indptr[tok + 1]; }
+                else { beg = p.indptr[tok]; end = p.indptr[tok + 1]; mx = p.colmax[tok]; }
                 h->t_cur[tid] = beg;
                 h->t_end[tid] = end;
+                h->t_max[tid] = mx;
             }
             if (tid == 0) { h->cb_cnt = 0; h->theta = 0.0f; h->r_cnt = 0; }
             __syncthreads();
-            if (warp == 0) {  // stage capacities proportional to document frequency
-                long long df0 = (lane < T) ? h->t_end[lane] - h->t_cur[lane] : 0;
-                long long df1 = (lane + 32 < T) ? h->t_end[lane + 32] - h->t_cur[lane + 32] : 0;
-                long long tot = df0 + df1;
+            if (warp == 0) {
+                // stage capacities proportional to document frequency; pruning bounds from the column maxima
+                const long long df0 = (lane < T) ? h->t_end[lane] - h->t_cur[lane] : 0;
+                long long tot = df0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
                 const long long freecap = (long long)p.stagecap - (long long)T * kMinCap;
-                int c0 = 0, c1 = 0;
+                int c0 = 0;
                 if (lane < T) c0 = kMinCap + (int)(tot > 0 ? ((freecap * df0) / tot) & ~3ll : 0);
-                if (lane + 32 < T) c1 = kMinCap + (int)(tot > 0 ? ((freecap * df1) / tot) & ~3ll : 0);
-                int x = c0;  // exclusive scan of caps -> offsets (slots 0..31 then 32..63)
+                int csum;
+                const int off = warp_excl_scan(c0, csum);
+                const float mx = (lane < T) ? h->t_max[lane] : 0.0f;
+                double msum = (double)mx;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-                const int tot0 = __shfl_sync(0xffffffffu, x, 31);
-                int x1 = c1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x1, o); if (lane >= o) x1 += y; }
-                if (lane < T) { h->t_cap[lane] = c0; h->t_off[lane] = x - c0; }
-                if (lane + 32 < T) { h->t_cap[lane + 32] = c1; h->t_off[lane + 32] = tot0 + x1 - c1; }
+                for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+                // documents hit only by this token and tokens ranked below it (by column maximum, ties by slot)
+                double below = (double)mx;
+                for (int j = 0; j < T; ++j) {
+                    const float mj = __shfl_sync(0xffffffffu, mx, j);
+                    if (j != lane && (mj < mx || (mj == mx && j < lane))) below += (double)mj;
+                }
+                if (lane < T) {
+                    h->t_cap[lane] = c0;
+                    h->t_off[lane] = off;
+                    // float32 sums of <= 32 non-negative terms exceed the exact sum by < 2^-18 relative: pad by 2^-15
+                    h->t_rest[lane] = __double2float_ru((msum - (double)mx) * 1.00003);
+                    h->t_nebound[lane] = __double2float_ru(below * 1.00003);
+                }
                 if (lane == 0) {
                     h->total_df = (unsigned long long)tot;
                     if (tot > 0) atomicAdd(&p.ctrl->posting_count, (unsigned long long)tot);
@@ -541,13 +664,17 @@ struct Fast {
                 if (tot > 0) issue_loads(0, T);
             }
             __syncthreads();
+            PROF(13);
             if (h->total_df > 0) {
                 if (warp == 0) producer(T, ph_data0, ph_data1, ph_free0, ph_free1);
                 else consumer(T, k, ph_meta0, ph_meta1);
             }
             __syncthreads();
+            PROF(14);
             finalize(q, T);
+            PROF(15);
         }
+        PROF_FLUSH(tid == 32);
     }
 
     // Sort the surviving candidates, pad with untouched documents if fewer than k matched, write the result row.
@@ -610,6 +737,8 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.data = ix->d_data;
     p.indices = ix->d_indices;
     p.indptr = ix->d_indptr;
+    p.colmax = ix->d_colmax;
+    p.prune = env_int("BM25CU_PRUNE", 1);
     p.n_docs = ix->n_docs;
     p.n_vocab = ix->n_vocab;
     p.doc_base = ix->doc_base;
@@ -619,14 +748,21 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     const int threads = env_int("BM25CU_THREADS", 512);
     const int ctas_per_sm = env_int("BM25CU_CTAS_PER_SM", 1);
     const int kcap = next_pow2(a.k < 1 ? 1 : a.k);
-    p.cbcap = 2 * kcap < 512 ? 512 : 2 * kcap;
+    const int cb_min = env_int("BM25CU_CBMIN", 512);
+    p.cbcap = 2 * kcap < cb_min ? next_pow2(cb_min) : 2 * kcap;
     p.route_all_general = (!ix->nonneg) || (a.mask != nullptr) || (a.k > 2048) || env_int("BM25CU_FORCE_GENERAL", 0);
     const int budget = ix->max_smem_optin / (ctas_per_sm > 0 ? ctas_per_sm : 1) - (ctas_per_sm > 1 ? 1024 : 0);
     int stage = env_int("BM25CU_STAGE", ctas_per_sm > 1 ? 2048 : 4096);
     stage = (stage + 3) & ~3;
-    if (stage < kMaxTok * kMinCap * 2) stage = kMaxTok * kMinCap * 2;
+    if (stage < kMaxTok * kMinCap + 64) stage = kMaxTok * kMinCap + 64;
+    {   // the per-thread posting masks hold 64 warp iterations: (postings per consumer warp) / 32 + kMaxTok <= 64
+        const int nw = ((threads == 64 || threads == 128 || threads == 256 || threads == 1024) ? threads : 512) / 32 - 1;
+        const int max_stage = nw * 32 * (64 - kMaxTok - 2);
+        if (stage > max_stage) stage = max_stage & ~3;
+    }
     p.stagecap = stage;
     p.rcap = stage / 2 + 64;
+    p.partcap = stage < 256 ? 256 : (stage > 4096 ? 4096 : stage);
     size_t fixed = Fast<512>::fixed_smem(p);
     long long tagcap = (long long)budget - (long long)fixed - 64;
     if (tagcap < 4096) {
@@ -645,20 +781,17 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.spill = ix->d_spill.as<unsigned long long>();
     const size_t smem = fixed + p.tagcap;
     cudaError_t e;
+#define BM25CU_LAUNCH(NTV)                                                                                          \
+    e = cudaFuncSetAttribute(retrieve_fast_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    if (e == cudaSuccess) retrieve_fast_kernel<NTV><<<grid, NTV, smem, ix->stream>>>(p);
     switch (threads) {
-        case 256:
-            e = cudaFuncSetAttribute(retrieve_fast_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) retrieve_fast_kernel<256><<<grid, 256, smem, ix->stream>>>(p);
-            break;
-        case 1024:
-            e = cudaFuncSetAttribute(retrieve_fast_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) retrieve_fast_kernel<1024><<<grid, 1024, smem, ix->stream>>>(p);
-            break;
-        default:
-            e = cudaFuncSetAttribute(retrieve_fast_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) retrieve_fast_kernel<512><<<grid, 512, smem, ix->stream>>>(p);
-            break;
+        case 64: BM25CU_LAUNCH(64); break;
+        case 128: BM25CU_LAUNCH(128); break;
+        case 256: BM25CU_LAUNCH(256); break;
+        case 1024: BM25CU_LAUNCH(1024); break;
+        default: BM25CU_LAUNCH(512); break;
     }
+#undef BM25CU_LAUNCH
     BM25CU_CHECK(e);
     BM25CU_CHECK(cudaGetLastError());
     if (launches) ++*launches;
