@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const In *
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(long long *tile_sums, long long n_tiles,
+static __global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(long long *tile_sums, long long n_tiles,
                                                                          long long *grand_total) {
     __shared__ long long ws[33];
     long long carry = 0;
