@@ -146,6 +146,16 @@ class DeviceIndex:
                                        C.c_double(delta), C.c_int32(device), C.c_int32(0), C.byref(h)))
         return cls(h)
 
+    @classmethod
+    def build_device(cls, tokens_ptr, doc_ptr_ptr, n_docs, n_vocab, method, idf_method, k1, b, delta, device=0):
+        """Corpus already on the device: int32 tokens / int64 doc_ptr raw addresses."""
+        h = C.c_void_p()
+        check(lib().bm25cu_index_build(C.c_void_p(tokens_ptr), C.c_void_p(doc_ptr_ptr), C.c_int32(n_docs),
+                                       C.c_int32(n_vocab), C.c_int32(METHOD_CODES[method]),
+                                       C.c_int32(METHOD_CODES[idf_method]), C.c_double(k1), C.c_double(b),
+                                       C.c_double(delta), C.c_int32(device), C.c_int32(1), C.byref(h)))
+        return cls(h)
+
     def download(self):
         data = np.empty(self.nnz, np.float32)
         indices = np.empty(self.nnz, np.int32)
@@ -195,6 +205,53 @@ class DeviceIndex:
         if self._h is not None and _lib is not None:
             _lib.bm25cu_index_free(self._h)
         self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Builder:
+    """Two-step GPU index build of one doc-range shard (bm25cu_build_begin / _finish). Between the two steps the
+    caller sums the document frequencies, the document count and the total length over all shards."""
+
+    def __init__(self, tokens, doc_ptr, n_vocab, device=0, on_device=False, n_docs=None):
+        self._b = C.c_void_p()
+        self.n_vocab = int(n_vocab)
+        if on_device:
+            self.n_docs = int(n_docs)
+            check(lib().bm25cu_build_begin(C.c_void_p(tokens), C.c_void_p(doc_ptr), C.c_int32(self.n_docs),
+                                           C.c_int32(n_vocab), C.c_int32(device), C.c_int32(1), C.byref(self._b)))
+        else:
+            tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+            doc_ptr = np.ascontiguousarray(doc_ptr, dtype=np.int64)
+            self.n_docs = len(doc_ptr) - 1
+            check(lib().bm25cu_build_begin(ptr(tokens, C.c_int32), ptr(doc_ptr, C.c_int64), C.c_int32(self.n_docs),
+                                           C.c_int32(n_vocab), C.c_int32(device), C.c_int32(0), C.byref(self._b)))
+
+    def df(self) -> np.ndarray:
+        out = np.empty(self.n_vocab, np.int32)
+        check(lib().bm25cu_build_df_get(self._b, ptr(out, C.c_int32)))
+        return out
+
+    def set_df(self, df: np.ndarray):
+        df = np.ascontiguousarray(df, dtype=np.int32)
+        assert len(df) == self.n_vocab
+        check(lib().bm25cu_build_df_set(self._b, ptr(df, C.c_int32)))
+
+    def finish(self, n_docs_global, total_len_global, method, idf_method, k1, b, delta, doc_lo=0) -> "DeviceIndex":
+        h = C.c_void_p()
+        check(lib().bm25cu_build_finish(self._b, C.c_int64(n_docs_global), C.c_int64(total_len_global),
+                                        C.c_int32(METHOD_CODES[method]), C.c_int32(METHOD_CODES[idf_method]),
+                                        C.c_double(k1), C.c_double(b), C.c_double(delta), C.c_int32(doc_lo), C.byref(h)))
+        return DeviceIndex(h)
+
+    def close(self):
+        if self._b is not None and _lib is not None:
+            _lib.bm25cu_build_free(self._b)
+        self._b = None
 
     def __del__(self):
         try:
