@@ -98,19 +98,41 @@ def shape_of(args):
     return n_docs, avg_len, n_vocab, n_queries
 
 
-def build_corpus_index(args, device):
-    """Synthetic corpus + CSC on the GPU (setup, untimed)."""
-    import torch
-
+def build_corpus(args, device):
+    """Synthetic corpus + queries on the GPU (setup, untimed)."""
     from bm25s_b200 import synth
 
     n_docs, avg_len, n_vocab, n_queries = shape_of(args)
     tokens, ptr = synth.make_corpus_torch(n_docs, avg_len, n_vocab, seed=0, device=device)
-    data, indices, indptr, nonocc = synth.csc_from_tokens_torch(tokens, ptr, n_vocab, method=args.method)
-    del tokens, ptr
-    torch.cuda.empty_cache()
     q_tok, q_ptr = synth.make_queries_torch(n_queries, n_vocab, seed=1, device=device)
-    return (data, indices, indptr, nonocc), (q_tok, q_ptr), (n_docs, n_vocab, n_queries)
+    return (tokens, ptr), (q_tok, q_ptr)
+
+
+def build_index(args, tokens, ptr, rank, world, local_rank):
+    """The library's own GPU index build (bm25cu_build_begin/_finish) of this rank's doc-range shard; timed, reported
+    as `index_build_s` (not part of the metric)."""
+    import torch
+
+    from bm25s_b200 import DeviceIndex
+    from bm25s_b200.sharded import ShardedIndex, shard_bounds
+
+    n_docs, avg_len, n_vocab, n_queries = shape_of(args)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if world == 1:
+        dev = DeviceIndex.build_device(tokens.data_ptr(), ptr.data_ptr(), n_docs, n_vocab, args.method, args.method,
+                                       1.5, 0.75, 0.5, device=local_rank)
+    else:
+        lo, hi = shard_bounds(n_docs, world, rank)
+        t_lo, t_hi = int(ptr[lo].item()), int(ptr[hi].item())
+        tok_l = tokens[t_lo:t_hi].contiguous()
+        ptr_l = (ptr[lo:hi + 1] - t_lo).contiguous()
+        sh = ShardedIndex.build(tok_l.data_ptr(), ptr_l.data_ptr(), n_vocab, method=args.method, rank=rank, world=world,
+                                device=local_rank, doc_lo=lo, on_device=True, n_docs_local=hi - lo,
+                                total_len_local=t_hi - t_lo)
+        dev = sh.dev
+    torch.cuda.synchronize()
+    return dev, time.perf_counter() - t0
 
 
 def peaks():
@@ -168,20 +190,30 @@ def main():
               "l2": "inputs larger than L2 (index 3.9 GB vs 126 MB L2), no flush between steps",
               "sharding": f"doc-range x{world}" if world > 1 else "single shard"}
 
-    (data, indices, indptr, nonocc), (q_tok, q_ptr), _ = build_corpus_index(args, device)
-    nnz = int(data.numel())
+    import torch.distributed as dist
+
+    if world > 1 and args.impl == "ours":
+        dist.init_process_group("nccl", device_id=device)
+    (tokens, ptr), (q_tok, q_ptr) = build_corpus(args, device)
+    dev, build_s = build_index(args, tokens, ptr, rank if args.impl == "ours" else 0, world if args.impl == "ours" else 1,
+                               local_rank)
+    del tokens, ptr
+    torch.cuda.empty_cache()
+    nnz = dev.nnz
     q_tok_h = q_tok.cpu().numpy()
     q_ptr_h = q_ptr.cpu().numpy()
     n_q_tokens = int(q_ptr_h[-1])
     shift_h = None
-    if nonocc is not None:
-        no_h = nonocc.cpu().numpy()
-        shift_h = np.array([no_h[q_tok_h[q_ptr_h[i]:q_ptr_h[i + 1]]].sum() for i in range(n_queries)], np.float32)
+    csc_host = None
+    if (args.impl == "reference") or (rank == 0 and world == 1 and not args.no_cpu_baseline) or dev.has_nonocc:
+        data_h, indices_h, indptr_h, no_h = dev.download()
+        csc_host = (data_h, indices_h, indptr_h)
+        if no_h is not None:
+            shift_h = np.array([no_h[q_tok_h[q_ptr_h[i]:q_ptr_h[i + 1]]].sum() for i in range(n_queries)], np.float32)
 
     # ------------------------------------------------------------------ reference arm: CPU port on host cores
     if args.impl == "reference":
-        csc_host = (data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy())
-        del data, indices, indptr
+        dev.close()
         torch.cuda.empty_cache()
         from oracle import c_oracle as CO
 
@@ -211,21 +243,10 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
-    import torch.distributed as dist
+    from bm25s_b200 import _lib
 
-    from bm25s_b200 import DeviceIndex, _lib
-
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    lo, hi = n_docs * rank // world, n_docs * (rank + 1) // world
-    dev = DeviceIndex.upload_device(data.data_ptr(), indices.data_ptr(), indptr.data_ptr(), nnz, n_vocab, n_docs,
-                                    nonocc_ptr=None if nonocc is None else nonocc.data_ptr(), device=local_rank,
-                                    doc_lo=lo, doc_hi=hi)
-    csc_host = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        csc_host = (data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy())
-    del data, indices, indptr
-    torch.cuda.empty_cache()
+    if not (rank == 0 and world == 1 and not args.no_cpu_baseline):
+        csc_host = None
     stream = torch.cuda.current_stream()
     dev.set_stream(stream.cuda_stream)
 
@@ -330,7 +351,7 @@ def main():
                     "api": "bm25cu_retrieve (host numpy arrays in/out)" if world == 1 else "pinned H2D + retrieve_device + all_gather + merge + D2H"},
             "gpu_launches": int(sum(s["launches"] for s in stats_acc)),
             "roofline": roofline,
-            "n_general": int(stats_acc[-1]["n_general"]), "nnz": nnz}
+            "n_general": int(stats_acc[-1]["n_general"]), "nnz_local": int(nnz), "index_build_s": round(build_s, 3)}
 
     if rank == 0 and csc_host is not None:
         cb, (n_s, ref_ids, ref_sc) = cpu_baseline(csc_host, q_tok_h, q_ptr_h, n_docs, k, shift_h, args.cpu_seconds)
