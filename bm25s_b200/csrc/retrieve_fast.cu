@@ -2,26 +2,39 @@
 //
 // Replaces, per query, BM25._compute_relevance_from_scores (bm25s/__init__.py:312-318), the BM25L/BM25+ shift
 // (bm25s/__init__.py:616-618) and selection.topk (bm25s/selection.py:14-37) without ever materialising a
-// num_docs vector. Persistent CTAs (one per SM by default) pull queries from a device-side queue. For a query the
-// document range is walked in *windows*; a window's postings of every query token are streamed from HBM into a
-// double-buffered shared-memory stage by 1-D bulk async copies (cp.async.bulk + mbarrier: the TMA engine).
+// num_docs vector. Persistent CTAs (one per SM) pull queries from a device-side queue. For a query the document
+// range is walked in *windows*; a window's postings of every query token are streamed from HBM into a
+// double-buffered shared-memory pool by 1-D bulk async copies (cp.async.bulk + mbarrier: the TMA engine).
 //
 // Warp specialisation: warp 0 is the PRODUCER - it waits for a stage to land, derives the window (first staged
-// document, coverage end of truncated tokens, postings per token inside the window), publishes that metadata,
-// advances the per-token cursors and issues the bulk copies of the following window as soon as the consumers have
-// released the other stage buffer. All other warps are CONSUMERS and only see ready windows.
+// document, coverage end of truncated tokens, postings per token inside the window, the slice of every consumer
+// warp), publishes that metadata, advances the per-token cursors and issues the bulk copies of the following window as
+// soon as the consumers have released the other stage. All other warps are CONSUMERS and only see ready windows.
 //
 // Exactness (bit-identical float32 scores): a document hit by ONE query token scores exactly that posting's value
-// (0 + s = s), so no accumulator is needed for it. Ownership of a document inside a window is resolved through a
-// one-byte tag per document in shared memory (P1: write tag = token slot; P2: losers mark 0x80|slot; P3: owners of
-// unmarked tags score directly, the surviving marker takes charge of the contested document). Documents hit by >= 2
-// tokens ("contested", a few percent) are re-summed in the reference's order - token by token in query order - from
-// binary searches of the staged window postings (P4). Candidates above the running k-th best score go to a
-// shared-memory candidate buffer of (score, ~doc) keys which is cut back to k by a bitonic sort; that key order also
-// makes ties deterministic (lower doc id first), independent of the tiling.
+// (0 + s = s), so no accumulator is needed for it. Ownership inside a window is resolved through one tag byte per
+// GROUP of G = 1, 2 or 4 consecutive documents (G grows when the claiming postings are sparse, which makes windows
+// G times larger): tag = [contested:1][token slot:4][valid:1][doc low bits:2].
+//   P1  every (surviving) essential posting claims its group:  tag = mine
+//   P2  essential postings that read back something else, and non-essential postings that find their own document
+//       claimed, set the contested bit
+//   P3  a posting that reads back exactly `mine` is the only hit of its document: score = s. A contested winner, or
+//       a posting whose document has no winner (another document of the group won), goes to the slow list
+//   P4  slow list: the document is re-summed in query-token order - the reference's float32 order - from binary
+//       searches of the staged window postings of every token (one thread per document)
+//   P5  the claiming postings clean their tags (the tag array is all-clean between windows)
+//
+// Threshold pruning (exact): theta = running k-th best score. A token is NON-ESSENTIAL in a window when a document
+// containing it and every token with a smaller column maximum cannot exceed theta: only its document ids are staged
+// and its postings merely probe the tags (P2). An essential posting (d, s) is dropped in P1 when
+// s + (sum of the other tokens' column maxima) <= theta. Bounds carry a 2^-15 relative pad against float32 rounding;
+// a dropped posting can only belong to a document whose exact score is <= theta, so results equal exhaustive scoring.
+//
+// Candidates above theta go to a shared-memory buffer of (score, ~doc) keys which is cut back to k by a bitonic
+// sort; that key order also makes ties deterministic (lower doc id first), independent of tiling and sharding.
 //
 // The kernel requires non-negative finite scores (true for the five BM25 variants; checked at upload), at most
-// 64 query tokens and no weight mask; anything else is routed to the dense general kernel (general.cu).
+// 15 query tokens, k <= 2048 and no weight mask; anything else is routed to the dense general kernel (general.cu).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -41,9 +54,14 @@ namespace bm25cu {
 #define PROF_FLUSH(cond)
 #endif
 
-constexpr int kMaxTok = 32;    // token slots per query on this path (tag byte: slot, 0x80 | slot, or 0xFF = clean)
-constexpr int kMinCap = 16;    // minimum staged postings per token per window (multiple of 4)
-constexpr unsigned char kClean = 0xFF;
+constexpr int kMaxTok = 15;     // token slots per query on this path (4 bits of the tag byte)
+constexpr int kTokArr = 16;
+constexpr int kMinCap = 16;     // minimum staged postings per live token per window (multiple of 4)
+constexpr int kMaxWarps = 32;
+constexpr int kSlowSmem = 1024; // slow-list entries kept in shared memory (the rest spills to HBM)
+constexpr int kPartCap = 2048;  // floats of scratch for the partial scores of slow-list documents
+constexpr int kSegMax = 3;      // token segments of a warp's slice kept in registers (more: generic path)
+constexpr unsigned kTagValid = 4u, kTagContested = 0x80u;
 
 struct FastParams {
     const float *data;
@@ -54,15 +72,16 @@ struct FastParams {
     RetrieveArgs a;
     Ctrl *ctrl;
     unsigned int *general_list;
-    int tagcap;    // bytes of tag array == max doc span of a window
-    int stagecap;  // postings per stage buffer
+    int tagcap;    // bytes of the tag array; a window spans at most tagcap * G documents
+    int poolcap;   // 4-byte slots per stage buffer (doc ids, and scores of the essential tokens)
     int cbcap;     // candidate entries (power of two, >= 2 * next_pow2(k))
-    int rcap;      // contested-doc list entries
-    int partcap;   // floats of scratch for the contested-document partial scores
     unsigned long long *spill;  // per-CTA global overflow of the candidate buffer
     int spillcap;
+    int2 *rspill;  // per-CTA global overflow of the slow list
+    int rspillcap;
     int route_all_general;
-    int prune;     // 0: every token is "essential" (no threshold pruning), 1: essential / non-essential split
+    int prune;     // 0: every token is essential and nothing is dropped (exhaustive), 1: threshold pruning
+    int max_shift; // largest log2(G)
 };
 
 // ---------------------------------------------------------------- PTX wrappers (mbarrier + bulk async copy)
@@ -100,29 +119,30 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 
 // ---------------------------------------------------------------- shared-memory layout
 struct SmemHdr {
-    uint64_t bar_data[2];   // stage b landed            (producer waits)
-    uint64_t bar_meta[2];   // window metadata of stage b published (consumers wait)
-    uint64_t bar_free[2];   // consumers are done with stage b      (producer waits)
-    long long t_cur[kMaxTok];
-    long long t_end[kMaxTok];
-    long long w_goff[2][kMaxTok];  // global posting index of the token's first posting in the window
-    int t_cap[kMaxTok];
-    int t_off[kMaxTok];       // element offset of the token's region inside a stage buffer
-    float t_max[kMaxTok];     // largest score of the token's column
-    float t_rest[kMaxTok];    // upper bound of what the OTHER query tokens can add to a document
-    float t_nebound[kMaxTok]; // upper bound of a document hit only by this token and tokens with smaller maxima
-    int t_skip[2][kMaxTok];   // leading elements to skip (16-byte alignment of the global source)
-    int t_n[2][kMaxTok];      // valid staged postings
-    int w_ne[2][kMaxTok];     // 1: token is non-essential in this window (scores not staged)
-    int w_cnt[2][kMaxTok];    // postings of the token inside the window of stage b
-    int w_off[2][kMaxTok];    // t_off + t_skip of stage b
-    int w_preE[2][kMaxTok], w_endE[2][kMaxTok];    // flattened index space of the essential postings
-    int w_preN[2][kMaxTok], w_endN[2][kMaxTok];    // flattened index space of the non-essential postings
-    int w_base[2];            // first document of the window
+    uint64_t bar_data[2];   // stage b landed                        (producer waits)
+    uint64_t bar_meta[2];   // window metadata of stage b published  (consumers wait)
+    uint64_t bar_free[2];   // consumers are done with stage b       (producer waits)
+    long long t_cur[kTokArr];
+    long long t_end[kTokArr];
+    long long t_df[kTokArr];
+    long long w_goff[2][kTokArr];  // global posting index of the token's first posting in the window
+    float t_max[kTokArr];     // largest score of the token's column
+    float t_rest[kTokArr];    // upper bound of what the OTHER query tokens can add to a document
+    float t_nebound[kTokArr]; // upper bound of a document hit only by this token and tokens with smaller maxima
+    int t_n[2][kTokArr];      // staged postings of stage b (valid elements)
+    int t_ne[2][kTokArr];     // 1: token is non-essential in stage b (scores not staged)
+    int w_cnt[2][kTokArr];    // postings of the token inside the window
+    int w_doc[2][kTokArr];    // pool slot of the first window document id
+    int w_sc[2][kTokArr];     // pool slot of the first window score (essential tokens)
+    int w_preE[2][kTokArr];   // exclusive prefix of the essential postings (flattened index space)
+    int w_preN[2][kTokArr];   // ... of the non-essential postings
+    int s_Et[2][kMaxWarps], s_Ei[2][kMaxWarps];   // first (token, index) of every consumer warp's essential slice
+    int s_Nt[2][kMaxWarps], s_Ni[2][kMaxWarps];   // ... non-essential slice
+    int w_base[2];            // first document of the window, rounded down to a multiple of G
+    int w_shift[2];           // log2(G) of the window
     int w_last[2];            // 1 if this is the query's last window
     int w_ME[2], w_MN[2];     // essential / non-essential postings in the window
-    int w_nE[2];              // essential tokens with postings in the window
-    unsigned int w_kept[2];   // essential postings that survived the upper-bound filter (consumers count)
+    unsigned int w_kept[2];   // warps with essential postings that survived the upper-bound filter
     unsigned int q_slot;
     unsigned int cb_cnt;
     unsigned int r_cnt;
@@ -136,42 +156,151 @@ __device__ __forceinline__ unsigned long long pack_cand(float s, int d) {
 __device__ __forceinline__ float cand_score(unsigned long long c) { return __uint_as_float((unsigned int)(c >> 32)); }
 __device__ __forceinline__ int cand_doc(unsigned long long c) { return (int)~(unsigned int)(c & 0xffffffffu); }
 
+// Explicit shared-space accesses (32-bit shared addresses): the generic-pointer path costs an address-space
+// conversion per access in these loops.
+__device__ __forceinline__ unsigned lds32(uint32_t a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float ldsf(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds8(uint32_t a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// one token's window postings as seen by a consumer warp (shared-space byte addresses, kept in registers)
+struct Seg {
+    uint32_t docs;  // address of the first document id of the segment
+    uint32_t sc;    // address of the first score (essential tokens)
+    float rest;
+    int t;
+    int n;          // postings of this segment
+};
+
+// ---------------------------------------------------------------- per-segment passes (register-cached slices)
+// `tagv` is the shared address of the (virtual) tag of group 0: the tag of document d is at tagv + (d >> sh).
+// Four warp iterations are processed together: all loads of a group are issued before any tag store, and the rare
+// store paths sit behind a warp vote so that they cost nothing when no lane needs them.
+__device__ __forceinline__ unsigned tag_of(unsigned tbits, unsigned d, unsigned gmask) { return tbits | (d & gmask); }
+
+__device__ __forceinline__ void pass_claim(const Seg &g, float theta, int sh, unsigned gmask, uint32_t tagv, int lane, int j0,
+                                           unsigned long long &kept) {
+    const unsigned tbits = (unsigned)(g.t << 3) | kTagValid;
+    const int iters = (g.n + 31) >> 5;
+    uint32_t ad = g.docs + (lane << 2), as = g.sc + (lane << 2);
+    int rem = g.n - lane;  // > 32 * u  <=>  element (it + u) * 32 + lane exists
+    for (int it = 0; it < iters; it += 4, ad += 512, as += 512, rem -= 128) {
+        float sv[4];
+        unsigned d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool v = rem > 32 * u;
+            sv[u] = v ? ldsf(as + 128 * u) : -1.0f;
+            d[u] = v ? lds32(ad + 128 * u) : 0u;
+        }
+        unsigned km = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (rem > 32 * u && __fmul_ru(__fadd_ru(sv[u], g.rest), 1.00002f) > theta) {
+                sts8(tagv + (d[u] >> sh), tag_of(tbits, d[u], gmask));
+                km |= 1u << u;
+            }
+        }
+        kept |= (unsigned long long)km << (j0 + it);
+    }
+}
+
+__device__ __forceinline__ void pass_mark_e(const Seg &g, int sh, unsigned gmask, uint32_t tagv, int lane, int j0,
+                                            unsigned long long kept) {
+    const unsigned tbits = (unsigned)(g.t << 3) | kTagValid;
+    const int iters = (g.n + 31) >> 5;
+    uint32_t ad = g.docs + (lane << 2);
+    for (int it = 0; it < iters; it += 4, ad += 512) {
+        const unsigned k4 = (unsigned)(kept >> (j0 + it)) & (iters - it >= 4 ? 15u : (1u << (iters - it)) - 1u);  // this segment's iterations only
+        if (__ballot_sync(0xffffffffu, k4 != 0u) == 0u) continue;
+        unsigned d[4], x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = (k4 >> u) & 1u ? lds32(ad + 128 * u) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = (k4 >> u) & 1u ? lds8(tagv + (d[u] >> sh)) : 0u;
+        unsigned bad = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (((k4 >> u) & 1u) && x[u] != tag_of(tbits, d[u], gmask)) bad |= 1u << u;
+        if (__ballot_sync(0xffffffffu, bad != 0u)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((bad >> u) & 1u) sts8(tagv + (d[u] >> sh), x[u] | kTagContested);
+        }
+    }
+}
+
+__device__ __forceinline__ void pass_probe_n(const Seg &g, int sh, unsigned gmask, uint32_t tagv, int lane) {
+    const int iters = (g.n + 31) >> 5;
+    uint32_t ad = g.docs + (lane << 2);
+    int rem = g.n - lane;
+    for (int it = 0; it < iters; it += 4, ad += 512, rem -= 128) {
+        unsigned d[4], x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = rem > 32 * u ? lds32(ad + 128 * u) : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = rem > 32 * u ? lds8(tagv + (d[u] >> sh)) : 0u;
+        unsigned hit = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if ((x[u] & 7u) == (kTagValid | (d[u] & gmask))) hit |= 1u << u;  // invalid lanes read x = 0: never valid
+        if (__ballot_sync(0xffffffffu, hit != 0u)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((hit >> u) & 1u) sts8(tagv + (d[u] >> sh), x[u] | kTagContested);
+        }
+    }
+}
+
+__device__ __forceinline__ void pass_clean(const Seg &g, int sh, uint32_t tagv, int lane, int j0, unsigned long long kept) {
+    const int iters = (g.n + 31) >> 5;
+    uint32_t ad = g.docs + (lane << 2);
+    for (int it = 0; it < iters; it += 4, ad += 512) {
+        const unsigned k4 = (unsigned)(kept >> (j0 + it)) & (iters - it >= 4 ? 15u : (1u << (iters - it)) - 1u);  // this segment's iterations only
+        unsigned d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = (k4 >> u) & 1u ? lds32(ad + 128 * u) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if ((k4 >> u) & 1u) sts8(tagv + (d[u] >> sh), 0u);
+    }
+}
+
 template <int NT>
 struct Fast {
     static constexpr int CNT = NT - 32;  // consumer threads
     static constexpr int NW = CNT / 32;  // consumer warps
     SmemHdr *h;
     unsigned long long *cb;   // [cbcap]
-    int *rlist;               // [rcap]
-    float *part;              // [partcap]
-    int *sdocs;               // [2][stagecap]
-    float *sscores;           // [2][stagecap]
+    int2 *rlist;              // [kSlowSmem]  (doc, slot | rule << 8)
+    float *part;              // [kPartCap]
+    int *pool;                // [2][poolcap] 4-byte slots: document ids and (essential tokens) float scores
     unsigned char *tag;       // [tagcap]
     const FastParams &p;
     unsigned long long *spill;
+    int2 *rspill;
 
     __device__ Fast(const FastParams &pp, unsigned char *smem) : p(pp) {
         h = reinterpret_cast<SmemHdr *>(smem);
         size_t o = (sizeof(SmemHdr) + 15) & ~size_t(15);
         cb = reinterpret_cast<unsigned long long *>(smem + o);
         o += (size_t)p.cbcap * 8;
-        rlist = reinterpret_cast<int *>(smem + o);
-        o += (size_t)p.rcap * 4;
+        rlist = reinterpret_cast<int2 *>(smem + o);
+        o += (size_t)kSlowSmem * 8;
         part = reinterpret_cast<float *>(smem + o);
-        o += (size_t)p.partcap * 4;
+        o += (size_t)kPartCap * 4;
         o = (o + 15) & ~size_t(15);
-        sdocs = reinterpret_cast<int *>(smem + o);
-        o += (size_t)2 * p.stagecap * 4;
-        sscores = reinterpret_cast<float *>(smem + o);
-        o += (size_t)2 * p.stagecap * 4;
+        pool = reinterpret_cast<int *>(smem + o);
+        o += (size_t)2 * p.poolcap * 4;
         tag = smem + o;
         spill = p.spill + (size_t)blockIdx.x * p.spillcap;
+        rspill = p.rspill + (size_t)blockIdx.x * p.rspillcap;
     }
     static size_t fixed_smem(const FastParams &p) {
         size_t o = (sizeof(SmemHdr) + 15) & ~size_t(15);
-        o += (size_t)p.cbcap * 8 + (size_t)p.rcap * 4 + (size_t)p.partcap * 4;
+        o += (size_t)p.cbcap * 8 + (size_t)kSlowSmem * 8 + (size_t)kPartCap * 4;
         o = (o + 15) & ~size_t(15);
-        o += (size_t)4 * p.stagecap * 4;
+        o += (size_t)2 * p.poolcap * 4;
         return o;
     }
 
@@ -187,6 +316,11 @@ struct Fast {
         const unsigned long long c = pack_cand(s, d);
         if (slot < (unsigned)p.cbcap) cb[slot] = c;
         else if (slot - p.cbcap < (unsigned)p.spillcap) spill[slot - p.cbcap] = c;
+    }
+    __device__ __forceinline__ void slow_push(int d, int info) {
+        const unsigned int r = atomicAdd(&h->r_cnt, 1u);
+        if (r < (unsigned)kSlowSmem) rlist[r] = make_int2(d, info);
+        else if (r - kSlowSmem < (unsigned)p.rspillcap) rspill[r - kSlowSmem] = make_int2(d, info);
     }
 
     // bitonic sort of key[0..P) descending (P power of two, <= cbcap), shared memory
@@ -227,14 +361,14 @@ struct Fast {
                 return;
             }
             // rare: merge the spilled candidates in chunks of (cbcap - keep)
-            const float th = (keep == (unsigned)k) ? cand_score(cb[k - 1]) : 0.0f;
+            const unsigned long long th_key = (keep == (unsigned)k) ? cb[k - 1] : 0ull;  // full key: score, then lower doc id
             const unsigned int room = (unsigned)p.cbcap - keep;
             const unsigned int chunk = min(room, spilled - sp_done);
             if (id == 0) h->cb_cnt = keep;
             bsync<CONS>();
             for (unsigned int i = id; i < chunk; i += nthr) {
                 const unsigned long long c = spill[sp_done + i];
-                if (cand_score(c) > th || keep < (unsigned)k) cb[atomicAdd(&h->cb_cnt, 1u)] = c;
+                if (c > th_key) cb[atomicAdd(&h->cb_cnt, 1u)] = c;
             }
             bsync<CONS>();
             n = h->cb_cnt;
@@ -242,30 +376,73 @@ struct Fast {
         }
     }
 
-    // producer: stage the next window of every live token into buffer b. A token is non-essential when even a
-    // document containing it and every token with a smaller column maximum cannot reach the current threshold:
-    // only its document ids are staged then.
+    __device__ __forceinline__ int warp_excl_scan(int v, int &total) {
+        const int lane = threadIdx.x & 31;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        total = __shfl_sync(0xffffffffu, x, 31);
+        return x - v;
+    }
+
+    // producer: stage the next window of every live token into stage b. Pool slots are shared out in proportion to
+    // the column lengths (an essential token needs two slots per posting, a non-essential one a single slot).
     __device__ void issue_loads(int b, int T) {
         const int lane = threadIdx.x & 31;
         const float theta_p = *reinterpret_cast<volatile float *>(&h->theta);
+        long long cur = 0, rem = 0, w = 0, dfE = 0;
+        int ne = 0;
         if (lane < T) {
-            const int t = lane;
-            const long long cur = h->t_cur[t], rem = h->t_end[t] - cur;
-            const int ne = (p.prune && h->t_nebound[t] < theta_p) ? 1 : 0;
+            cur = h->t_cur[lane];
+            rem = h->t_end[lane] - cur;
+            ne = (p.prune && h->t_nebound[lane] < theta_p) ? 1 : 0;
+            if (rem > 0) {
+                w = h->t_df[lane] * (ne ? 1 : 2);
+                if (!ne) dfE = h->t_df[lane];
+            }
+        }
+        long long wsum = w;
+        int live = rem > 0 ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+            dfE += __shfl_xor_sync(0xffffffffu, dfE, o);
+            live += __shfl_xor_sync(0xffffffffu, live, o);
+        }
+        int cap = 0, slots = 0;
+        if (rem > 0) {
+            const long long freeslots = (long long)p.poolcap - (long long)live * (2 * kMinCap);
+            const long long share = (freeslots * w) / wsum;        // slots
+            cap = kMinCap + (int)((share / (ne ? 1 : 2)) & ~3ll);  // postings, multiple of 4
+            const long long want = ((rem + 3 + 3) & ~3ll);         // never stage beyond the column (+ alignment skip)
+            if (cap > want) cap = (int)want;
+            slots = cap * (ne ? 1 : 2);
+        }
+        int tot;
+        const int off = warp_excl_scan(slots, tot);
+        if (lane < T) {
             int n = 0, a = 0;
             if (rem > 0) {
                 a = (int)(cur & 3);
-                const int cap = h->t_cap[t];
                 n = (int)min((long long)(cap - a), rem);
                 const uint32_t bytes = (uint32_t)(((a + n + 3) & ~3) * 4);
                 mbar_expect_tx(&h->bar_data[b], ne ? bytes : 2 * bytes);
-                const size_t so = (size_t)b * p.stagecap + h->t_off[t];
-                bulk_g2s(sdocs + so, p.indices + (cur - a), bytes, &h->bar_data[b]);
-                if (!ne) bulk_g2s(sscores + so, p.data + (cur - a), bytes, &h->bar_data[b]);
+                int *dst = pool + (size_t)b * p.poolcap + off;
+                bulk_g2s(dst, p.indices + (cur - a), bytes, &h->bar_data[b]);
+                if (!ne) bulk_g2s(dst + cap, p.data + (cur - a), bytes, &h->bar_data[b]);
             }
-            h->t_skip[b][t] = a;
-            h->t_n[b][t] = n;
-            h->w_ne[b][t] = ne;
+            h->t_n[b][lane] = n;
+            h->t_ne[b][lane] = ne;
+            h->w_doc[b][lane] = off + a;
+            h->w_sc[b][lane] = off + cap + a;
+        }
+        // tag granularity G = 2^sh of the window: a claiming posting shares its group with G - 1 neighbours, each
+        // claimed with the density of the essential postings; keep (G - 1) * density <= 1/32
+        {
+            int sh = 0;
+            const long long nd = p.n_docs > 0 ? p.n_docs : 1;
+            while (sh < p.max_shift && ((long long)((2 << sh) - 1) * dfE * 32 <= nd)) ++sh;
+            if (lane == 0) h->w_shift[b] = sh;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&h->bar_data[b]);
@@ -290,15 +467,6 @@ struct Fast {
         return lo + __popc(__ballot_sync(0xffffffffu, pr));
     }
 
-    __device__ __forceinline__ int warp_excl_scan(int v, int &total) {
-        const int lane = threadIdx.x & 31;
-        int x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        total = __shfl_sync(0xffffffffu, x, 31);
-        return x - v;
-    }
-
     // ------------------------------------------------------------------------------------------ producer warp
     __device__ void producer(int T, uint32_t &ph_data0, uint32_t &ph_data1, uint32_t &ph_free0, uint32_t &ph_free1) {
         const int lane = threadIdx.x & 31;
@@ -307,18 +475,18 @@ struct Fast {
         for (;;) {
             if (b == 0) { mbar_wait(&h->bar_data[0], ph_data0); ph_data0 ^= 1; }
             else { mbar_wait(&h->bar_data[1], ph_data1); ph_data1 ^= 1; }
-            const int *bd = sdocs + (size_t)b * p.stagecap;
+            const int *bp = pool + (size_t)b * p.poolcap;
             int n0 = 0, off0 = 0, first = 0x7fffffff, e = 0x7fffffff, last0 = -1, ne = 0;
             long long cur = 0, tend = 0;
             if (lane < T) {
                 n0 = h->t_n[b][lane];
-                off0 = h->t_off[lane] + h->t_skip[b][lane];
-                ne = h->w_ne[b][lane];
+                off0 = h->w_doc[b][lane];
+                ne = h->t_ne[b][lane];
                 cur = h->t_cur[lane];
                 tend = h->t_end[lane];
                 if (n0 > 0) {
-                    first = bd[off0];
-                    last0 = bd[off0 + n0 - 1];
+                    first = bp[off0];
+                    last0 = bp[off0 + n0 - 1];
                     if (cur + n0 < tend) e = last0 + 1;
                 }
             }
@@ -327,8 +495,10 @@ struct Fast {
                 first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
                 e = min(e, __shfl_xor_sync(0xffffffffu, e, o));
             }
-            const int base = first;
-            const int cap_end = (base > 0x7fffffff - p.tagcap) ? 0x7fffffff : base + p.tagcap;
+            const int sh = h->w_shift[b];
+            const int base = first & ~((1 << sh) - 1);
+            const long long span = (long long)p.tagcap << sh;
+            const int cap_end = ((long long)base + span > 0x7fffffffll) ? 0x7fffffff : (int)(base + span);
             const int wend = min(e, cap_end);
             int c0 = (n0 > 0 && last0 < wend) ? n0 : 0;
             // tokens whose staged postings reach beyond the window end need a search (rare)
@@ -337,22 +507,18 @@ struct Fast {
                 const int src = __ffs(need0) - 1;
                 need0 &= need0 - 1;
                 const int so = __shfl_sync(0xffffffffu, off0, src), sn = __shfl_sync(0xffffffffu, n0, src);
-                const int c = warp_count_below(bd + so, sn, wend);
+                const int c = warp_count_below(bp + so, sn, wend);
                 if (lane == src) c0 = c;
             }
             int ME, MN;
             const int wE = ne ? 0 : c0, wN = ne ? c0 : 0;
             const int preE = warp_excl_scan(wE, ME), preN = warp_excl_scan(wN, MN);
-            const int nE = __popc(__ballot_sync(0xffffffffu, wE > 0));
             bool more = false;
             if (lane < T) {
                 h->w_cnt[b][lane] = c0;
-                h->w_off[b][lane] = off0;
                 h->w_goff[b][lane] = cur;
                 h->w_preE[b][lane] = preE;
-                h->w_endE[b][lane] = preE + wE;
                 h->w_preN[b][lane] = preN;
-                h->w_endN[b][lane] = preN + wN;
                 h->t_cur[lane] = cur + c0;
                 more = (cur + c0) < tend;
             }
@@ -362,8 +528,25 @@ struct Fast {
                 h->w_last[b] = any_more ? 0 : 1;
                 h->w_ME[b] = ME;
                 h->w_MN[b] = MN;
-                h->w_nE[b] = nE;
                 h->w_kept[b] = 0;
+            }
+            __syncwarp();
+            // slice of consumer warp `lane`: first (token, index) of its share of both flattened index spaces
+            if (lane < NW) {
+                const int eLo = (int)((unsigned)ME * (unsigned)lane / (unsigned)NW);
+                const int nLo = (int)((unsigned)MN * (unsigned)lane / (unsigned)NW);
+                int te = 0, tn = 0;
+                for (int t = 0; t < T; ++t) {
+                    const int c = h->w_cnt[b][t];
+                    if (c > 0) {
+                        if (!h->t_ne[b][t]) { if (h->w_preE[b][t] <= eLo) te = t; }
+                        else { if (h->w_preN[b][t] <= nLo) tn = t; }
+                    }
+                }
+                h->s_Et[b][lane] = te;
+                h->s_Ei[b][lane] = eLo - h->w_preE[b][te];
+                h->s_Nt[b][lane] = tn;
+                h->s_Ni[b][lane] = nLo - h->w_preN[b][tn];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&h->bar_meta[b]);  // release: metadata visible to the consumers
@@ -389,22 +572,101 @@ struct Fast {
         }
     }
 
-    // Visit the flattened positions [lo, hi) of one index space (pre/end per token slot) with the whole warp:
-    // body(t, f, j) is called by the lane that owns position f; `off[t] - pre[t] + f` is the staged element.
-    // j counts the warp's iterations (one bit of the per-thread masks), identical on every replay.
+    // Visit `count` consecutive positions of one flattened index space with the whole warp, starting at element i0 of
+    // token t0 (generic path for slices that span more than kSegMax tokens). `ne_sel` selects the space. body(seg, i, j)
+    // is called by the lane that owns element i of the segment; j counts the warp's iterations (one bit of the
+    // per-thread masks) exactly as the register-cached passes do.
     template <typename Body>
-    __device__ __forceinline__ void for_range(const int *pre, const int *end, int lo, int hi, Body body) {
+    __device__ __forceinline__ void for_slice(int b, int ne_sel, int t0, int i0, int count, Body body) {
         const int lane = threadIdx.x & 31;
-        int t = 0, j = 0, f = lo;
-        while (f < hi) {
-            while (f >= end[t]) ++t;  // warp-uniform
-            const int seg_hi = min(end[t], hi);
-            const int pre_t = pre[t];
-            for (; f < seg_hi; f += 32, ++j) {
-                const int ff = f + lane;
-                if (ff < seg_hi) body(t, ff - pre_t, j);
+        const uint32_t pool_s = smem_u32(pool + (size_t)b * p.poolcap);
+        int t = t0, i = i0, j = 0;
+        while (count > 0) {
+            const int seg = min(count, h->w_cnt[b][t] - i);
+            Seg sg;
+            sg.docs = pool_s + 4u * (unsigned)(h->w_doc[b][t] + i);
+            sg.sc = pool_s + 4u * (unsigned)(h->w_sc[b][t] + i);
+            sg.rest = h->t_rest[t];
+            sg.t = t;
+            sg.n = seg;
+            const int iters = (seg + 31) >> 5;
+            for (int it = 0; it < iters; ++it, ++j) {
+                const int q = (it << 5) + lane;
+                if (q < seg) body(sg, q, j);
             }
-            f = seg_hi;
+            count -= seg;
+            i = 0;
+            if (count > 0) {
+                do { ++t; } while (h->t_ne[b][t] != ne_sel || h->w_cnt[b][t] == 0);
+            }
+        }
+    }
+
+    // Collect the (at most kSegMax) token segments of a warp's slice into registers. Returns false when the slice
+    // spans more tokens (many-token queries): the caller then uses the generic for_slice path.
+    __device__ __forceinline__ bool gather_segs(int b, int ne_sel, int t0, int i0, int count, Seg (&sg)[kSegMax]) {
+        const uint32_t pool_s = smem_u32(pool + (size_t)b * p.poolcap);
+        int t = t0, i = i0;
+#pragma unroll
+        for (int s = 0; s < kSegMax; ++s) {
+            sg[s].n = 0;
+            sg[s].docs = pool_s;
+            sg[s].sc = pool_s;
+            sg[s].rest = 0.0f;
+            sg[s].t = 0;
+            if (count > 0) {
+                const int seg = min(count, h->w_cnt[b][t] - i);
+                sg[s].docs = pool_s + 4u * (unsigned)(h->w_doc[b][t] + i);
+                sg[s].sc = pool_s + 4u * (unsigned)(h->w_sc[b][t] + i);
+                sg[s].rest = h->t_rest[t];
+                sg[s].t = t;
+                sg[s].n = seg;
+                count -= seg;
+                i = 0;
+                if (count > 0) {
+                    do { ++t; } while (h->t_ne[b][t] != ne_sel || h->w_cnt[b][t] == 0);
+                }
+            }
+        }
+        return count == 0;
+    }
+
+    // P3 on one register-cached segment: sole hits score directly; contested winners and documents without a winner
+    // go to the slow list.
+    __device__ __forceinline__ void pass_resolve(const Seg &g, float theta, int sh, unsigned gmask, uint32_t tagv, int lane,
+                                                 int j0, unsigned long long kept) {
+        const unsigned tbits = (unsigned)(g.t << 3) | kTagValid;
+        const int iters = (g.n + 31) >> 5;
+        uint32_t ad = g.docs + (lane << 2), as = g.sc + (lane << 2);
+        for (int it = 0; it < iters; it += 4, ad += 512, as += 512) {
+            const unsigned k4 = (unsigned)(kept >> (j0 + it)) & (iters - it >= 4 ? 15u : (1u << (iters - it)) - 1u);  // this segment's iterations only
+            if (__ballot_sync(0xffffffffu, k4 != 0u) == 0u) continue;
+            unsigned d[4], x[4];
+            float sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                d[u] = (k4 >> u) & 1u ? lds32(ad + 128 * u) : 0u;
+                sv[u] = (k4 >> u) & 1u ? ldsf(as + 128 * u) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = (k4 >> u) & 1u ? lds8(tagv + (d[u] >> sh)) : 0u;
+            unsigned act = 0;  // lanes with something to do: a sole hit above theta, or a slow-list entry
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!((k4 >> u) & 1u)) continue;
+                const unsigned mine = tag_of(tbits, d[u], gmask);
+                if (x[u] == mine ? (sv[u] > theta) : ((x[u] & 0x7Fu) == mine || ((x[u] ^ mine) & gmask) != 0u)) act |= 1u << u;
+            }
+            if (__ballot_sync(0xffffffffu, act != 0u)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!((act >> u) & 1u)) continue;
+                    const unsigned mine = tag_of(tbits, d[u], gmask);
+                    if (x[u] == mine) emit(sv[u], (int)d[u]);
+                    else if ((x[u] & 0x7Fu) == mine) slow_push((int)d[u], g.t);   // contested winner: resolves its document
+                    else slow_push((int)d[u], g.t | (1 << 8));                    // another document won the group (rule 1)
+                }
+            }
         }
     }
 
@@ -423,12 +685,13 @@ struct Fast {
             else { mbar_wait(&h->bar_meta[1], ph_meta1); ph_meta1 ^= 1; }
             PROF(1);
             PROF_CNT(16, 1);
-            const int *bd = sdocs + (size_t)b * p.stagecap;
-            const float *bs = sscores + (size_t)b * p.stagecap;
-            const int base = h->w_base[b];
+            const int *bp = pool + (size_t)b * p.poolcap;
+            const float *bpf = reinterpret_cast<const float *>(bp);
+            const uint32_t pool_s = smem_u32(bp);
+            const int sh = h->w_shift[b];
+            const unsigned gmask = (1u << sh) - 1u;
+            const uint32_t tagv = smem_u32(tag) - (uint32_t)(h->w_base[b] >> sh);  // tag of document d: tagv + (d >> sh)
             const int last = h->w_last[b];
-            const int *wcnt = h->w_cnt[b];
-            const int *woff = h->w_off[b];
             const int ME = h->w_ME[b], MN = h->w_MN[b];
 
             if (first_window) {
@@ -437,11 +700,14 @@ struct Fast {
                 // below it cannot be in the top-k. Avoids flooding the candidate buffer while theta is still 0.
                 first_window = false;
                 int best_t = 0, best_c = 0;
-                for (int t = 0; t < T; ++t) { const int c = wcnt[t]; if (c > best_c) { best_c = c; best_t = t; } }
+                for (int t = 0; t < T; ++t) {
+                    const int c = h->t_ne[b][t] ? 0 : h->w_cnt[b][t];
+                    if (c > best_c) { best_c = c; best_t = t; }
+                }
                 const int m = min(best_c, p.cbcap);
                 if (m >= k) {
                     const int P = next_pow2(m);
-                    const float *sc = bs + woff[best_t];
+                    const float *sc = bpf + h->w_sc[b][best_t];
                     for (int i = ctid; i < P; i += CNT) cb[i] = (i < m) ? ((unsigned long long)__float_as_uint(sc[i]) << 32) : 0ull;
                     sort_desc<true>(cb, P, ctid, CNT);
                     const unsigned int bits = (unsigned int)(cb[k - 1] >> 32);
@@ -450,127 +716,175 @@ struct Fast {
                     if (ctid == 0) h->theta = theta;
                 }
             }
-
             PROF(2);
             PROF_CNT(17, ME); PROF_CNT(18, MN);
-            // this warp's slice of the two flattened index spaces (32-bit: postings per window * warps < 2^31)
+
+            // this warp's slices of the two flattened index spaces, cached as token segments in registers
             const int eLo = (int)((unsigned)ME * (unsigned)cw / (unsigned)NW), eHi = (int)((unsigned)ME * (unsigned)(cw + 1) / (unsigned)NW);
             const int nLo = (int)((unsigned)MN * (unsigned)cw / (unsigned)NW), nHi = (int)((unsigned)MN * (unsigned)(cw + 1) / (unsigned)NW);
-            const int *preE = h->w_preE[b], *endE = h->w_endE[b], *preN = h->w_preN[b], *endN = h->w_endN[b];
-            unsigned long long keptE = 0ull, hitN = 0ull;
+            const int eN = eHi - eLo, nN = nHi - nLo;
+            const int eT0 = h->s_Et[b][cw], eI0 = h->s_Ei[b][cw], nT0 = h->s_Nt[b][cw], nI0 = h->s_Ni[b][cw];
+            Seg se[kSegMax], sn[kSegMax];
+            const bool fastE = gather_segs(b, 0, eT0, eI0, eN, se);
+            const bool fastN = gather_segs(b, 1, nT0, nI0, nN, sn);
+            unsigned long long keptE = 0ull;
 
-            // ---- P1: essential postings that can still reach the threshold claim their document's tag byte.
-            //      A posting (d, s) of token t is dropped when s + (sum of the other tokens' column maxima) <= theta:
-            //      no document containing it can enter the top-k.
-            for_range(preE, endE, eLo, eHi, [&](int t, int i, int j) {
-                const int o = woff[t] + i;
-                const float s = bs[o];
-                const float ub = __fmul_ru(__fadd_ru(s, h->t_rest[t]), 1.00002f);
-                if (ub > theta) {
-                    tag[bd[o] - base] = (unsigned char)t;
-                    keptE |= 1ull << j;
-                }
-            });
-            {
-                int kc = __popcll(keptE);
+            // ---- P1: essential postings that can still reach the threshold claim their document's group
+            if (fastE) {
+                int j0 = 0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) kc += __shfl_xor_sync(0xffffffffu, kc, o);
-                if (lane == 0 && kc > 0) atomicAdd(&h->w_kept[b], (unsigned)kc);
+                for (int s2 = 0; s2 < kSegMax; ++s2) {
+                    if (se[s2].n > 0) {
+                        pass_claim(se[s2], theta, sh, gmask, tagv, lane, j0, keptE);
+                        j0 += (se[s2].n + 31) >> 5;
+                    }
+                }
+            } else {
+                for_slice(b, 0, eT0, eI0, eN, [&](const Seg &sg, int i, int j) {
+                    const float s = ldsf(sg.sc + 4u * i);
+                    const float ub = __fmul_ru(__fadd_ru(s, sg.rest), 1.00002f);
+                    if (ub > theta) {
+                        const unsigned d = lds32(sg.docs + 4u * i);
+                        sts8(tagv + (d >> sh), (unsigned)(sg.t << 3) | kTagValid | (d & gmask));
+                        keptE |= 1ull << j;
+                    }
+                });
             }
+            // warp-uniform: some lane of this warp kept a posting (the passes below use warp votes)
+            const bool warp_kept = __ballot_sync(0xffffffffu, keptE != 0ull) != 0u;
+            if (lane == 0 && warp_kept) atomicAdd(&h->w_kept[b], 1u);
             PROF(3);
             bsync<true>();
             PROF(4);
-            const bool active = h->w_kept[b] > 0;
-            PROF_CNT(19, active ? 1 : 0); PROF_CNT(20, h->w_kept[b]);  // no surviving essential posting: nothing in this window can score
+            const bool active = h->w_kept[b] > 0;  // no surviving essential posting: nothing in this window can score
+            PROF_CNT(19, active ? 1 : 0);
             if (active) {
-                // ---- P2: essential postings that lost the claim mark the document as contested; non-essential
-                //      postings probe the tag and mark documents that some essential posting claimed
-                if (h->w_nE[b] >= 2 && keptE) {
-                    for_range(preE, endE, eLo, eHi, [&](int t, int i, int j) {
+                // ---- P2: postings that do not read back their own claim set the contested bit; non-essential postings
+                //      that find their own document claimed do the same
+                if (fastE) {
+                    int j0 = 0;
+#pragma unroll
+                    for (int s2 = 0; s2 < kSegMax; ++s2) {
+                        if (se[s2].n > 0) {
+                            if (warp_kept) pass_mark_e(se[s2], sh, gmask, tagv, lane, j0, keptE);
+                            j0 += (se[s2].n + 31) >> 5;
+                        }
+                    }
+                } else if (warp_kept) {
+                    for_slice(b, 0, eT0, eI0, eN, [&](const Seg &sg, int i, int j) {
                         if ((keptE >> j) & 1ull) {
-                            const int o = bd[woff[t] + i] - base;
-                            if (tag[o] != (unsigned char)t) tag[o] = (unsigned char)(0x80 | t);
+                            const unsigned d = lds32(sg.docs + 4u * i);
+                            const unsigned x = lds8(tagv + (d >> sh));
+                            if (x != ((unsigned)(sg.t << 3) | kTagValid | (d & gmask))) sts8(tagv + (d >> sh), x | kTagContested);
                         }
                     });
                 }
-                for_range(preN, endN, nLo, nHi, [&](int t, int i, int j) {
-                    const int o = bd[woff[t] + i] - base;
-                    if (tag[o] != kClean) {
-                        tag[o] = (unsigned char)(0x80 | t);
-                        hitN |= 1ull << j;
-                    }
-                });
+                if (fastN) {
+#pragma unroll
+                    for (int s2 = 0; s2 < kSegMax; ++s2)
+                        if (sn[s2].n > 0) pass_probe_n(sn[s2], sh, gmask, tagv, lane);
+                } else {
+                    for_slice(b, 1, nT0, nI0, nN, [&](const Seg &sg, int i, int j) {
+                        const unsigned d = lds32(sg.docs + 4u * i);
+                        const unsigned x = lds8(tagv + (d >> sh));
+                        if ((x & 7u) == (kTagValid | (d & gmask))) sts8(tagv + (d >> sh), x | kTagContested);
+                    });
+                }
                 PROF(5);
                 bsync<true>();
                 PROF(6);
-                // ---- P3: uncontested owners score directly; the surviving marker owns the contested document
-                if (keptE) {
-                    for_range(preE, endE, eLo, eHi, [&](int t, int i, int j) {
-                        if ((keptE >> j) & 1ull) {
-                            const int o = woff[t] + i;
-                            const int d = bd[o];
-                            const unsigned char x = tag[d - base];
-                            if (x == (unsigned char)t) {
-                                const float s = bs[o];
-                                if (s > theta) emit(s, d);
-                            } else if (x == (unsigned char)(0x80 | t)) {
-                                const unsigned int r = atomicAdd(&h->r_cnt, 1u);
-                                if (r < (unsigned)p.rcap) rlist[r] = d;
+                // ---- P3: sole hits score directly; contested winners and documents without a winner go to the slow list
+                if (warp_kept) {
+                    if (fastE) {
+                        int j0 = 0;
+#pragma unroll
+                        for (int s2 = 0; s2 < kSegMax; ++s2) {
+                            if (se[s2].n > 0) {
+                                pass_resolve(se[s2], theta, sh, gmask, tagv, lane, j0, keptE);
+                                j0 += (se[s2].n + 31) >> 5;
                             }
                         }
-                    });
-                }
-                if (hitN) {
-                    for_range(preN, endN, nLo, nHi, [&](int t, int i, int j) {
-                        if ((hitN >> j) & 1ull) {
-                            const int d = bd[woff[t] + i];
-                            if (tag[d - base] == (unsigned char)(0x80 | t)) {
-                                const unsigned int r = atomicAdd(&h->r_cnt, 1u);
-                                if (r < (unsigned)p.rcap) rlist[r] = d;
+                    } else {
+                        for_slice(b, 0, eT0, eI0, eN, [&](const Seg &sg, int i, int j) {
+                            if ((keptE >> j) & 1ull) {
+                                const unsigned d = lds32(sg.docs + 4u * i);
+                                const unsigned x = lds8(tagv + (d >> sh));
+                                const unsigned mine = (unsigned)(sg.t << 3) | kTagValid | (d & gmask);
+                                if (x == mine) {
+                                    const float s = ldsf(sg.sc + 4u * i);
+                                    if (s > theta) emit(s, (int)d);
+                                } else if ((x & 0x7Fu) == mine) {
+                                    slow_push((int)d, sg.t);
+                                } else if (((x ^ mine) & gmask) != 0u) {
+                                    slow_push((int)d, sg.t | (1 << 8));
+                                }
                             }
-                        }
-                    });
+                        });
+                    }
                 }
                 PROF(7);
                 bsync<true>();
                 PROF(8);
-                // ---- P5: the essential postings clean the tags they claimed (tags are all-clean between windows)
-                if (keptE) {
-                    for_range(preE, endE, eLo, eHi, [&](int t, int i, int j) {
-                        if ((keptE >> j) & 1ull) tag[bd[woff[t] + i] - base] = kClean;
-                    });
+                // ---- P5: the claiming postings clean their tags (tags are all-clean between windows)
+                if (warp_kept) {
+                    if (fastE) {
+                        int j0 = 0;
+#pragma unroll
+                        for (int s2 = 0; s2 < kSegMax; ++s2) {
+                            if (se[s2].n > 0) {
+                                pass_clean(se[s2], sh, tagv, lane, j0, keptE);
+                                j0 += (se[s2].n + 31) >> 5;
+                            }
+                        }
+                    } else {
+                        for_slice(b, 0, eT0, eI0, eN, [&](const Seg &sg, int i, int j) {
+                            if ((keptE >> j) & 1ull) sts8(tagv + (lds32(sg.docs + 4u * i) >> sh), 0u);
+                        });
+                    }
                 }
-                // ---- P4: contested documents are summed in query-token order (the reference's float32 order).
-                //      a) one thread per (document, token): binary search of the token's window postings
-                //      b) one thread per document: ordered sum of the partial scores found
-                const int R = min((int)h->r_cnt, p.rcap);
                 PROF(9);
+                // ---- P4: slow list. Documents are re-summed in query-token order (the reference's float32 order):
+                //      a) one thread per (document, token): binary search of the token's window postings
+                //      b) one thread per document: ordered sum; rule 1: only the essential hit with the smallest token
+                //         slot emits (several postings of the same document may be listed)
+                const int R = (int)min(h->r_cnt, (unsigned)(kSlowSmem + p.rspillcap));
                 PROF_CNT(21, R);
                 if (R > 0) {
-                    const int chunk_docs = max(1, p.partcap / T);
+                    const int chunk_docs = kPartCap / T;
                     for (int r0 = 0; r0 < R; r0 += chunk_docs) {
                         const int nd = min(chunk_docs, R - r0);
                         const int pairs = nd * T;
                         for (int jj = ctid; jj < pairs; jj += CNT) {
                             const int r = jj / T, t = jj - r * T;
-                            const int d = rlist[r0 + r];
-                            const int c = wcnt[t];
+                            const int ri = r0 + r;
+                            const int d = (ri < kSlowSmem) ? rlist[ri].x : rspill[ri - kSlowSmem].x;
+                            const int c = h->w_cnt[b][t];
                             float v = -1.0f;
                             if (c > 0) {
-                                const int *dt = bd + woff[t];
+                                const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
                                 int lo = 0, hi = c;
-                                while (lo < hi) { const int m = (lo + hi) >> 1; if (dt[m] < d) lo = m + 1; else hi = m; }
-                                if (lo < c && dt[lo] == d)
-                                    v = h->w_ne[b][t] ? p.data[h->w_goff[b][t] + lo] : bs[woff[t] + lo];
+                                while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < d) lo = m + 1; else hi = m; }
+                                if (lo < c && (int)lds32(dt + 4u * lo) == d)
+                                    v = h->t_ne[b][t] ? p.data[h->w_goff[b][t] + lo] : bpf[h->w_sc[b][t] + lo];
                             }
                             part[jj] = v;
                         }
                         bsync<true>();
                         for (int r = ctid; r < nd; r += CNT) {
+                            const int ri = r0 + r;
+                            const int2 e = (ri < kSlowSmem) ? rlist[ri] : rspill[ri - kSlowSmem];
+                            const int myslot = e.y & 0xFF, rule = e.y >> 8;
                             float sum = 0.0f;
+                            int min_e = 99;
                             const float *pv = part + r * T;
-                            for (int t = 0; t < T; ++t) { const float v = pv[t]; if (v >= 0.0f) sum = __fadd_rn(sum, v); }
-                            if (sum > theta) emit(sum, rlist[r0 + r]);
+                            for (int t = 0; t < T; ++t) {
+                                const float v = pv[t];
+                                if (v >= 0.0f) {
+                                    sum = __fadd_rn(sum, v);
+                                    if (!h->t_ne[b][t] && t < min_e) min_e = t;
+                                }
+                            }
+                            if ((rule == 0 || min_e == myslot) && sum > theta) emit(sum, e.x);
                         }
                         bsync<true>();
                     }
@@ -596,10 +910,9 @@ struct Fast {
             for (int i = 0; i < 2; ++i) { mbar_init(&h->bar_data[i], 1); mbar_init(&h->bar_meta[i], 1); mbar_init(&h->bar_free[i], 1); }
             fence_mbar_init();
         }
-        for (int i = tid * 16; i < p.tagcap; i += NT * 16) *reinterpret_cast<uint4 *>(tag + i) = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (int i = tid * 16; i < p.tagcap; i += NT * 16) *reinterpret_cast<uint4 *>(tag + i) = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         uint32_t ph_data0 = 0, ph_data1 = 0, ph_free0 = 0, ph_free1 = 0, ph_meta0 = 0, ph_meta1 = 0;
-
         PROF_DECL;
         for (;;) {
             PROF(12);
@@ -624,21 +937,17 @@ struct Fast {
                 else { beg = p.indptr[tok]; end = p.indptr[tok + 1]; mx = p.colmax[tok]; }
                 h->t_cur[tid] = beg;
                 h->t_end[tid] = end;
+                h->t_df[tid] = end - beg;
                 h->t_max[tid] = mx;
             }
             if (tid == 0) { h->cb_cnt = 0; h->theta = 0.0f; h->r_cnt = 0; }
             __syncthreads();
             if (warp == 0) {
-                // stage capacities proportional to document frequency; pruning bounds from the column maxima
-                const long long df0 = (lane < T) ? h->t_end[lane] - h->t_cur[lane] : 0;
+                // pruning bounds from the column maxima
+                const long long df0 = (lane < T) ? h->t_df[lane] : 0;
                 long long tot = df0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-                const long long freecap = (long long)p.stagecap - (long long)T * kMinCap;
-                int c0 = 0;
-                if (lane < T) c0 = kMinCap + (int)(tot > 0 ? ((freecap * df0) / tot) & ~3ll : 0);
-                int csum;
-                const int off = warp_excl_scan(c0, csum);
                 const float mx = (lane < T) ? h->t_max[lane] : 0.0f;
                 double msum = (double)mx;
 #pragma unroll
@@ -650,9 +959,7 @@ struct Fast {
                     if (j != lane && (mj < mx || (mj == mx && j < lane))) below += (double)mj;
                 }
                 if (lane < T) {
-                    h->t_cap[lane] = c0;
-                    h->t_off[lane] = off;
-                    // float32 sums of <= 32 non-negative terms exceed the exact sum by < 2^-18 relative: pad by 2^-15
+                    // float32 sums of <= 15 non-negative terms exceed the exact sum by < 2^-19 relative: pad by 2^-15
                     h->t_rest[lane] = __double2float_ru((msum - (double)mx) * 1.00003);
                     h->t_nebound[lane] = __double2float_ru(below * 1.00003);
                 }
@@ -739,30 +1046,33 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.indptr = ix->d_indptr;
     p.colmax = ix->d_colmax;
     p.prune = env_int("BM25CU_PRUNE", 1);
+    p.max_shift = env_int("BM25CU_MAXSHIFT", 2);
+    if (p.max_shift < 0) p.max_shift = 0;
+    if (p.max_shift > 2) p.max_shift = 2;
     p.n_docs = ix->n_docs;
     p.n_vocab = ix->n_vocab;
     p.doc_base = ix->doc_base;
     p.a = a;
     p.ctrl = d_ctrl;
     p.general_list = d_general_list;
-    const int threads = env_int("BM25CU_THREADS", 512);
+    int threads = env_int("BM25CU_THREADS", 512);
+    if (threads != 128 && threads != 256 && threads != 1024) threads = 512;
     const int ctas_per_sm = env_int("BM25CU_CTAS_PER_SM", 1);
     const int kcap = next_pow2(a.k < 1 ? 1 : a.k);
     const int cb_min = env_int("BM25CU_CBMIN", 512);
     p.cbcap = 2 * kcap < cb_min ? next_pow2(cb_min) : 2 * kcap;
     p.route_all_general = (!ix->nonneg) || (a.mask != nullptr) || (a.k > 2048) || env_int("BM25CU_FORCE_GENERAL", 0);
     const int budget = ix->max_smem_optin / (ctas_per_sm > 0 ? ctas_per_sm : 1) - (ctas_per_sm > 1 ? 1024 : 0);
-    int stage = env_int("BM25CU_STAGE", ctas_per_sm > 1 ? 2048 : 4096);
-    stage = (stage + 3) & ~3;
-    if (stage < kMaxTok * kMinCap + 64) stage = kMaxTok * kMinCap + 64;
-    {   // the per-thread posting masks hold 64 warp iterations: (postings per consumer warp) / 32 + kMaxTok <= 64
-        const int nw = ((threads == 64 || threads == 128 || threads == 256 || threads == 1024) ? threads : 512) / 32 - 1;
-        const int max_stage = nw * 32 * (64 - kMaxTok - 2);
-        if (stage > max_stage) stage = max_stage & ~3;
-    }
-    p.stagecap = stage;
-    p.rcap = stage / 2 + 64;
-    p.partcap = stage < 256 ? 256 : (stage > 4096 ? 4096 : stage);
+    const int nw = threads / 32 - 1;
+    // pool: 4-byte slots per stage. The per-thread posting masks hold 64 warp iterations:
+    // (postings per consumer warp) / 32 + kMaxTok + 1 <= 64, and a posting takes at least one slot.
+    int pool = env_int("BM25CU_POOL", ctas_per_sm > 1 ? 6144 : 14336);
+    pool = (pool + 3) & ~3;
+    const int min_pool = kMaxTok * 2 * kMinCap + 256;
+    if (pool < min_pool) pool = min_pool;
+    const int max_pool = nw * 32 * (64 - kMaxTok - 2);
+    if (pool > max_pool) pool = max_pool & ~3;
+    p.poolcap = pool;
     size_t fixed = Fast<512>::fixed_smem(p);
     long long tagcap = (long long)budget - (long long)fixed - 64;
     if (tagcap < 4096) {
@@ -774,18 +1084,19 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     const int tag_env = env_int("BM25CU_TAG", 0);
     if (tag_env > 0 && tag_env < tagcap) tagcap = tag_env;
     p.tagcap = (int)(tagcap & ~15ll);
-    p.spillcap = p.stagecap + p.rcap;
+    p.rspillcap = p.poolcap;
+    p.spillcap = 2 * p.poolcap;
     const int grid = ix->sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1);
-    int rc = ix->d_spill.reserve((size_t)grid * p.spillcap * 8);
+    int rc = ix->d_spill.reserve((size_t)grid * ((size_t)p.spillcap * 8 + (size_t)p.rspillcap * 8));
     if (rc) return rc;
     p.spill = ix->d_spill.as<unsigned long long>();
+    p.rspill = reinterpret_cast<int2 *>(p.spill + (size_t)grid * p.spillcap);
     const size_t smem = fixed + p.tagcap;
     cudaError_t e;
 #define BM25CU_LAUNCH(NTV)                                                                                          \
     e = cudaFuncSetAttribute(retrieve_fast_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     if (e == cudaSuccess) retrieve_fast_kernel<NTV><<<grid, NTV, smem, ix->stream>>>(p);
     switch (threads) {
-        case 64: BM25CU_LAUNCH(64); break;
         case 128: BM25CU_LAUNCH(128); break;
         case 256: BM25CU_LAUNCH(256); break;
         case 1024: BM25CU_LAUNCH(1024); break;

@@ -144,7 +144,7 @@ def test_edge_cases_small():
     data, indices, indptr = _random_csc(rng, n_docs, n_vocab, 20, with_zero=True)
     dev = DeviceIndex.upload(data, indices, indptr, n_docs)
     queries = [[], [3], [3, 3, 3], [5, 7, 5, 9, 5], list(range(80)), [int(x) for x in rng.integers(0, n_vocab, 70)],
-               [11, 12], [], [int(x) for x in rng.integers(0, n_vocab, 64)]]
+               [11, 12], [], [int(x) for x in rng.integers(0, n_vocab, 15)], [int(x) for x in rng.integers(0, n_vocab, 16)]]
     ptr = np.zeros(len(queries) + 1, np.int64)
     np.cumsum([len(q) for q in queries], out=ptr[1:])
     flat = np.array([t for q in queries for t in q], np.int32)
@@ -153,7 +153,7 @@ def test_edge_cases_small():
         assert ids.shape == (len(queries), k)
         if k == 0:
             continue
-        assert st["n_general"] == sum(len(q) > 32 for q in queries)  # queries longer than 32 tokens take the general path
+        assert st["n_general"] == sum(len(q) > 15 for q in queries)  # queries longer than 15 tokens take the general path
         rid, rsc = O.retrieve(data, indptr, indices, n_docs, queries, k)
         dense_fn = lambda qi: O.score_dense(data, indptr, indices, n_docs, queries[qi])  # noqa: E731
         check_topk_rows(ids, sc, rid, rsc, dense_fn, what=f"edge k={k}")
@@ -184,7 +184,8 @@ def test_random_corpus_vs_c_oracle(k):
     dense_fn = lambda qi: CO.scores_dense(data, indices, indptr, n_docs, queries[qi], shift=sh[qi])  # noqa: E731
     check_topk_rows(ids, sc, rid, rsc, dense_fn if k <= 100 else None, what=f"random k={k}")
     # small stage / tag settings force many windows and the same answer
-    for env in ({"BM25CU_STAGE": "2048", "BM25CU_TAG": "4096"}, {"BM25CU_THREADS": "256", "BM25CU_CTAS_PER_SM": "2"}):
+    for env in ({"BM25CU_POOL": "1024", "BM25CU_TAG": "4096"}, {"BM25CU_THREADS": "256", "BM25CU_CTAS_PER_SM": "2"},
+                {"BM25CU_MAXSHIFT": "0"}, {"BM25CU_PRUNE": "0"}, {"BM25CU_MAXSHIFT": "1", "BM25CU_TAG": "8192"}):
         old = {kk: os.environ.get(kk) for kk in env}
         os.environ.update(env)
         try:
