@@ -7,9 +7,12 @@
 // double-buffered shared-memory pool by 1-D bulk async copies (cp.async.bulk + mbarrier: the TMA engine).
 //
 // Warp specialisation: warp 0 is the PRODUCER - it waits for a stage to land, derives the window (first staged
-// document, coverage end of truncated tokens, postings per token inside the window, the slice of every consumer
-// warp), publishes that metadata, advances the per-token cursors and issues the bulk copies of the following window as
-// soon as the consumers have released the other stage. All other warps are CONSUMERS and only see ready windows.
+// document, coverage end of truncated tokens, postings per token inside the window), cuts the window's document range
+// into one sub-range per consumer warp (per-token offsets by binary search), publishes that metadata, advances the
+// per-token cursors and issues the bulk copies of the following window as soon as the consumers have released the other
+// stage. All other warps are CONSUMERS: each owns a document sub-range of the window - its postings of every token,
+// its tag bytes - and runs all passes on it with warp-level synchronisation only, so warps drift apart and hide each
+// other's latencies; the consumers meet once per window (stage release, candidate-buffer compaction).
 //
 // Exactness (bit-identical float32 scores): a document hit by ONE query token scores exactly that posting's value
 // (0 + s = s), so no accumulator is needed for it. Ownership inside a window is resolved through one tag byte per
@@ -58,9 +61,7 @@ constexpr int kMaxTok = 15;     // token slots per query on this path (4 bits of
 constexpr int kTokArr = 16;
 constexpr int kMinCap = 16;     // minimum staged postings per live token per window (multiple of 4)
 constexpr int kMaxWarps = 32;
-constexpr int kSlowSmem = 1024; // slow-list entries kept in shared memory (the rest spills to HBM)
-constexpr int kPartCap = 2048;  // floats of scratch for the partial scores of slow-list documents
-constexpr int kSegMax = 3;      // token segments of a warp's slice kept in registers (more: generic path)
+constexpr int kSegMax = 4;      // essential / non-essential token slices of a warp kept in registers (more: generic path)
 constexpr unsigned kTagValid = 4u, kTagContested = 0x80u;
 
 struct FastParams {
@@ -77,8 +78,6 @@ struct FastParams {
     int cbcap;     // candidate entries (power of two, >= 2 * next_pow2(k))
     unsigned long long *spill;  // per-CTA global overflow of the candidate buffer
     int spillcap;
-    int2 *rspill;  // per-CTA global overflow of the slow list
-    int rspillcap;
     int route_all_general;
     int prune;     // 0: every token is essential and nothing is dropped (exhaustive), 1: threshold pruning
     int max_shift; // largest log2(G)
@@ -134,10 +133,8 @@ struct SmemHdr {
     int w_cnt[2][kTokArr];    // postings of the token inside the window
     int w_doc[2][kTokArr];    // pool slot of the first window document id
     int w_sc[2][kTokArr];     // pool slot of the first window score (essential tokens)
-    int w_preE[2][kTokArr];   // exclusive prefix of the essential postings (flattened index space)
-    int w_preN[2][kTokArr];   // ... of the non-essential postings
-    int s_Et[2][kMaxWarps], s_Ei[2][kMaxWarps];   // first (token, index) of every consumer warp's essential slice
-    int s_Nt[2][kMaxWarps], s_Ni[2][kMaxWarps];   // ... non-essential slice
+    int w_off[2][kTokArr][kMaxWarps + 1];  // w_off[b][t][w]: first window posting of token t in warp w's doc sub-range
+    int2 w_slow[kMaxWarps][32];            // per-warp slow list (doc, slot | rule << 8)
     int w_base[2];            // first document of the window, rounded down to a multiple of G
     int w_shift[2];           // log2(G) of the window
     int w_last[2];            // 1 if this is the query's last window
@@ -172,56 +169,67 @@ struct Seg {
     int n;          // postings of this segment
 };
 
-// ---------------------------------------------------------------- per-segment passes (register-cached slices)
+// ---------------------------------------------------------------- per-slice passes
 // `tagv` is the shared address of the (virtual) tag of group 0: the tag of document d is at tagv + (d >> sh).
 // Four warp iterations are processed together: all loads of a group are issued before any tag store, and the rare
 // store paths sit behind a warp vote so that they cost nothing when no lane needs them.
+// A posting (d, s) of an essential token is KEPT when s + rest (the other tokens' column maxima) can exceed theta;
+// theta is constant within a window, so every pass re-derives the same predicate (`allkept`: rest alone exceeds theta).
 __device__ __forceinline__ unsigned tag_of(unsigned tbits, unsigned d, unsigned gmask) { return tbits | (d & gmask); }
+__device__ __forceinline__ bool kept_posting(float s, float rest, float theta) {
+    return __fmul_ru(__fadd_ru(s, rest), 1.00002f) > theta;
+}
 
-__device__ __forceinline__ void pass_claim(const Seg &g, float theta, int sh, unsigned gmask, uint32_t tagv, int lane, int j0,
-                                           unsigned long long &kept) {
+// P1: kept postings claim their document's group. Returns (per lane) whether anything was kept.
+__device__ __forceinline__ bool pass_claim(const Seg &g, float theta, bool allkept, int sh, unsigned gmask, uint32_t tagv,
+                                           int lane) {
     const unsigned tbits = (unsigned)(g.t << 3) | kTagValid;
     const int iters = (g.n + 31) >> 5;
     uint32_t ad = g.docs + (lane << 2), as = g.sc + (lane << 2);
     int rem = g.n - lane;  // > 32 * u  <=>  element (it + u) * 32 + lane exists
+    bool any = false;
     for (int it = 0; it < iters; it += 4, ad += 512, as += 512, rem -= 128) {
         float sv[4];
         unsigned d[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const bool v = rem > 32 * u;
-            sv[u] = v ? ldsf(as + 128 * u) : -1.0f;
+            sv[u] = (v && !allkept) ? ldsf(as + 128 * u) : 0.0f;
             d[u] = v ? lds32(ad + 128 * u) : 0u;
         }
-        unsigned km = 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (rem > 32 * u && __fmul_ru(__fadd_ru(sv[u], g.rest), 1.00002f) > theta) {
+            if (rem > 32 * u && (allkept || kept_posting(sv[u], g.rest, theta))) {
                 sts8(tagv + (d[u] >> sh), tag_of(tbits, d[u], gmask));
-                km |= 1u << u;
+                any = true;
             }
         }
-        kept |= (unsigned long long)km << (j0 + it);
     }
+    return any;
 }
 
-__device__ __forceinline__ void pass_mark_e(const Seg &g, int sh, unsigned gmask, uint32_t tagv, int lane, int j0,
-                                            unsigned long long kept) {
+// P2 (essential): kept postings that do not read back their own claim set the contested bit
+__device__ __forceinline__ void pass_mark_e(const Seg &g, float theta, bool allkept, int sh, unsigned gmask, uint32_t tagv,
+                                            int lane) {
     const unsigned tbits = (unsigned)(g.t << 3) | kTagValid;
     const int iters = (g.n + 31) >> 5;
-    uint32_t ad = g.docs + (lane << 2);
-    for (int it = 0; it < iters; it += 4, ad += 512) {
-        const unsigned k4 = (unsigned)(kept >> (j0 + it)) & (iters - it >= 4 ? 15u : (1u << (iters - it)) - 1u);  // this segment's iterations only
-        if (__ballot_sync(0xffffffffu, k4 != 0u) == 0u) continue;
+    uint32_t ad = g.docs + (lane << 2), as = g.sc + (lane << 2);
+    int rem = g.n - lane;
+    for (int it = 0; it < iters; it += 4, ad += 512, as += 512, rem -= 128) {
         unsigned d[4], x[4];
+        bool v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) d[u] = (k4 >> u) & 1u ? lds32(ad + 128 * u) : 0u;
+        for (int u = 0; u < 4; ++u) {
+            v[u] = rem > 32 * u;
+            if (v[u] && !allkept) v[u] = kept_posting(ldsf(as + 128 * u), g.rest, theta);
+            d[u] = v[u] ? lds32(ad + 128 * u) : 0u;
+        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = (k4 >> u) & 1u ? lds8(tagv + (d[u] >> sh)) : 0u;
+        for (int u = 0; u < 4; ++u) x[u] = v[u] ? lds8(tagv + (d[u] >> sh)) : 0u;
         unsigned bad = 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (((k4 >> u) & 1u) && x[u] != tag_of(tbits, d[u], gmask)) bad |= 1u << u;
+            if (v[u] && x[u] != tag_of(tbits, d[u], gmask)) bad |= 1u << u;
         if (__ballot_sync(0xffffffffu, bad != 0u)) {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -230,6 +238,7 @@ __device__ __forceinline__ void pass_mark_e(const Seg &g, int sh, unsigned gmask
     }
 }
 
+// P2 (non-essential): postings that find their own document claimed set the contested bit
 __device__ __forceinline__ void pass_probe_n(const Seg &g, int sh, unsigned gmask, uint32_t tagv, int lane) {
     const int iters = (g.n + 31) >> 5;
     uint32_t ad = g.docs + (lane << 2);
@@ -252,17 +261,23 @@ __device__ __forceinline__ void pass_probe_n(const Seg &g, int sh, unsigned gmas
     }
 }
 
-__device__ __forceinline__ void pass_clean(const Seg &g, int sh, uint32_t tagv, int lane, int j0, unsigned long long kept) {
+// P5: kept postings clean the tags they (or a posting of the same group) claimed
+__device__ __forceinline__ void pass_clean(const Seg &g, float theta, bool allkept, int sh, uint32_t tagv, int lane) {
     const int iters = (g.n + 31) >> 5;
-    uint32_t ad = g.docs + (lane << 2);
-    for (int it = 0; it < iters; it += 4, ad += 512) {
-        const unsigned k4 = (unsigned)(kept >> (j0 + it)) & (iters - it >= 4 ? 15u : (1u << (iters - it)) - 1u);  // this segment's iterations only
+    uint32_t ad = g.docs + (lane << 2), as = g.sc + (lane << 2);
+    int rem = g.n - lane;
+    for (int it = 0; it < iters; it += 4, ad += 512, as += 512, rem -= 128) {
         unsigned d[4];
+        bool v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) d[u] = (k4 >> u) & 1u ? lds32(ad + 128 * u) : 0u;
+        for (int u = 0; u < 4; ++u) {
+            v[u] = rem > 32 * u;
+            if (v[u] && !allkept) v[u] = kept_posting(ldsf(as + 128 * u), g.rest, theta);
+            d[u] = v[u] ? lds32(ad + 128 * u) : 0u;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if ((k4 >> u) & 1u) sts8(tagv + (d[u] >> sh), 0u);
+            if (v[u]) sts8(tagv + (d[u] >> sh), 0u);
     }
 }
 
@@ -272,33 +287,25 @@ struct Fast {
     static constexpr int NW = CNT / 32;  // consumer warps
     SmemHdr *h;
     unsigned long long *cb;   // [cbcap]
-    int2 *rlist;              // [kSlowSmem]  (doc, slot | rule << 8)
-    float *part;              // [kPartCap]
     int *pool;                // [2][poolcap] 4-byte slots: document ids and (essential tokens) float scores
     unsigned char *tag;       // [tagcap]
     const FastParams &p;
     unsigned long long *spill;
-    int2 *rspill;
 
     __device__ Fast(const FastParams &pp, unsigned char *smem) : p(pp) {
         h = reinterpret_cast<SmemHdr *>(smem);
         size_t o = (sizeof(SmemHdr) + 15) & ~size_t(15);
         cb = reinterpret_cast<unsigned long long *>(smem + o);
         o += (size_t)p.cbcap * 8;
-        rlist = reinterpret_cast<int2 *>(smem + o);
-        o += (size_t)kSlowSmem * 8;
-        part = reinterpret_cast<float *>(smem + o);
-        o += (size_t)kPartCap * 4;
         o = (o + 15) & ~size_t(15);
         pool = reinterpret_cast<int *>(smem + o);
         o += (size_t)2 * p.poolcap * 4;
         tag = smem + o;
         spill = p.spill + (size_t)blockIdx.x * p.spillcap;
-        rspill = p.rspill + (size_t)blockIdx.x * p.rspillcap;
     }
     static size_t fixed_smem(const FastParams &p) {
         size_t o = (sizeof(SmemHdr) + 15) & ~size_t(15);
-        o += (size_t)p.cbcap * 8 + (size_t)kSlowSmem * 8 + (size_t)kPartCap * 4;
+        o += (size_t)p.cbcap * 8;
         o = (o + 15) & ~size_t(15);
         o += (size_t)2 * p.poolcap * 4;
         return o;
@@ -316,11 +323,6 @@ struct Fast {
         const unsigned long long c = pack_cand(s, d);
         if (slot < (unsigned)p.cbcap) cb[slot] = c;
         else if (slot - p.cbcap < (unsigned)p.spillcap) spill[slot - p.cbcap] = c;
-    }
-    __device__ __forceinline__ void slow_push(int d, int info) {
-        const unsigned int r = atomicAdd(&h->r_cnt, 1u);
-        if (r < (unsigned)kSlowSmem) rlist[r] = make_int2(d, info);
-        else if (r - kSlowSmem < (unsigned)p.rspillcap) rspill[r - kSlowSmem] = make_int2(d, info);
     }
 
     // bitonic sort of key[0..P) descending (P power of two, <= cbcap), shared memory
@@ -476,6 +478,7 @@ struct Fast {
             if (b == 0) { mbar_wait(&h->bar_data[0], ph_data0); ph_data0 ^= 1; }
             else { mbar_wait(&h->bar_data[1], ph_data1); ph_data1 ^= 1; }
             const int *bp = pool + (size_t)b * p.poolcap;
+            const uint32_t pool_s = smem_u32(bp);
             int n0 = 0, off0 = 0, first = 0x7fffffff, e = 0x7fffffff, last0 = -1, ne = 0;
             long long cur = 0, tend = 0;
             if (lane < T) {
@@ -490,16 +493,19 @@ struct Fast {
                     if (cur + n0 < tend) e = last0 + 1;
                 }
             }
+            int lastmax = last0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
                 e = min(e, __shfl_xor_sync(0xffffffffu, e, o));
+                lastmax = max(lastmax, __shfl_xor_sync(0xffffffffu, lastmax, o));
             }
             const int sh = h->w_shift[b];
             const int base = first & ~((1 << sh) - 1);
             const long long span = (long long)p.tagcap << sh;
             const int cap_end = ((long long)base + span > 0x7fffffffll) ? 0x7fffffff : (int)(base + span);
-            const int wend = min(e, cap_end);
+            int wend = min(e, cap_end);
+            if (lastmax < wend - 1) wend = lastmax + 1;  // tight end: the sub-ranges below split real documents only
             int c0 = (n0 > 0 && last0 < wend) ? n0 : 0;
             // tokens whose staged postings reach beyond the window end need a search (rare)
             unsigned int need0 = __ballot_sync(0xffffffffu, n0 > 0 && last0 >= wend);
@@ -511,14 +517,12 @@ struct Fast {
                 if (lane == src) c0 = c;
             }
             int ME, MN;
-            const int wE = ne ? 0 : c0, wN = ne ? c0 : 0;
-            const int preE = warp_excl_scan(wE, ME), preN = warp_excl_scan(wN, MN);
+            (void)warp_excl_scan(ne ? 0 : c0, ME);
+            (void)warp_excl_scan(ne ? c0 : 0, MN);
             bool more = false;
             if (lane < T) {
                 h->w_cnt[b][lane] = c0;
                 h->w_goff[b][lane] = cur;
-                h->w_preE[b][lane] = preE;
-                h->w_preN[b][lane] = preN;
                 h->t_cur[lane] = cur + c0;
                 more = (cur + c0) < tend;
             }
@@ -528,25 +532,22 @@ struct Fast {
                 h->w_last[b] = any_more ? 0 : 1;
                 h->w_ME[b] = ME;
                 h->w_MN[b] = MN;
-                h->w_kept[b] = 0;
             }
             __syncwarp();
-            // slice of consumer warp `lane`: first (token, index) of its share of both flattened index spaces
-            if (lane < NW) {
-                const int eLo = (int)((unsigned)ME * (unsigned)lane / (unsigned)NW);
-                const int nLo = (int)((unsigned)MN * (unsigned)lane / (unsigned)NW);
-                int te = 0, tn = 0;
+            // document sub-range of consumer warp w: [bnd(w), bnd(w + 1)), boundaries on multiples of G. Lane w finds,
+            // for every token, the first window posting at or after bnd(w).
+            if (lane <= NW) {
+                const long long wspan = (long long)wend - base;
+                int bnd = (lane == NW) ? wend : (int)(base + (((wspan * lane) / NW) & ~(long long)((1 << sh) - 1)));
                 for (int t = 0; t < T; ++t) {
                     const int c = h->w_cnt[b][t];
-                    if (c > 0) {
-                        if (!h->t_ne[b][t]) { if (h->w_preE[b][t] <= eLo) te = t; }
-                        else { if (h->w_preN[b][t] <= nLo) tn = t; }
-                    }
+                    const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
+                    int lo = 0, hi = c;
+                    if (lane == 0) hi = 0;
+                    else if (lane == NW) lo = c;
+                    while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < bnd) lo = m + 1; else hi = m; }
+                    h->w_off[b][t][lane] = lo;
                 }
-                h->s_Et[b][lane] = te;
-                h->s_Ei[b][lane] = eLo - h->w_preE[b][te];
-                h->s_Nt[b][lane] = tn;
-                h->s_Ni[b][lane] = nLo - h->w_preN[b][tn];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&h->bar_meta[b]);  // release: metadata visible to the consumers
@@ -572,102 +573,95 @@ struct Fast {
         }
     }
 
-    // Visit `count` consecutive positions of one flattened index space with the whole warp, starting at element i0 of
-    // token t0 (generic path for slices that span more than kSegMax tokens). `ne_sel` selects the space. body(seg, i, j)
-    // is called by the lane that owns element i of the segment; j counts the warp's iterations (one bit of the
-    // per-thread masks) exactly as the register-cached passes do.
-    template <typename Body>
-    __device__ __forceinline__ void for_slice(int b, int ne_sel, int t0, int i0, int count, Body body) {
-        const int lane = threadIdx.x & 31;
-        const uint32_t pool_s = smem_u32(pool + (size_t)b * p.poolcap);
-        int t = t0, i = i0, j = 0;
-        while (count > 0) {
-            const int seg = min(count, h->w_cnt[b][t] - i);
-            Seg sg;
-            sg.docs = pool_s + 4u * (unsigned)(h->w_doc[b][t] + i);
-            sg.sc = pool_s + 4u * (unsigned)(h->w_sc[b][t] + i);
-            sg.rest = h->t_rest[t];
-            sg.t = t;
-            sg.n = seg;
-            const int iters = (seg + 31) >> 5;
-            for (int it = 0; it < iters; ++it, ++j) {
-                const int q = (it << 5) + lane;
-                if (q < seg) body(sg, q, j);
-            }
-            count -= seg;
-            i = 0;
-            if (count > 0) {
-                do { ++t; } while (h->t_ne[b][t] != ne_sel || h->w_cnt[b][t] == 0);
-            }
-        }
+    // This warp's slice of token t in stage b (its document sub-range), as shared-space addresses
+    __device__ __forceinline__ Seg slice_of(int b, int t, int cw, uint32_t pool_s) {
+        const int o0 = h->w_off[b][t][cw], o1 = h->w_off[b][t][cw + 1];
+        Seg g;
+        g.docs = pool_s + 4u * (unsigned)(h->w_doc[b][t] + o0);
+        g.sc = pool_s + 4u * (unsigned)(h->w_sc[b][t] + o0);
+        g.rest = h->t_rest[t];
+        g.t = t;
+        g.n = o1 - o0;
+        return g;
     }
 
-    // Collect the (at most kSegMax) token segments of a warp's slice into registers. Returns false when the slice
-    // spans more tokens (many-token queries): the caller then uses the generic for_slice path.
-    __device__ __forceinline__ bool gather_segs(int b, int ne_sel, int t0, int i0, int count, Seg (&sg)[kSegMax]) {
-        const uint32_t pool_s = smem_u32(pool + (size_t)b * p.poolcap);
-        int t = t0, i = i0;
-#pragma unroll
-        for (int s = 0; s < kSegMax; ++s) {
-            sg[s].n = 0;
-            sg[s].docs = pool_s;
-            sg[s].sc = pool_s;
-            sg[s].rest = 0.0f;
-            sg[s].t = 0;
-            if (count > 0) {
-                const int seg = min(count, h->w_cnt[b][t] - i);
-                sg[s].docs = pool_s + 4u * (unsigned)(h->w_doc[b][t] + i);
-                sg[s].sc = pool_s + 4u * (unsigned)(h->w_sc[b][t] + i);
-                sg[s].rest = h->t_rest[t];
-                sg[s].t = t;
-                sg[s].n = seg;
-                count -= seg;
-                i = 0;
-                if (count > 0) {
-                    do { ++t; } while (h->t_ne[b][t] != ne_sel || h->w_cnt[b][t] == 0);
-                }
-            }
-        }
-        return count == 0;
-    }
-
-    // P3 on one register-cached segment: sole hits score directly; contested winners and documents without a winner
-    // go to the slow list.
-    __device__ __forceinline__ void pass_resolve(const Seg &g, float theta, int sh, unsigned gmask, uint32_t tagv, int lane,
-                                                 int j0, unsigned long long kept) {
+    // P3 on one slice: sole hits score directly; contested winners and documents without a winner go to the warp's
+    // slow list, which is resolved whenever it fills up (and once more at the end of the window).
+    __device__ __forceinline__ void pass_resolve(const Seg &g, float theta, bool allkept, int sh, unsigned gmask, uint32_t tagv,
+                                                 int lane, int b, int T, int cw, uint32_t pool_s, int &slow_n) {
         const unsigned tbits = (unsigned)(g.t << 3) | kTagValid;
         const int iters = (g.n + 31) >> 5;
         uint32_t ad = g.docs + (lane << 2), as = g.sc + (lane << 2);
-        for (int it = 0; it < iters; it += 4, ad += 512, as += 512) {
-            const unsigned k4 = (unsigned)(kept >> (j0 + it)) & (iters - it >= 4 ? 15u : (1u << (iters - it)) - 1u);  // this segment's iterations only
-            if (__ballot_sync(0xffffffffu, k4 != 0u) == 0u) continue;
+        int rem = g.n - lane;
+        for (int it = 0; it < iters; it += 4, ad += 512, as += 512, rem -= 128) {
             unsigned d[4], x[4];
             float sv[4];
+            bool v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                d[u] = (k4 >> u) & 1u ? lds32(ad + 128 * u) : 0u;
-                sv[u] = (k4 >> u) & 1u ? ldsf(as + 128 * u) : 0.0f;
+                v[u] = rem > 32 * u;
+                sv[u] = v[u] ? ldsf(as + 128 * u) : 0.0f;
+                if (v[u] && !allkept) v[u] = kept_posting(sv[u], g.rest, theta);
+                d[u] = v[u] ? lds32(ad + 128 * u) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = (k4 >> u) & 1u ? lds8(tagv + (d[u] >> sh)) : 0u;
-            unsigned act = 0;  // lanes with something to do: a sole hit above theta, or a slow-list entry
+            for (int u = 0; u < 4; ++u) x[u] = v[u] ? lds8(tagv + (d[u] >> sh)) : 0u;
+            unsigned act = 0, slow = 0;  // act: a sole hit above theta; slow: needs the slow path
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (!((k4 >> u) & 1u)) continue;
+                if (!v[u]) continue;
                 const unsigned mine = tag_of(tbits, d[u], gmask);
-                if (x[u] == mine ? (sv[u] > theta) : ((x[u] & 0x7Fu) == mine || ((x[u] ^ mine) & gmask) != 0u)) act |= 1u << u;
+                if (x[u] == mine) { if (sv[u] > theta) act |= 1u << u; }
+                else if ((x[u] & 0x7Fu) == mine || ((x[u] ^ mine) & gmask) != 0u) slow |= 1u << u;
             }
-            if (__ballot_sync(0xffffffffu, act != 0u)) {
+            if (__ballot_sync(0xffffffffu, (act | slow) != 0u)) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (!((act >> u) & 1u)) continue;
-                    const unsigned mine = tag_of(tbits, d[u], gmask);
-                    if (x[u] == mine) emit(sv[u], (int)d[u]);
-                    else if ((x[u] & 0x7Fu) == mine) slow_push((int)d[u], g.t);   // contested winner: resolves its document
-                    else slow_push((int)d[u], g.t | (1 << 8));                    // another document won the group (rule 1)
+                    if ((act >> u) & 1u) emit(sv[u], (int)d[u]);
+                    const unsigned m = __ballot_sync(0xffffffffu, (slow >> u) & 1u);
+                    if (m) {
+                        const int cnt = __popc(m);
+                        if (slow_n + cnt > 32) { resolve_slow(b, T, cw, pool_s, theta, slow_n); slow_n = 0; }
+                        if ((slow >> u) & 1u) {
+                            const unsigned mine = tag_of(tbits, d[u], gmask);
+                            const int rule = ((x[u] & 0x7Fu) == mine) ? 0 : 1;  // 0: contested winner, 1: another document won
+                            h->w_slow[cw][slow_n + __popc(m & ((1u << lane) - 1u))] = make_int2((int)d[u], g.t | (rule << 8));
+                        }
+                        slow_n += cnt;
+                        __syncwarp();
+                    }
                 }
             }
         }
+    }
+
+    // P4: one lane per listed document re-sums it in query-token order (the reference's float32 order) from binary
+    // searches of this warp's slice of every token. rule 1: only the essential hit with the smallest token slot emits
+    // (several postings of the same document may be listed).
+    __device__ void resolve_slow(int b, int T, int cw, uint32_t pool_s, float theta, int n) {
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+        if (lane < n) {
+            const int2 e = h->w_slow[cw][lane];
+            const int d = e.x, myslot = e.y & 0xFF, rule = e.y >> 8;
+            float sum = 0.0f;
+            int min_e = 99;
+            for (int t = 0; t < T; ++t) {
+                const int o0 = h->w_off[b][t][cw], o1 = h->w_off[b][t][cw + 1];
+                if (o1 == o0) continue;
+                const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
+                int lo = o0, hi = o1;
+                while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < d) lo = m + 1; else hi = m; }
+                if (lo < o1 && (int)lds32(dt + 4u * lo) == d) {
+                    const bool ne = h->t_ne[b][t] != 0;
+                    const float v = ne ? p.data[h->w_goff[b][t] + lo] : ldsf(pool_s + 4u * (unsigned)(h->w_sc[b][t] + lo));
+                    sum = __fadd_rn(sum, v);
+                    if (!ne && t < min_e) min_e = t;
+                }
+            }
+            if ((rule == 0 || min_e == myslot) && sum > theta) emit(sum, d);
+        }
+        __syncwarp();
     }
 
     // ------------------------------------------------------------------------------------------ consumer warps
@@ -692,7 +686,6 @@ struct Fast {
             const unsigned gmask = (1u << sh) - 1u;
             const uint32_t tagv = smem_u32(tag) - (uint32_t)(h->w_base[b] >> sh);  // tag of document d: tagv + (d >> sh)
             const int last = h->w_last[b];
-            const int ME = h->w_ME[b], MN = h->w_MN[b];
 
             if (first_window) {
                 // Seed theta: the k-th largest score among the staged postings of the token with the most postings in
@@ -717,184 +710,61 @@ struct Fast {
                 }
             }
             PROF(2);
-            PROF_CNT(17, ME); PROF_CNT(18, MN);
+            PROF_CNT(17, h->w_ME[b]); PROF_CNT(18, h->w_MN[b]);
 
-            // this warp's slices of the two flattened index spaces, cached as token segments in registers
-            const int eLo = (int)((unsigned)ME * (unsigned)cw / (unsigned)NW), eHi = (int)((unsigned)ME * (unsigned)(cw + 1) / (unsigned)NW);
-            const int nLo = (int)((unsigned)MN * (unsigned)cw / (unsigned)NW), nHi = (int)((unsigned)MN * (unsigned)(cw + 1) / (unsigned)NW);
-            const int eN = eHi - eLo, nN = nHi - nLo;
-            const int eT0 = h->s_Et[b][cw], eI0 = h->s_Ei[b][cw], nT0 = h->s_Nt[b][cw], nI0 = h->s_Ni[b][cw];
-            Seg se[kSegMax], sn[kSegMax];
-            const bool fastE = gather_segs(b, 0, eT0, eI0, eN, se);
-            const bool fastN = gather_segs(b, 1, nT0, nI0, nN, sn);
-            unsigned long long keptE = 0ull;
-
-            // ---- P1: essential postings that can still reach the threshold claim their document's group
-            if (fastE) {
-                int j0 = 0;
-#pragma unroll
-                for (int s2 = 0; s2 < kSegMax; ++s2) {
-                    if (se[s2].n > 0) {
-                        pass_claim(se[s2], theta, sh, gmask, tagv, lane, j0, keptE);
-                        j0 += (se[s2].n + 31) >> 5;
-                    }
+            // ---- this warp's document sub-range: its slice of every token
+            unsigned emask = 0, nmask = 0;  // tokens with a non-empty essential / non-essential slice (warp-uniform)
+            for (int t = 0; t < T; ++t) {
+                if (h->w_off[b][t][cw + 1] > h->w_off[b][t][cw]) {
+                    if (h->t_ne[b][t]) nmask |= 1u << t; else emask |= 1u << t;
                 }
-            } else {
-                for_slice(b, 0, eT0, eI0, eN, [&](const Seg &sg, int i, int j) {
-                    const float s = ldsf(sg.sc + 4u * i);
-                    const float ub = __fmul_ru(__fadd_ru(s, sg.rest), 1.00002f);
-                    if (ub > theta) {
-                        const unsigned d = lds32(sg.docs + 4u * i);
-                        sts8(tagv + (d >> sh), (unsigned)(sg.t << 3) | kTagValid | (d & gmask));
-                        keptE |= 1ull << j;
-                    }
-                });
             }
-            // warp-uniform: some lane of this warp kept a posting (the passes below use warp votes)
-            const bool warp_kept = __ballot_sync(0xffffffffu, keptE != 0ull) != 0u;
-            if (lane == 0 && warp_kept) atomicAdd(&h->w_kept[b], 1u);
+            // ---- P1: essential postings that can still reach the threshold claim their document's group
+            bool kept_any = false;
+            for (unsigned m = emask; m; m &= m - 1) {
+                const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                kept_any |= pass_claim(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
+            }
+            const bool warp_kept = __ballot_sync(0xffffffffu, kept_any) != 0u;
             PROF(3);
-            bsync<true>();
-            PROF(4);
-            const bool active = h->w_kept[b] > 0;  // no surviving essential posting: nothing in this window can score
-            PROF_CNT(19, active ? 1 : 0);
-            if (active) {
+            __syncwarp();
+            PROF_CNT(19, warp_kept ? 1 : 0);
+            if (warp_kept) {  // no surviving essential posting: nothing in this sub-range can score
                 // ---- P2: postings that do not read back their own claim set the contested bit; non-essential postings
                 //      that find their own document claimed do the same
-                if (fastE) {
-                    int j0 = 0;
-#pragma unroll
-                    for (int s2 = 0; s2 < kSegMax; ++s2) {
-                        if (se[s2].n > 0) {
-                            if (warp_kept) pass_mark_e(se[s2], sh, gmask, tagv, lane, j0, keptE);
-                            j0 += (se[s2].n + 31) >> 5;
-                        }
-                    }
-                } else if (warp_kept) {
-                    for_slice(b, 0, eT0, eI0, eN, [&](const Seg &sg, int i, int j) {
-                        if ((keptE >> j) & 1ull) {
-                            const unsigned d = lds32(sg.docs + 4u * i);
-                            const unsigned x = lds8(tagv + (d >> sh));
-                            if (x != ((unsigned)(sg.t << 3) | kTagValid | (d & gmask))) sts8(tagv + (d >> sh), x | kTagContested);
-                        }
-                    });
+                for (unsigned m = emask; m; m &= m - 1) {
+                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                    pass_mark_e(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
                 }
-                if (fastN) {
-#pragma unroll
-                    for (int s2 = 0; s2 < kSegMax; ++s2)
-                        if (sn[s2].n > 0) pass_probe_n(sn[s2], sh, gmask, tagv, lane);
-                } else {
-                    for_slice(b, 1, nT0, nI0, nN, [&](const Seg &sg, int i, int j) {
-                        const unsigned d = lds32(sg.docs + 4u * i);
-                        const unsigned x = lds8(tagv + (d >> sh));
-                        if ((x & 7u) == (kTagValid | (d & gmask))) sts8(tagv + (d >> sh), x | kTagContested);
-                    });
+                for (unsigned m = nmask; m; m &= m - 1) {
+                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                    pass_probe_n(g, sh, gmask, tagv, lane);
                 }
                 PROF(5);
-                bsync<true>();
-                PROF(6);
+                __syncwarp();
                 // ---- P3: sole hits score directly; contested winners and documents without a winner go to the slow list
-                if (warp_kept) {
-                    if (fastE) {
-                        int j0 = 0;
-#pragma unroll
-                        for (int s2 = 0; s2 < kSegMax; ++s2) {
-                            if (se[s2].n > 0) {
-                                pass_resolve(se[s2], theta, sh, gmask, tagv, lane, j0, keptE);
-                                j0 += (se[s2].n + 31) >> 5;
-                            }
-                        }
-                    } else {
-                        for_slice(b, 0, eT0, eI0, eN, [&](const Seg &sg, int i, int j) {
-                            if ((keptE >> j) & 1ull) {
-                                const unsigned d = lds32(sg.docs + 4u * i);
-                                const unsigned x = lds8(tagv + (d >> sh));
-                                const unsigned mine = (unsigned)(sg.t << 3) | kTagValid | (d & gmask);
-                                if (x == mine) {
-                                    const float s = ldsf(sg.sc + 4u * i);
-                                    if (s > theta) emit(s, (int)d);
-                                } else if ((x & 0x7Fu) == mine) {
-                                    slow_push((int)d, sg.t);
-                                } else if (((x ^ mine) & gmask) != 0u) {
-                                    slow_push((int)d, sg.t | (1 << 8));
-                                }
-                            }
-                        });
-                    }
+                int slow_n = 0;
+                for (unsigned m = emask; m; m &= m - 1) {
+                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                    pass_resolve(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane, b, T, cw, pool_s, slow_n);
                 }
                 PROF(7);
-                bsync<true>();
-                PROF(8);
+                __syncwarp();
                 // ---- P5: the claiming postings clean their tags (tags are all-clean between windows)
-                if (warp_kept) {
-                    if (fastE) {
-                        int j0 = 0;
-#pragma unroll
-                        for (int s2 = 0; s2 < kSegMax; ++s2) {
-                            if (se[s2].n > 0) {
-                                pass_clean(se[s2], sh, tagv, lane, j0, keptE);
-                                j0 += (se[s2].n + 31) >> 5;
-                            }
-                        }
-                    } else {
-                        for_slice(b, 0, eT0, eI0, eN, [&](const Seg &sg, int i, int j) {
-                            if ((keptE >> j) & 1ull) sts8(tagv + (lds32(sg.docs + 4u * i) >> sh), 0u);
-                        });
-                    }
+                for (unsigned m = emask; m; m &= m - 1) {
+                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                    pass_clean(g, theta, kept_posting(0.0f, g.rest, theta), sh, tagv, lane);
                 }
                 PROF(9);
-                // ---- P4: slow list. Documents are re-summed in query-token order (the reference's float32 order):
-                //      a) one thread per (document, token): binary search of the token's window postings
-                //      b) one thread per document: ordered sum; rule 1: only the essential hit with the smallest token
-                //         slot emits (several postings of the same document may be listed)
-                const int R = (int)min(h->r_cnt, (unsigned)(kSlowSmem + p.rspillcap));
-                PROF_CNT(21, R);
-                if (R > 0) {
-                    const int chunk_docs = kPartCap / T;
-                    for (int r0 = 0; r0 < R; r0 += chunk_docs) {
-                        const int nd = min(chunk_docs, R - r0);
-                        const int pairs = nd * T;
-                        for (int jj = ctid; jj < pairs; jj += CNT) {
-                            const int r = jj / T, t = jj - r * T;
-                            const int ri = r0 + r;
-                            const int d = (ri < kSlowSmem) ? rlist[ri].x : rspill[ri - kSlowSmem].x;
-                            const int c = h->w_cnt[b][t];
-                            float v = -1.0f;
-                            if (c > 0) {
-                                const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
-                                int lo = 0, hi = c;
-                                while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < d) lo = m + 1; else hi = m; }
-                                if (lo < c && (int)lds32(dt + 4u * lo) == d)
-                                    v = h->t_ne[b][t] ? p.data[h->w_goff[b][t] + lo] : bpf[h->w_sc[b][t] + lo];
-                            }
-                            part[jj] = v;
-                        }
-                        bsync<true>();
-                        for (int r = ctid; r < nd; r += CNT) {
-                            const int ri = r0 + r;
-                            const int2 e = (ri < kSlowSmem) ? rlist[ri] : rspill[ri - kSlowSmem];
-                            const int myslot = e.y & 0xFF, rule = e.y >> 8;
-                            float sum = 0.0f;
-                            int min_e = 99;
-                            const float *pv = part + r * T;
-                            for (int t = 0; t < T; ++t) {
-                                const float v = pv[t];
-                                if (v >= 0.0f) {
-                                    sum = __fadd_rn(sum, v);
-                                    if (!h->t_ne[b][t] && t < min_e) min_e = t;
-                                }
-                            }
-                            if ((rule == 0 || min_e == myslot) && sum > theta) emit(sum, e.x);
-                        }
-                        bsync<true>();
-                    }
-                } else {
-                    bsync<true>();
-                }
+                // ---- P4: the rest of the slow list
+                PROF_CNT(21, slow_n);
+                if (slow_n > 0) resolve_slow(b, T, cw, pool_s, theta, slow_n);
             }
             PROF(10);
-            // all consumers are done with stage b and the tags of this window
-            if (ctid == 0) { h->r_cnt = 0; mbar_arrive(&h->bar_free[b]); }
+            // the consumers meet once per window: stage b and its tags are released, the candidate buffer is checked
+            bsync<true>();
+            PROF(4);
+            if (ctid == 0) mbar_arrive(&h->bar_free[b]);
             if (h->cb_cnt >= (unsigned)trigger) { compact<true>(k, ctid, CNT); theta = fmaxf(theta, h->theta); PROF_CNT(22, 1); }
             PROF(11);
             if (last) break;
@@ -940,7 +810,7 @@ struct Fast {
                 h->t_df[tid] = end - beg;
                 h->t_max[tid] = mx;
             }
-            if (tid == 0) { h->cb_cnt = 0; h->theta = 0.0f; h->r_cnt = 0; }
+            if (tid == 0) { h->cb_cnt = 0; h->theta = 0.0f; }
             __syncthreads();
             if (warp == 0) {
                 // pruning bounds from the column maxima
@@ -1064,14 +934,13 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.route_all_general = (!ix->nonneg) || (a.mask != nullptr) || (a.k > 2048) || env_int("BM25CU_FORCE_GENERAL", 0);
     const int budget = ix->max_smem_optin / (ctas_per_sm > 0 ? ctas_per_sm : 1) - (ctas_per_sm > 1 ? 1024 : 0);
     const int nw = threads / 32 - 1;
-    // pool: 4-byte slots per stage. The per-thread posting masks hold 64 warp iterations:
-    // (postings per consumer warp) / 32 + kMaxTok + 1 <= 64, and a posting takes at least one slot.
+    // pool: 4-byte slots per stage
     int pool = env_int("BM25CU_POOL", ctas_per_sm > 1 ? 6144 : 14336);
     pool = (pool + 3) & ~3;
     const int min_pool = kMaxTok * 2 * kMinCap + 256;
     if (pool < min_pool) pool = min_pool;
-    const int max_pool = nw * 32 * (64 - kMaxTok - 2);
-    if (pool > max_pool) pool = max_pool & ~3;
+    (void)nw;
+    if (pool > 32768) pool = 32768;
     p.poolcap = pool;
     size_t fixed = Fast<512>::fixed_smem(p);
     long long tagcap = (long long)budget - (long long)fixed - 64;
@@ -1084,13 +953,11 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     const int tag_env = env_int("BM25CU_TAG", 0);
     if (tag_env > 0 && tag_env < tagcap) tagcap = tag_env;
     p.tagcap = (int)(tagcap & ~15ll);
-    p.rspillcap = p.poolcap;
     p.spillcap = 2 * p.poolcap;
     const int grid = ix->sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1);
-    int rc = ix->d_spill.reserve((size_t)grid * ((size_t)p.spillcap * 8 + (size_t)p.rspillcap * 8));
+    int rc = ix->d_spill.reserve((size_t)grid * (size_t)p.spillcap * 8);
     if (rc) return rc;
     p.spill = ix->d_spill.as<unsigned long long>();
-    p.rspill = reinterpret_cast<int2 *>(p.spill + (size_t)grid * p.spillcap);
     const size_t smem = fixed + p.tagcap;
     cudaError_t e;
 #define BM25CU_LAUNCH(NTV)                                                                                          \
