@@ -61,7 +61,7 @@ constexpr int kMaxTok = 15;     // token slots per query on this path (4 bits of
 constexpr int kTokArr = 16;
 constexpr int kMinCap = 16;     // minimum staged postings per live token per window (multiple of 4)
 constexpr int kMaxWarps = 32;
-constexpr int kSegMax = 4;      // essential / non-essential token slices of a warp kept in registers (more: generic path)
+constexpr int kMaxChunk = 48;   // 32-posting chunks of essential postings per consumer warp and window (more: slice path)
 constexpr unsigned kTagValid = 4u, kTagContested = 0x80u;
 
 struct FastParams {
@@ -81,6 +81,8 @@ struct FastParams {
     int route_all_general;
     int prune;     // 0: every token is essential and nothing is dropped (exhaustive), 1: threshold pruning
     int max_shift; // largest log2(G)
+    int nwarps;    // consumer warps of the launch configuration
+    int debug;     // timing experiments only (BM25CU_DEBUG_SKIP bit mask; results are wrong when non-zero)
 };
 
 // ---------------------------------------------------------------- PTX wrappers (mbarrier + bulk async copy)
@@ -133,7 +135,9 @@ struct SmemHdr {
     int w_cnt[2][kTokArr];    // postings of the token inside the window
     int w_doc[2][kTokArr];    // pool slot of the first window document id
     int w_sc[2][kTokArr];     // pool slot of the first window score (essential tokens)
-    int w_off[2][kTokArr][kMaxWarps + 1];  // w_off[b][t][w]: first window posting of token t in warp w's doc sub-range
+    int s_lo[kMaxWarps][kTokArr];          // per consumer warp: first / one-past-last window posting of token t in the warp's
+    int s_hi[kMaxWarps][kTokArr];          // document sub-range (computed by the warp itself for the current window)
+    int w_end[2];                          // one past the last document of the window
     int2 w_slow[kMaxWarps][32];            // per-warp slow list (doc, slot | rule << 8)
     int w_base[2];            // first document of the window, rounded down to a multiple of G
     int w_shift[2];           // log2(G) of the window
@@ -159,6 +163,11 @@ __device__ __forceinline__ unsigned lds32(uint32_t a) { unsigned v; asm volatile
 __device__ __forceinline__ float ldsf(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ unsigned lds8(uint32_t a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts8(uint32_t a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 
 // one token's window postings as seen by a consumer warp (shared-space byte addresses, kept in registers)
 struct Seg {
@@ -281,12 +290,156 @@ __device__ __forceinline__ void pass_clean(const Seg &g, float theta, bool allke
     }
 }
 
+// ---------------------------------------------------------------- chunk passes (essential postings)
+// A consumer warp's essential postings of a window are cut into chunks of <= 32 consecutive postings of one token
+// (descriptor: docs address, scores address, count | slot << 8 | allkept << 16, rest). Four chunks are processed
+// together, one posting per lane and chunk, so short per-token slices still fill the unrolled group.
+struct Chunk4 {
+    uint32_t docs[4], sc[4];
+    float rest[4];
+    unsigned tbits[4];
+    int cnt[4];
+    bool allkept[4];
+};
+__device__ __forceinline__ void load_chunks(uint32_t chunk_s, int c0, int nch, Chunk4 &c) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        c.cnt[u] = 0;
+        c.docs[u] = 0; c.sc[u] = 0; c.rest[u] = 0.0f; c.tbits[u] = 0; c.allkept[u] = true;
+        if (c0 + u < nch) {
+            const uint4 d = lds128(chunk_s + 16u * (unsigned)(c0 + u));
+            c.docs[u] = d.x;
+            c.sc[u] = d.y;
+            c.cnt[u] = (int)(d.z & 0xFFu);
+            c.tbits[u] = (((d.z >> 8) & 0xFFu) << 3) | kTagValid;
+            c.allkept[u] = ((d.z >> 16) & 1u) != 0u;
+            c.rest[u] = __uint_as_float(d.w);
+        }
+    }
+}
+
+// P1 over chunks: kept postings claim their document's group. Returns (per lane) whether anything was kept.
+__device__ __forceinline__ bool chunks_claim(uint32_t chunk_s, int nch, float theta, int sh, unsigned gmask, uint32_t tagv, int lane) {
+    bool any = false;
+    for (int c0 = 0; c0 < nch; c0 += 4) {
+        Chunk4 c;
+        load_chunks(chunk_s, c0, nch, c);
+        unsigned d[4];
+        float sv[4];
+        bool v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = lane < c.cnt[u];
+            sv[u] = (v[u] && !c.allkept[u]) ? ldsf(c.sc[u] + 4u * lane) : 0.0f;
+            d[u] = v[u] ? lds32(c.docs[u] + 4u * lane) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (v[u] && (c.allkept[u] || kept_posting(sv[u], c.rest[u], theta))) {
+                sts8(tagv + (d[u] >> sh), tag_of(c.tbits[u], d[u], gmask));
+                any = true;
+            }
+        }
+    }
+    return any;
+}
+
+// P2 (essential) over chunks: kept postings that do not read back their own claim set the contested bit
+__device__ __forceinline__ void chunks_mark(uint32_t chunk_s, int nch, float theta, int sh, unsigned gmask, uint32_t tagv, int lane) {
+    for (int c0 = 0; c0 < nch; c0 += 4) {
+        Chunk4 c;
+        load_chunks(chunk_s, c0, nch, c);
+        unsigned d[4], x[4];
+        bool v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = lane < c.cnt[u];
+            if (v[u] && !c.allkept[u]) v[u] = kept_posting(ldsf(c.sc[u] + 4u * lane), c.rest[u], theta);
+            d[u] = v[u] ? lds32(c.docs[u] + 4u * lane) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = v[u] ? lds8(tagv + (d[u] >> sh)) : 0u;
+        unsigned bad = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v[u] && x[u] != tag_of(c.tbits[u], d[u], gmask)) bad |= 1u << u;
+        if (__ballot_sync(0xffffffffu, bad != 0u)) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((bad >> u) & 1u) sts8(tagv + (d[u] >> sh), x[u] | kTagContested);
+        }
+    }
+}
+
+// P5 over chunks: kept postings clean the tags
+__device__ __forceinline__ void chunks_clean(uint32_t chunk_s, int nch, float theta, int sh, uint32_t tagv, int lane) {
+    for (int c0 = 0; c0 < nch; c0 += 4) {
+        Chunk4 c;
+        load_chunks(chunk_s, c0, nch, c);
+        unsigned d[4];
+        bool v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = lane < c.cnt[u];
+            if (v[u] && !c.allkept[u]) v[u] = kept_posting(ldsf(c.sc[u] + 4u * lane), c.rest[u], theta);
+            d[u] = v[u] ? lds32(c.docs[u] + 4u * lane) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v[u]) sts8(tagv + (d[u] >> sh), 0u);
+    }
+}
+
+// P2 (non-essential), vectorised: each lane probes four consecutive document ids per 16-byte load
+__device__ __forceinline__ void probe4(const uint4 dv, int sh, unsigned gmask, uint32_t tagv) {
+    const unsigned d[4] = {dv.x, dv.y, dv.z, dv.w};
+    unsigned x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = lds8(tagv + (d[u] >> sh));
+    unsigned hit = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if ((x[u] & 7u) == (kTagValid | (d[u] & gmask))) hit |= 1u << u;
+    if (hit) {  // rare
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if ((hit >> u) & 1u) sts8(tagv + (d[u] >> sh), x[u] | kTagContested);
+    }
+}
+__device__ __forceinline__ void pass_probe_n_vec(const Seg &g, int sh, unsigned gmask, uint32_t tagv, int lane) {
+    // head: scalar elements up to the first 16-byte boundary
+    const int head = min(g.n, (int)((4u - ((g.docs >> 2) & 3u)) & 3u));
+    if (lane < head) {
+        const unsigned d = lds32(g.docs + 4u * lane);
+        const unsigned x = lds8(tagv + (d >> sh));
+        if ((x & 7u) == (kTagValid | (d & gmask))) sts8(tagv + (d >> sh), x | kTagContested);
+    }
+    const int nbody = g.n - head;
+    const int nv = nbody >> 2;  // full vectors
+    const uint32_t vb = g.docs + 4u * head;
+    int i = lane;
+    for (; i + 32 < nv; i += 64) {  // two vectors per lane in flight
+        const uint4 a = lds128(vb + 16u * i), b2 = lds128(vb + 16u * (i + 32));
+        probe4(a, sh, gmask, tagv);
+        probe4(b2, sh, gmask, tagv);
+    }
+    if (i < nv) probe4(lds128(vb + 16u * i), sh, gmask, tagv);
+    // tail
+    const int tail0 = head + (nv << 2);
+    if (lane < g.n - tail0) {
+        const unsigned d = lds32(g.docs + 4u * (tail0 + lane));
+        const unsigned x = lds8(tagv + (d >> sh));
+        if ((x & 7u) == (kTagValid | (d & gmask))) sts8(tagv + (d >> sh), x | kTagContested);
+    }
+}
+
 template <int NT>
 struct Fast {
     static constexpr int CNT = NT - 32;  // consumer threads
     static constexpr int NW = CNT / 32;  // consumer warps
     SmemHdr *h;
     unsigned long long *cb;   // [cbcap]
+    uint4 *chunks;            // [nwarps][kMaxChunk] essential-posting chunk descriptors
     int *pool;                // [2][poolcap] 4-byte slots: document ids and (essential tokens) float scores
     unsigned char *tag;       // [tagcap]
     const FastParams &p;
@@ -298,6 +451,8 @@ struct Fast {
         cb = reinterpret_cast<unsigned long long *>(smem + o);
         o += (size_t)p.cbcap * 8;
         o = (o + 15) & ~size_t(15);
+        chunks = reinterpret_cast<uint4 *>(smem + o);
+        o += (size_t)p.nwarps * kMaxChunk * 16;
         pool = reinterpret_cast<int *>(smem + o);
         o += (size_t)2 * p.poolcap * 4;
         tag = smem + o;
@@ -307,6 +462,7 @@ struct Fast {
         size_t o = (sizeof(SmemHdr) + 15) & ~size_t(15);
         o += (size_t)p.cbcap * 8;
         o = (o + 15) & ~size_t(15);
+        o += (size_t)p.nwarps * kMaxChunk * 16;
         o += (size_t)2 * p.poolcap * 4;
         return o;
     }
@@ -388,64 +544,72 @@ struct Fast {
     }
 
     // producer: stage the next window of every live token into stage b. Pool slots are shared out in proportion to
-    // the column lengths (an essential token needs two slots per posting, a non-essential one a single slot).
-    __device__ void issue_loads(int b, int T) {
+    // the column lengths (an essential token needs two slots per posting, a non-essential one a single slot). The
+    // share-out (cap / offset per token, tag granularity) only changes when a token runs dry or turns non-essential,
+    // so it is cached in the producer lanes' registers (lane == token slot) and recomputed on change.
+    struct Layout {
+        int cap, off, ne, live, sh;
+    };
+    __device__ __forceinline__ void issue_loads(int b, int T, Layout &L) {
         const int lane = threadIdx.x & 31;
         const float theta_p = *reinterpret_cast<volatile float *>(&h->theta);
-        long long cur = 0, rem = 0, w = 0, dfE = 0;
+        long long cur = 0, rem = 0;
         int ne = 0;
         if (lane < T) {
             cur = h->t_cur[lane];
             rem = h->t_end[lane] - cur;
             ne = (p.prune && h->t_nebound[lane] < theta_p) ? 1 : 0;
-            if (rem > 0) {
+        }
+        const int live = rem > 0 ? 1 : 0;
+        if (__any_sync(0xffffffffu, ne != L.ne || live != L.live)) {
+            long long w = 0, dfE = 0;
+            if (live) {
                 w = h->t_df[lane] * (ne ? 1 : 2);
                 if (!ne) dfE = h->t_df[lane];
             }
-        }
-        long long wsum = w;
-        int live = rem > 0 ? 1 : 0;
+            long long wsum = w;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-            dfE += __shfl_xor_sync(0xffffffffu, dfE, o);
-            live += __shfl_xor_sync(0xffffffffu, live, o);
-        }
-        int cap = 0, slots = 0;
-        if (rem > 0) {
-            const long long freeslots = (long long)p.poolcap - (long long)live * (2 * kMinCap);
-            const long long share = (freeslots * w) / wsum;        // slots
-            cap = kMinCap + (int)((share / (ne ? 1 : 2)) & ~3ll);  // postings, multiple of 4
-            const long long want = ((rem + 3 + 3) & ~3ll);         // never stage beyond the column (+ alignment skip)
-            if (cap > want) cap = (int)want;
-            slots = cap * (ne ? 1 : 2);
-        }
-        int tot;
-        const int off = warp_excl_scan(slots, tot);
-        if (lane < T) {
-            int n = 0, a = 0;
-            if (rem > 0) {
-                a = (int)(cur & 3);
-                n = (int)min((long long)(cap - a), rem);
-                const uint32_t bytes = (uint32_t)(((a + n + 3) & ~3) * 4);
-                mbar_expect_tx(&h->bar_data[b], ne ? bytes : 2 * bytes);
-                int *dst = pool + (size_t)b * p.poolcap + off;
-                bulk_g2s(dst, p.indices + (cur - a), bytes, &h->bar_data[b]);
-                if (!ne) bulk_g2s(dst + cap, p.data + (cur - a), bytes, &h->bar_data[b]);
+            for (int o = 16; o > 0; o >>= 1) {
+                wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+                dfE += __shfl_xor_sync(0xffffffffu, dfE, o);
             }
-            h->t_n[b][lane] = n;
-            h->t_ne[b][lane] = ne;
-            h->w_doc[b][lane] = off + a;
-            h->w_sc[b][lane] = off + cap + a;
-        }
-        // tag granularity G = 2^sh of the window: a claiming posting shares its group with G - 1 neighbours, each
-        // claimed with the density of the essential postings; keep (G - 1) * density <= 1/32
-        {
+            const int nlive = __reduce_add_sync(0xffffffffu, live);
+            int cap = 0, slots = 0;
+            if (live) {
+                const long long freeslots = (long long)p.poolcap - (long long)nlive * (2 * kMinCap);
+                const long long share = (freeslots * w) / wsum;        // slots
+                cap = kMinCap + (int)((share / (ne ? 1 : 2)) & ~3ll);  // postings, multiple of 4
+                slots = cap * (ne ? 1 : 2);
+            }
+            int tot;
+            L.off = warp_excl_scan(slots, tot);
+            L.cap = cap;
+            L.ne = ne;
+            L.live = live;
+            // tag granularity G = 2^sh: a claiming posting shares its group with G - 1 neighbours, each claimed with
+            // the density of the essential postings; keep (G - 1) * density <= 1/32
             int sh = 0;
             const long long nd = p.n_docs > 0 ? p.n_docs : 1;
             while (sh < p.max_shift && ((long long)((2 << sh) - 1) * dfE * 32 <= nd)) ++sh;
-            if (lane == 0) h->w_shift[b] = sh;
+            L.sh = sh;
         }
+        if (lane < T) {
+            int n = 0, a = 0;
+            if (live) {
+                a = (int)(cur & 3);
+                n = (int)min((long long)(L.cap - a), rem);
+                const uint32_t bytes = (uint32_t)(((a + n + 3) & ~3) * 4);
+                mbar_expect_tx(&h->bar_data[b], ne ? bytes : 2 * bytes);
+                int *dst = pool + (size_t)b * p.poolcap + L.off;
+                bulk_g2s(dst, p.indices + (cur - a), bytes, &h->bar_data[b]);
+                if (!ne) bulk_g2s(dst + L.cap, p.data + (cur - a), bytes, &h->bar_data[b]);
+            }
+            h->t_n[b][lane] = n;
+            h->t_ne[b][lane] = ne;
+            h->w_doc[b][lane] = L.off + a;
+            h->w_sc[b][lane] = L.off + L.cap + a;
+        }
+        if (lane == 0) h->w_shift[b] = L.sh;
         __syncwarp();
         if (lane == 0) mbar_arrive(&h->bar_data[b]);
     }
@@ -470,13 +634,16 @@ struct Fast {
     }
 
     // ------------------------------------------------------------------------------------------ producer warp
-    __device__ void producer(int T, uint32_t &ph_data0, uint32_t &ph_data1, uint32_t &ph_free0, uint32_t &ph_free1) {
+    __device__ void producer(int T, Layout &L, uint32_t &ph_data0, uint32_t &ph_data1, uint32_t &ph_free0, uint32_t &ph_free1) {
         const int lane = threadIdx.x & 31;
         int b = 0;
         int nwin = 0;
+        PROF_DECL;
         for (;;) {
+            PROF(24);
             if (b == 0) { mbar_wait(&h->bar_data[0], ph_data0); ph_data0 ^= 1; }
             else { mbar_wait(&h->bar_data[1], ph_data1); ph_data1 ^= 1; }
+            PROF(25);
             const int *bp = pool + (size_t)b * p.poolcap;
             const uint32_t pool_s = smem_u32(bp);
             int n0 = 0, off0 = 0, first = 0x7fffffff, e = 0x7fffffff, last0 = -1, ne = 0;
@@ -493,13 +660,9 @@ struct Fast {
                     if (cur + n0 < tend) e = last0 + 1;
                 }
             }
-            int lastmax = last0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-                e = min(e, __shfl_xor_sync(0xffffffffu, e, o));
-                lastmax = max(lastmax, __shfl_xor_sync(0xffffffffu, lastmax, o));
-            }
+            const int lastmax = __reduce_max_sync(0xffffffffu, last0);
+            first = __reduce_min_sync(0xffffffffu, first);
+            e = __reduce_min_sync(0xffffffffu, e);
             const int sh = h->w_shift[b];
             const int base = first & ~((1 << sh) - 1);
             const long long span = (long long)p.tagcap << sh;
@@ -516,9 +679,7 @@ struct Fast {
                 const int c = warp_count_below(bp + so, sn, wend);
                 if (lane == src) c0 = c;
             }
-            int ME, MN;
-            (void)warp_excl_scan(ne ? 0 : c0, ME);
-            (void)warp_excl_scan(ne ? c0 : 0, MN);
+            const int ME = __reduce_add_sync(0xffffffffu, ne ? 0 : c0), MN = __reduce_add_sync(0xffffffffu, ne ? c0 : 0);
             bool more = false;
             if (lane < T) {
                 h->w_cnt[b][lane] = c0;
@@ -529,37 +690,26 @@ struct Fast {
             const bool any_more = __any_sync(0xffffffffu, more);
             if (lane == 0) {
                 h->w_base[b] = base;
+                h->w_end[b] = wend;
                 h->w_last[b] = any_more ? 0 : 1;
                 h->w_ME[b] = ME;
                 h->w_MN[b] = MN;
             }
             __syncwarp();
-            // document sub-range of consumer warp w: [bnd(w), bnd(w + 1)), boundaries on multiples of G. Lane w finds,
-            // for every token, the first window posting at or after bnd(w).
-            if (lane <= NW) {
-                const long long wspan = (long long)wend - base;
-                int bnd = (lane == NW) ? wend : (int)(base + (((wspan * lane) / NW) & ~(long long)((1 << sh) - 1)));
-                for (int t = 0; t < T; ++t) {
-                    const int c = h->w_cnt[b][t];
-                    const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
-                    int lo = 0, hi = c;
-                    if (lane == 0) hi = 0;
-                    else if (lane == NW) lo = c;
-                    while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < bnd) lo = m + 1; else hi = m; }
-                    h->w_off[b][t][lane] = lo;
-                }
-            }
-            __syncwarp();
             if (lane == 0) mbar_arrive(&h->bar_meta[b]);  // release: metadata visible to the consumers
+            PROF(26);
             ++nwin;
             if (!any_more) break;
             if (nwin >= 2) {  // the other stage was used by window nwin-2: wait until the consumers released it
                 if (b == 0) { mbar_wait(&h->bar_free[1], ph_free1); ph_free1 ^= 1; }
                 else { mbar_wait(&h->bar_free[0], ph_free0); ph_free0 ^= 1; }
             }
-            issue_loads(b ^ 1, T);
+            PROF(27);
+            issue_loads(b ^ 1, T, L);
+            PROF(28);
             b ^= 1;
         }
+        PROF_FLUSH(lane == 0);
         // consume the releases not waited for above (keeps the barrier parities in step across queries)
         if (nwin >= 2) {
             const int bb = (nwin - 2) & 1;
@@ -575,7 +725,7 @@ struct Fast {
 
     // This warp's slice of token t in stage b (its document sub-range), as shared-space addresses
     __device__ __forceinline__ Seg slice_of(int b, int t, int cw, uint32_t pool_s) {
-        const int o0 = h->w_off[b][t][cw], o1 = h->w_off[b][t][cw + 1];
+        const int o0 = h->s_lo[cw][t], o1 = h->s_hi[cw][t];
         Seg g;
         g.docs = pool_s + 4u * (unsigned)(h->w_doc[b][t] + o0);
         g.sc = pool_s + 4u * (unsigned)(h->w_sc[b][t] + o0);
@@ -635,6 +785,54 @@ struct Fast {
         }
     }
 
+    // P3 over chunks (same logic as pass_resolve, one posting per lane and chunk)
+    __device__ __forceinline__ void chunks_resolve(uint32_t chunk_s, int nch, float theta, int sh, unsigned gmask, uint32_t tagv,
+                                                   int lane, int b, int T, int cw, uint32_t pool_s, int &slow_n) {
+        for (int c0 = 0; c0 < nch; c0 += 4) {
+            Chunk4 c;
+            load_chunks(chunk_s, c0, nch, c);
+            unsigned d[4], x[4];
+            float sv[4];
+            bool v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = lane < c.cnt[u];
+                sv[u] = v[u] ? ldsf(c.sc[u] + 4u * lane) : 0.0f;
+                if (v[u] && !c.allkept[u]) v[u] = kept_posting(sv[u], c.rest[u], theta);
+                d[u] = v[u] ? lds32(c.docs[u] + 4u * lane) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = v[u] ? lds8(tagv + (d[u] >> sh)) : 0u;
+            unsigned act = 0, slow = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!v[u]) continue;
+                const unsigned mine = tag_of(c.tbits[u], d[u], gmask);
+                if (x[u] == mine) { if (sv[u] > theta) act |= 1u << u; }
+                else if ((x[u] & 0x7Fu) == mine || ((x[u] ^ mine) & gmask) != 0u) slow |= 1u << u;
+            }
+            if (__ballot_sync(0xffffffffu, (act | slow) != 0u)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if ((act >> u) & 1u) emit(sv[u], (int)d[u]);
+                    const unsigned m = __ballot_sync(0xffffffffu, (slow >> u) & 1u);
+                    if (m) {
+                        const int cnt = __popc(m);
+                        if (slow_n + cnt > 32) { resolve_slow(b, T, cw, pool_s, theta, slow_n); slow_n = 0; }
+                        if ((slow >> u) & 1u) {
+                            const unsigned mine = tag_of(c.tbits[u], d[u], gmask);
+                            const int rule = ((x[u] & 0x7Fu) == mine) ? 0 : 1;
+                            h->w_slow[cw][slow_n + __popc(m & ((1u << lane) - 1u))] =
+                                make_int2((int)d[u], (int)((c.tbits[u] >> 3) & 15u) | (rule << 8));
+                        }
+                        slow_n += cnt;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+
     // P4: one lane per listed document re-sums it in query-token order (the reference's float32 order) from binary
     // searches of this warp's slice of every token. rule 1: only the essential hit with the smallest token slot emits
     // (several postings of the same document may be listed).
@@ -647,7 +845,7 @@ struct Fast {
             float sum = 0.0f;
             int min_e = 99;
             for (int t = 0; t < T; ++t) {
-                const int o0 = h->w_off[b][t][cw], o1 = h->w_off[b][t][cw + 1];
+                const int o0 = h->s_lo[cw][t], o1 = h->s_hi[cw][t];
                 if (o1 == o0) continue;
                 const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
                 int lo = o0, hi = o1;
@@ -666,7 +864,7 @@ struct Fast {
 
     // ------------------------------------------------------------------------------------------ consumer warps
     __device__ void consumer(int T, int k, uint32_t &ph_meta0, uint32_t &ph_meta1) {
-        const int ctid = threadIdx.x - 32;
+        const int ctid = threadIdx.x;  // consumers are warps 0..NW-1; the producer is the last warp (the scheduler favours it)
         const int cw = ctid >> 5, lane = ctid & 31;
         const int trigger = p.cbcap / 2;
         float theta = 0.0f;
@@ -712,18 +910,65 @@ struct Fast {
             PROF(2);
             PROF_CNT(17, h->w_ME[b]); PROF_CNT(18, h->w_MN[b]);
 
-            // ---- this warp's document sub-range: its slice of every token
+            // ---- this warp's document sub-range [bnd(cw), bnd(cw + 1)), boundaries on multiples of G: lane t finds the
+            //      first posting of token t at or after the lower bound, lane 16 + t does the same for the upper bound
+            {
+                const int wbase = h->w_base[b], wendd = h->w_end[b];
+                const long long wspan = (long long)wendd - wbase;
+                const int t = lane & 15, side = lane >> 4;
+                const int wq = cw + side;
+                const int bnd = (wq == NW) ? wendd : (int)(wbase + (((wspan * wq) / NW) & ~(long long)gmask));
+                if (t < T) {
+                    const int c = h->w_cnt[b][t];
+                    const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
+                    int lo = 0, hi = c;
+                    if (wq == 0) hi = 0;
+                    else if (wq == NW) lo = c;
+                    while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < bnd) lo = m + 1; else hi = m; }
+                    if (side == 0) h->s_lo[cw][t] = lo; else h->s_hi[cw][t] = lo;
+                }
+                __syncwarp();
+            }
+            // ---- this warp's slice of every token
             unsigned emask = 0, nmask = 0;  // tokens with a non-empty essential / non-essential slice (warp-uniform)
             for (int t = 0; t < T; ++t) {
-                if (h->w_off[b][t][cw + 1] > h->w_off[b][t][cw]) {
+                if (h->s_hi[cw][t] > h->s_lo[cw][t]) {
                     if (h->t_ne[b][t]) nmask |= 1u << t; else emask |= 1u << t;
                 }
             }
+            // ---- chunk list of this warp's essential postings (<= 32 consecutive postings of one token per chunk)
+            const uint32_t chunk_s = smem_u32(chunks + (size_t)cw * kMaxChunk);
+            int nch = 0;
+            bool chunk_ok = true;
+            for (unsigned m = emask; m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                const int o0 = h->s_lo[cw][t], n = h->s_hi[cw][t] - o0;
+                const int nc = (n + 31) >> 5;
+                if (nch + nc > kMaxChunk) { chunk_ok = false; break; }
+                const float rest = h->t_rest[t];
+                const unsigned ak = kept_posting(0.0f, rest, theta) ? 1u : 0u;
+                const uint32_t dbase = pool_s + 4u * (unsigned)(h->w_doc[b][t] + o0), sbase = pool_s + 4u * (unsigned)(h->w_sc[b][t] + o0);
+                for (int c = lane; c < nc; c += 32) {
+                    uint4 dsc;
+                    dsc.x = dbase + 128u * c;
+                    dsc.y = sbase + 128u * c;
+                    dsc.z = (unsigned)min(32, n - 32 * c) | ((unsigned)t << 8) | (ak << 16);
+                    dsc.w = __float_as_uint(rest);
+                    chunks[(size_t)cw * kMaxChunk + nch + c] = dsc;
+                }
+                nch += nc;
+            }
+            __syncwarp();
             // ---- P1: essential postings that can still reach the threshold claim their document's group
             bool kept_any = false;
-            for (unsigned m = emask; m; m &= m - 1) {
-                const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                kept_any |= pass_claim(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
+            if (p.debug & 16) {
+            } else if (chunk_ok) {
+                kept_any = chunks_claim(chunk_s, nch, theta, sh, gmask, tagv, lane);
+            } else {
+                for (unsigned m = emask; m; m &= m - 1) {
+                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                    kept_any |= pass_claim(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
+                }
             }
             const bool warp_kept = __ballot_sync(0xffffffffu, kept_any) != 0u;
             PROF(3);
@@ -732,28 +977,44 @@ struct Fast {
             if (warp_kept) {  // no surviving essential posting: nothing in this sub-range can score
                 // ---- P2: postings that do not read back their own claim set the contested bit; non-essential postings
                 //      that find their own document claimed do the same
-                for (unsigned m = emask; m; m &= m - 1) {
-                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                    pass_mark_e(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
+                if (p.debug & 2) {
+                } else if (chunk_ok) {
+                    chunks_mark(chunk_s, nch, theta, sh, gmask, tagv, lane);
+                } else {
+                    for (unsigned m = emask; m; m &= m - 1) {
+                        const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                        pass_mark_e(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
+                    }
                 }
+                if (!(p.debug & 1))
                 for (unsigned m = nmask; m; m &= m - 1) {
                     const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                    pass_probe_n(g, sh, gmask, tagv, lane);
+                    pass_probe_n_vec(g, sh, gmask, tagv, lane);
                 }
                 PROF(5);
                 __syncwarp();
                 // ---- P3: sole hits score directly; contested winners and documents without a winner go to the slow list
                 int slow_n = 0;
-                for (unsigned m = emask; m; m &= m - 1) {
-                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                    pass_resolve(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane, b, T, cw, pool_s, slow_n);
+                if (p.debug & 4) {
+                } else if (chunk_ok) {
+                    chunks_resolve(chunk_s, nch, theta, sh, gmask, tagv, lane, b, T, cw, pool_s, slow_n);
+                } else {
+                    for (unsigned m = emask; m; m &= m - 1) {
+                        const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                        pass_resolve(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane, b, T, cw, pool_s, slow_n);
+                    }
                 }
                 PROF(7);
                 __syncwarp();
                 // ---- P5: the claiming postings clean their tags (tags are all-clean between windows)
-                for (unsigned m = emask; m; m &= m - 1) {
-                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                    pass_clean(g, theta, kept_posting(0.0f, g.rest, theta), sh, tagv, lane);
+                if (p.debug & 8) {
+                } else if (chunk_ok) {
+                    chunks_clean(chunk_s, nch, theta, sh, tagv, lane);
+                } else {
+                    for (unsigned m = emask; m; m &= m - 1) {
+                        const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                        pass_clean(g, theta, kept_posting(0.0f, g.rest, theta), sh, tagv, lane);
+                    }
                 }
                 PROF(9);
                 // ---- P4: the rest of the slow list
@@ -812,7 +1073,9 @@ struct Fast {
             }
             if (tid == 0) { h->cb_cnt = 0; h->theta = 0.0f; }
             __syncthreads();
-            if (warp == 0) {
+            Layout lay;
+            lay.cap = 0; lay.off = 0; lay.ne = -1; lay.live = -1; lay.sh = 0;  // forces the first share-out
+            if (warp == NW) {
                 // pruning bounds from the column maxima
                 const long long df0 = (lane < T) ? h->t_df[lane] : 0;
                 long long tot = df0;
@@ -838,12 +1101,12 @@ struct Fast {
                     if (tot > 0) atomicAdd(&p.ctrl->posting_count, (unsigned long long)tot);
                 }
                 __syncwarp();
-                if (tot > 0) issue_loads(0, T);
+                if (tot > 0) issue_loads(0, T, lay);
             }
             __syncthreads();
             PROF(13);
             if (h->total_df > 0) {
-                if (warp == 0) producer(T, ph_data0, ph_data1, ph_free0, ph_free1);
+                if (warp == NW) producer(T, lay, ph_data0, ph_data1, ph_free0, ph_free1);
                 else consumer(T, k, ph_meta0, ph_meta1);
             }
             __syncthreads();
@@ -851,7 +1114,7 @@ struct Fast {
             finalize(q, T);
             PROF(15);
         }
-        PROF_FLUSH(tid == 32);
+        PROF_FLUSH(tid == 0);
     }
 
     // Sort the surviving candidates, pad with untouched documents if fewer than k matched, write the result row.
@@ -934,6 +1197,8 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.route_all_general = (!ix->nonneg) || (a.mask != nullptr) || (a.k > 2048) || env_int("BM25CU_FORCE_GENERAL", 0);
     const int budget = ix->max_smem_optin / (ctas_per_sm > 0 ? ctas_per_sm : 1) - (ctas_per_sm > 1 ? 1024 : 0);
     const int nw = threads / 32 - 1;
+    p.nwarps = nw;
+    p.debug = env_int("BM25CU_DEBUG_SKIP", 0);
     // pool: 4-byte slots per stage
     int pool = env_int("BM25CU_POOL", ctas_per_sm > 1 ? 6144 : 14336);
     pool = (pool + 3) & ~3;

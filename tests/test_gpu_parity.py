@@ -185,7 +185,8 @@ def test_random_corpus_vs_c_oracle(k):
     check_topk_rows(ids, sc, rid, rsc, dense_fn if k <= 100 else None, what=f"random k={k}")
     # small stage / tag settings force many windows and the same answer
     for env in ({"BM25CU_POOL": "1024", "BM25CU_TAG": "4096"}, {"BM25CU_THREADS": "256", "BM25CU_CTAS_PER_SM": "2"},
-                {"BM25CU_MAXSHIFT": "0"}, {"BM25CU_PRUNE": "0"}, {"BM25CU_MAXSHIFT": "1", "BM25CU_TAG": "8192"}):
+                {"BM25CU_MAXSHIFT": "0"}, {"BM25CU_PRUNE": "0"}, {"BM25CU_MAXSHIFT": "1", "BM25CU_TAG": "8192"},
+                {"BM25CU_THREADS": "128", "BM25CU_PRUNE": "0"}, {"BM25CU_THREADS": "1024"}):
         old = {kk: os.environ.get(kk) for kk in env}
         os.environ.update(env)
         try:

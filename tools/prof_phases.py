@@ -26,4 +26,5 @@ print(st)
 print('consumer cycles total (sum over CTAs, thread ctid0):', tot, 'per CTA', tot/148, 'kernel ms', st['fast_kernel_ms'], 'cycles@1.965GHz', st['fast_kernel_ms']*1.965e6)
 for i in range(16):
     print(f"{i:2d} {names[i]:22s} {p[i]:>14d} {100*p[i]/max(tot,1):6.2f}%")
+print('producer: loop-top', p[24], 'wait data', p[25], 'analysis+publish', p[26], 'wait free', p[27], 'issue', p[28])
 print('windows', p[16], 'ME', p[17], 'MN', p[18], 'active windows', p[19], 'keptE', p[20], 'R', p[21], 'compactions', p[22])
