@@ -339,8 +339,15 @@ def main():
     alg_bytes = int(stats_acc[-1]["algorithmic_bytes"])
     peak, peak_src = peaks()
     achieved = alg_bytes / (fast_ms / 1000.0) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if world == 1 and args.shape == "msmarco" and k == 10 and os.path.exists(tpath):
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+            traffic = float(json.load(open(tpath))["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "retrieve_fast_kernel",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "retrieve_fast_kernel",
                 "kernel_ms": fast_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
