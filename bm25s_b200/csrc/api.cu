@@ -1,6 +1,8 @@
 // extern "C" entry points of the query path (declared in include/bm25cu.h).
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace bm25cu;
@@ -17,7 +19,15 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
     BM25CU_CHECK(cudaMemsetAsync(d_ctrl, 0, sizeof(Ctrl), ix->stream));
     int launches = 0;
     BM25CU_CHECK(cudaEventRecord(ix->ev[1], ix->stream));
-    if ((rc = launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches))) return rc;
+    {
+        // BM25CU_KERNEL selects the structure of K1: 5 = per-warp document sub-ranges (retrieve_fast.cu),
+        // 6 = bit tags + streamed non-essential postings (retrieve_v6.cu)
+        const char *kv = getenv("BM25CU_KERNEL");
+        const int kernel = (kv && *kv) ? atoi(kv) : 5;
+        rc = (kernel == 6) ? launch_retrieve_v6(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
+                           : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
+        if (rc) return rc;
+    }
     BM25CU_CHECK(cudaEventRecord(ix->ev[2], ix->stream));
     if ((rc = launch_retrieve_general(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches))) return rc;
     BM25CU_CHECK(cudaEventRecord(ix->ev[3], ix->stream));

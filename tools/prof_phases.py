@@ -27,4 +27,5 @@ print('consumer cycles total (sum over CTAs, thread ctid0):', tot, 'per CTA', to
 for i in range(16):
     print(f"{i:2d} {names[i]:22s} {p[i]:>14d} {100*p[i]/max(tot,1):6.2f}%")
 print('producer: loop-top', p[24], 'wait data', p[25], 'analysis+publish', p[26], 'wait free', p[27], 'issue', p[28])
+print('v6: resolve pass (excl. final slow)', p[20], 'hash hits', p[18], 'overflow windows', p[19], 'slow docs (warp 0)', p[23])
 print('windows', p[16], 'ME', p[17], 'MN', p[18], 'active windows', p[19], 'keptE', p[20], 'R', p[21], 'compactions', p[22])
