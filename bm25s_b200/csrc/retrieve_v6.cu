@@ -4,25 +4,26 @@
 // with padded upper bounds, (score, ~doc) candidate keys); what differs is how a window is organised:
 //
 //   * only the ESSENTIAL tokens' postings (ids + scores) are staged in shared memory by the producer warp (bulk async
-//     copies, two stages). NON-ESSENTIAL tokens are never staged: the consumer warps stream their document ids
-//     straight from global memory in 512-posting blocks (four 16-byte loads per lane), block j of a column belonging to
-//     warp j mod NW for the whole query, every warp keeping its own cursor per token. No search for window
-//     boundaries is needed: a block is probed for the documents that fall into the current window and revisited in
-//     the next window if it reaches beyond it;
+//     copies, two stages). NON-ESSENTIAL tokens are never staged: for every window the producer finds the end of each
+//     non-essential column's window slice by a warp-cooperative 32-ary search in global memory (up to four columns
+//     searched together, one window ahead of the consumers) and publishes exact posting ranges; the consumer warps
+//     split those ranges by posting index and load their share straight into registers (up to 12 x 16 bytes per lane
+//     in flight, issued before the claim phase so that the latency hides behind it);
 //   * a window therefore spans as many documents as the tag array allows (2 bits per document: PRESENT and MULTI),
-//     not what a pool of all tokens' postings would cover - about half as many windows per query;
-//   * the consumer warps split a window's essential postings by POSTING INDEX (no per-warp document sub-ranges, no
+//     not what a pool of all tokens' postings would cover;
+//   * the consumer warps split a window's essential postings by POSTING INDEX too (no per-warp document sub-ranges, no
 //     boundary searches) and meet at named barriers between the phases:
-//       A  surviving essential postings set PRESENT with an atomic OR; one that finds it already set (another token
-//          hit the same document) sets MULTI
-//       C  non-essential postings whose document is PRESENT set MULTI and file (doc, token, posting index) in a
-//          small hash table
-//       D  essential postings read their document's bits: not MULTI -> the posting's score is the document's score
-//          (0 + s = s exactly); MULTI -> the slow list: the document is re-summed in query-token order (the
-//          reference's float32 order) from binary searches of the staged essential postings and hash look-ups of the
-//          non-essential ones; among a document's surviving essential postings the one with the smallest token slot
-//          emits
-//       E  the essential postings clear their tag bytes, the hash table is reset
+//       A   surviving essential postings set PRESENT with an atomic OR; one that finds it already set (another token
+//           hit the same document) sets MULTI
+//       C   non-essential postings whose document is PRESENT set MULTI and file (doc, token, posting index) in a
+//           small hash table
+//       D1  the scores of the hash entries are fetched (all loads in flight together); essential postings read their
+//           document's bits: not MULTI -> the posting's score is the document's score (0 + s = s exactly);
+//           MULTI -> the CTA's slow list
+//       D2  slow list, one thread per entry: the document is re-summed in query-token order (the reference's float32
+//           order) from binary searches of the staged essential postings and hash look-ups of the non-essential
+//           ones; among a document's surviving essential postings the one with the smallest token slot emits. The
+//           tags of the window are cleared.
 #include <cstdlib>
 
 #include "fast_common.cuh"
@@ -31,9 +32,9 @@ namespace bm25cu {
 namespace v6 {
 
 constexpr int kHash = 1024;     // entries of the per-window hash of non-essential contributions (power of two)
-constexpr int kHashMax = 768;   // inserts beyond this switch the window to global binary searches
-constexpr int kRows = 4;        // non-essential block: kRows rows of 128 postings (one 16-byte load per lane and row)
-constexpr int kBlkShift = 9;    // log2(128 * kRows)
+constexpr int kHashMax = 768;   // inserts beyond this switch the window to binary searches in global memory
+constexpr int kSlowCap = 1024;  // entries of the CTA's slow list (more: resolved on the spot)
+constexpr int kPre = 8;         // rows of 128 non-essential postings a warp keeps in flight (one 16-byte load per lane and row)
 
 struct Hdr {
     uint64_t bar_data[2];   // stage b landed                        (producer waits)
@@ -43,27 +44,28 @@ struct Hdr {
     long long t_cur[kTokArr];
     long long t_end[kTokArr];
     long long t_df[kTokArr];
-    long long w_goff[2][kTokArr];  // global posting index of the token's first posting in the window (frozen once non-essential)
+    long long w_goff[2][kTokArr];  // global posting index of the token's first posting in the window
     float t_max[kTokArr];     // largest score of the token's column
     float t_rest[kTokArr];    // upper bound of what the OTHER query tokens can add to a document
     float t_nebound[kTokArr]; // upper bound of a document hit only by this token and tokens with smaller maxima
     int t_n[2][kTokArr];      // staged postings of stage b (essential tokens)
     int t_ne[2][kTokArr];     // 1: token is non-essential in stage b
-    int w_cnt[2][kTokArr];    // essential postings of the token inside the window
-    int w_doc[2][kTokArr];    // pool slot of the first window document id
+    int w_cnt[2][kTokArr];    // postings of the token inside the window
+    int w_doc[2][kTokArr];    // pool slot of the first window document id (essential tokens)
     int w_sc[2][kTokArr];     // pool slot of the first window score
-    int n_cur[kMaxWarps][kTokArr];  // per consumer warp: next non-essential block of the token (relative to the column's first block), -1: not started
-    int2 w_slow[kMaxWarps][32];     // per-warp slow list (doc, token slot)
+    int2 slow[kSlowCap];      // slow list (doc, token slot)
     int hk[kHash];            // hash: document (-1 empty)
     int ht[kHash];            //       token slot
     int hi[kHash];            //       posting index relative to the column start
-    int w_base[2];            // first document of the window, rounded down to a multiple of 4
+    float hv[kHash];          //       score (fetched in D1)
+    int w_base[2];            // first document of the window, a multiple of 4
     int w_end[2];             // one past the last document of the window
     int w_last[2];            // 1 if this is the query's last window
     int w_ME[2];              // essential postings in the window
+    int w_MN[2];              // non-essential postings in the window
     unsigned int w_emask[2];  // tokens with essential postings in the window
-    unsigned int w_nmask[2];  // non-essential tokens
-    unsigned int h_cnt, h_over;
+    unsigned int w_nmask[2];  // tokens with non-essential postings in the window
+    unsigned int h_cnt, h_over, slow_cnt;
     unsigned int q_slot;
     unsigned int cb_cnt;
     float theta;
@@ -76,6 +78,7 @@ __device__ __forceinline__ unsigned atoms_or(uint32_t a, unsigned v) {
     return o;
 }
 __device__ __forceinline__ void reds_or(uint32_t a, unsigned v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128z(uint32_t a) { asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory"); }
 __device__ __forceinline__ uint4 ldg128(const int32_t *ptr) { return __ldg(reinterpret_cast<const uint4 *>(ptr)); }
 
 // Tag of document d: byte at tagv + (d >> 2) (tagv already has the window base folded in); bit (d & 3) is PRESENT,
@@ -98,7 +101,9 @@ __device__ __forceinline__ void pass_claim(const Seg &g, float theta, bool allke
     int rem = g.n - lane;  // > 32 * u  <=>  element (it + u) * 32 + lane exists
     for (int it = 0; it < iters; it += 4, ad += 512, as += 512, rem -= 128) {
         float sv[4];
-        unsigned d[4];
+        unsigned d[4], old[4], bit[4];
+        uint32_t aw[4];
+        bool kp[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const bool v = rem > 32 * u;
@@ -106,18 +111,20 @@ __device__ __forceinline__ void pass_claim(const Seg &g, float theta, bool allke
             d[u] = v ? lds32(ad + 128 * u) : 0u;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (rem > 32 * u && (allkept || kept_posting(sv[u], g.rest, theta))) {
-                const uint32_t a = tag_addr(tagv, d[u]);
-                const unsigned bit = tag_bit(a, d[u]);
-                const unsigned old = atoms_or(a & ~3u, 1u << bit);
-                if ((old >> bit) & 1u) reds_or(a & ~3u, 16u << bit);
-            }
+        for (int u = 0; u < 4; ++u) {  // all atomics are issued before any result is looked at
+            kp[u] = rem > 32 * u && (allkept || kept_posting(sv[u], g.rest, theta));
+            const uint32_t a = tag_addr(tagv, d[u]);
+            bit[u] = tag_bit(a, d[u]);
+            aw[u] = a & ~3u;
+            old[u] = kp[u] ? atoms_or(aw[u], 1u << bit[u]) : 0u;
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (kp[u] && ((old[u] >> bit[u]) & 1u)) reds_or(aw[u], 16u << bit[u]);
     }
 }
 
-// E: surviving essential postings clear their tag byte (all four documents of the byte are done by then)
+// per-posting tag clean-up (used when the window holds few essential postings; otherwise the tag range is zeroed)
 __device__ __forceinline__ void pass_clean(const Seg &g, float theta, bool allkept, uint32_t tagv, int lane) {
     const int iters = (g.n + 31) >> 5;
     uint32_t ad = g.docs + (lane << 2), as = g.sc + (lane << 2);
@@ -142,12 +149,12 @@ struct Fast {
     static constexpr int CNT = NT - 32;  // consumer threads
     static constexpr int NW = CNT / 32;  // consumer warps
     Hdr *h;
-    int slow_tot = 0;  // profile counter
     unsigned long long *cb;   // [cbcap]
     int *pool;                // [2][poolcap] 4-byte slots: document ids and float scores of the essential tokens
     unsigned char *tag;       // [tagcap]
     const FastParams &p;
     unsigned long long *spill;
+    bool hash_dirty = false;  // the hash holds entries of the previous window (cleared in the next claim phase)
 
     __device__ Fast(const FastParams &pp, unsigned char *smem) : p(pp) {
         h = reinterpret_cast<Hdr *>(smem);
@@ -180,7 +187,6 @@ struct Fast {
         if (slot < (unsigned)p.cbcap) cb[slot] = c;
         else if (slot - p.cbcap < (unsigned)p.spillcap) spill[slot - p.cbcap] = c;
     }
-
     // bitonic sort of key[0..P) descending (P power of two, <= cbcap), shared memory
     template <bool CONS>
     __device__ void sort_desc(unsigned long long *key, int P, int id, int nthr) {
@@ -315,11 +321,65 @@ struct Fast {
         return lo + __popc(__ballot_sync(0xffffffffu, pr));
     }
 
+    // For up to four columns at once: lo[j] <- first index in [lo[j], end[j]) whose document id is >= bound (end[j] if
+    // none). Whole warp: every round probes 32 positions per column, the columns' loads in flight together. est[j] is
+    // the expected distance; the searched range grows eightfold whenever everything in it is below the bound.
+    __device__ __forceinline__ void search4(int nj, long long (&lo)[4], const long long (&end)[4], long long (&est)[4], int bound) {
+        const int lane = threadIdx.x & 31;
+        const int32_t *ind = p.indices;
+        long long hi[4];
+        bool done[4], known[4];  // known: the element at hi is >= bound (otherwise hi is just the current cap)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            done[j] = (j >= nj) || (lo[j] >= end[j]);
+            known[j] = false;
+            hi[j] = done[j] ? lo[j] : min(end[j], lo[j] + est[j]);
+        }
+        for (int round = 0;; ++round) {
+            int v[4];
+            long long step[4];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] = 0x7fffffff;
+                step[j] = 1;
+                if (!done[j]) {
+                    any = true;
+                    step[j] = ((hi[j] - lo[j] - 1) >> 5) + 1;  // hi > lo here
+                    const long long idx = lo[j] + lane * step[j];
+                    if (idx < hi[j]) v[j] = ind[idx];
+                }
+            }
+            if (!any) break;
+            if (round > 256) { atomicOr(&p.ctrl->error, 2u); break; }  // cannot happen (the range shrinks 32-fold per round)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (done[j]) continue;
+                const int c = __popc(__ballot_sync(0xffffffffu, v[j] < bound));  // sorted ids: a prefix of the lanes
+                if (step[j] == 1) {
+                    const long long n = hi[j] - lo[j];
+                    if (c < n) { lo[j] += c; done[j] = true; continue; }
+                    lo[j] = hi[j];
+                } else {
+                    const long long cand_hi = lo[j] + c * step[j];
+                    if (c < 32 && cand_hi < hi[j]) { hi[j] = cand_hi; known[j] = true; }
+                    if (c > 0) lo[j] += (c - 1) * step[j] + 1;
+                }
+                if (lo[j] >= hi[j]) {  // everything below hi is smaller than the bound
+                    if (known[j] || hi[j] >= end[j]) done[j] = true;
+                    else { est[j] <<= 3; hi[j] = min(end[j], lo[j] + est[j]); }
+                }
+            }
+        }
+    }
+
     // ------------------------------------------------------------------------------------------ producer warp
     __device__ void producer(int T, Layout &L, uint32_t &ph_data0, uint32_t &ph_data1, uint32_t &ph_free0, uint32_t &ph_free1) {
         const int lane = threadIdx.x & 31;
         int b = 0;
         int nwin = 0;
+        int prev_end = -1;  // end of the previous window
+        const long long span = (long long)p.tagcap << 2;
         PROF_DECL;
         for (;;) {
             PROF(24);
@@ -328,13 +388,14 @@ struct Fast {
             PROF(25);
             const int *bp = pool + (size_t)b * p.poolcap;
             int n0 = 0, off0 = 0, first = 0x7fffffff, e = 0x7fffffff, last0 = -1, ne = 0;
-            long long cur = 0, tend = 0;
+            long long cur = 0, tend = 0, df = 0;
             if (lane < T) {
                 n0 = h->t_n[b][lane];
                 off0 = h->w_doc[b][lane];
                 ne = h->t_ne[b][lane];
                 cur = h->t_cur[lane];
                 tend = h->t_end[lane];
+                df = h->t_df[lane];
                 if (n0 > 0) {
                     first = bp[off0];
                     last0 = bp[off0 + n0 - 1];
@@ -344,8 +405,10 @@ struct Fast {
             const int lastmax = __reduce_max_sync(0xffffffffu, last0);
             first = __reduce_min_sync(0xffffffffu, first);
             e = __reduce_min_sync(0xffffffffu, e);
-            const int base = first & ~3;
-            const long long span = (long long)p.tagcap << 2;
+            // windows follow each other without a gap unless the next essential posting lies beyond a whole tag span
+            int base = first & ~3;
+            bool jump = true;
+            if (prev_end >= 0 && (long long)first < (long long)(prev_end & ~3) + span) { base = prev_end & ~3; jump = false; }
             const int cap_end = ((long long)base + span > 0x7fffffffll) ? 0x7fffffff : (int)(base + span);
             int wend = min(e, cap_end);
             if (lastmax < wend - 1) wend = lastmax + 1;
@@ -361,15 +424,50 @@ struct Fast {
             }
             const int ME = __reduce_add_sync(0xffffffffu, c0);
             const unsigned emask = __ballot_sync(0xffffffffu, c0 > 0);
-            const unsigned nmask = __ballot_sync(0xffffffffu, lane < T && ne && cur < tend);
+            // non-essential columns: exact window slices by searching global memory, four columns at a time
+            unsigned nem = __ballot_sync(0xffffffffu, lane < T && ne && cur < tend);
+            PROF(26);
+            while (nem) {
+                int tj[4];
+                long long lo[4], en[4], est[4];
+                int nj = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    tj[j] = -1; lo[j] = 0; en[j] = 0; est[j] = 64;
+                    if (nem) {
+                        tj[j] = __ffs(nem) - 1;
+                        nem &= nem - 1;
+                        nj = j + 1;
+                        lo[j] = __shfl_sync(0xffffffffu, cur, tj[j]);
+                        en[j] = __shfl_sync(0xffffffffu, tend, tj[j]);
+                        const long long dfj = __shfl_sync(0xffffffffu, df, tj[j]);
+                        const long long nd = p.n_docs > 0 ? p.n_docs : 1;
+                        est[j] = 64 + (2 * dfj * (long long)(wend - base)) / nd;
+                    }
+                }
+                if (jump && prev_end >= 0) {  // skip the postings between the previous window and this one
+                    long long est2[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) est2[j] = est[j];
+                    search4(nj, lo, en, est2, base);
+                }
+                long long st[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st[j] = lo[j];
+                search4(nj, lo, en, est, wend);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (lane == tj[j]) { cur = st[j]; c0 = (int)(lo[j] - st[j]); }
+            }
+            PROF(29);
+            const int MN = __reduce_add_sync(0xffffffffu, (lane < T && ne) ? c0 : 0);
+            const unsigned nmask = __ballot_sync(0xffffffffu, lane < T && ne && c0 > 0);
             bool more = false;
             if (lane < T) {
                 h->w_cnt[b][lane] = c0;
                 h->w_goff[b][lane] = cur;
-                if (!ne) {
-                    h->t_cur[lane] = cur + c0;
-                    more = (cur + c0) < tend;
-                }
+                h->t_cur[lane] = cur + c0;
+                if (!ne) more = (cur + c0) < tend;
             }
             const bool any_more = __any_sync(0xffffffffu, more);
             if (lane == 0) {
@@ -377,12 +475,13 @@ struct Fast {
                 h->w_end[b] = wend;
                 h->w_last[b] = any_more ? 0 : 1;
                 h->w_ME[b] = ME;
+                h->w_MN[b] = MN;
                 h->w_emask[b] = emask;
                 h->w_nmask[b] = nmask;
             }
+            prev_end = wend;
             __syncwarp();
             if (lane == 0) mbar_arrive(&h->bar_meta[b]);  // release: metadata visible to the consumers
-            PROF(26);
             ++nwin;
             if (!any_more) break;
             if (nwin >= 2) {  // the other stage was used by window nwin-2: wait until the consumers released it
@@ -429,6 +528,19 @@ struct Fast {
             if (pre >= hi) break;
         }
     }
+    // Calls f(token, first global posting index, count) for every column segment of the flat non-essential range [lo, hi)
+    template <class F>
+    __device__ __forceinline__ void for_nsegs(int b, unsigned nmask, int lo, int hi, F f) {
+        int pre = 0;
+        for (unsigned m = nmask; m; m &= m - 1) {
+            const int t = __ffs(m) - 1;
+            const int c = h->w_cnt[b][t];
+            const int s0 = max(lo, pre), s1 = min(hi, pre + c);
+            if (s1 > s0) f(t, h->w_goff[b][t] + (s0 - pre), s1 - s0);
+            pre += c;
+            if (pre >= hi) break;
+        }
+    }
 
     // C, one hit: the document is PRESENT and a non-essential posting contributes to it
     __device__ __forceinline__ void ne_hit(unsigned d, uint32_t a, int t, long long gidx, long long beg) {
@@ -442,94 +554,88 @@ struct Fast {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + gidx));
     }
 
-#ifdef BM25CU_PROFILE
-#define DBG_NE(dd, xx, path) do { if ((int)(dd) == p.dbg_doc) { const unsigned long long _s = atomicAdd(&p.ctrl->prof[29], 1ull); if (_s < 4) p.ctrl->prof[8 + _s] = 0x1000000000000000ull | ((unsigned long long)(path) << 56) | ((unsigned long long)(xx) << 40) | ((unsigned long long)t << 32) | (unsigned)wbase; } } while (0)
-#define DBG_E(dd, xx, sl) do { if ((int)(dd) == p.dbg_doc) { const unsigned long long _s = atomicAdd(&p.ctrl->prof[30], 1ull); if (_s < 4) p.ctrl->prof[12 + _s] = 0x2000000000000000ull | ((unsigned long long)(sl) << 56) | ((unsigned long long)(xx) << 40) | ((unsigned long long)g.t << 32) | (unsigned)__float_as_uint(theta); } } while (0)
-#else
-#define DBG_NE(dd, xx, path)
-#define DBG_E(dd, xx, sl)
-#endif
-    // C: this warp's blocks of non-essential token t that intersect the window [wbase, wend)
-    __device__ __forceinline__ void ne_probe(int b, int t, int cw, int lane, int wbase, int wend, uint32_t tagv) {
-        const long long beg = h->t_beg[t], end = h->t_end[t];
-        const long long gb0 = beg >> kBlkShift;
-        int r = h->n_cur[cw][t];
-        if (r < 0) {
-            const int r0 = (int)((h->w_goff[b][t] >> kBlkShift) - gb0);
-            r = r0 + (((cw - r0) % NW) + NW) % NW;  // first block >= r0 that belongs to this warp
-        }
-        const unsigned wlen = (unsigned)(wend - wbase);
+    // C: rows of 128 postings (16-byte aligned) of a column segment [g0, g0 + n); lane l holds postings 4 l .. 4 l + 3
+    __device__ __forceinline__ void ne_load_rows(long long abase, long long g1, int r0, int lane, uint4 (&v)[kPre]) {
         const int32_t *ind = p.indices;
-        // a block is kRows rows of 128 postings; lane l holds postings [128 j + 4 l, 128 j + 4 l + 4) of row j
-        long long i0 = (gb0 + r) << kBlkShift;
-        uint4 cur4[kRows];
 #pragma unroll
-        for (int j = 0; j < kRows; ++j) {
-            cur4[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (i0 + j * 128 + lane * 4 < end) cur4[j] = ldg128(ind + i0 + j * 128 + lane * 4);
+        for (int j = 0; j < kPre; ++j) {
+            const long long i4 = abase + (long long)(r0 + j) * 128 + lane * 4;
+            v[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (i4 < g1) v[j] = ldg128(ind + i4);
         }
-        while (i0 < end) {
-            const long long n0 = i0 + ((long long)NW << kBlkShift);  // next block of this warp (prefetched)
-            uint4 nxt4[kRows];
+    }
+    __device__ __forceinline__ void ne_probe_rows(int t, long long beg, long long abase, long long g0, long long g1, int r0, int lane,
+                                                  uint32_t tagv, const uint4 (&v)[kPre]) {
 #pragma unroll
-            for (int j = 0; j < kRows; ++j) {
-                nxt4[j] = make_uint4(0u, 0u, 0u, 0u);
-                if (n0 + j * 128 + lane * 4 < end) nxt4[j] = ldg128(ind + n0 + j * 128 + lane * 4);
-            }
-            const bool full = (i0 >= beg) && (i0 + (1 << kBlkShift) <= end);
-            int lastdoc;
-            bool inside = false;
-            if (full) {
-                const int firstdoc = (int)__shfl_sync(0xffffffffu, cur4[0].x, 0);
-                lastdoc = (int)__shfl_sync(0xffffffffu, cur4[kRows - 1].w, 31);
-                inside = firstdoc >= wbase && lastdoc < wend;
-            }
-            if (inside) {  // the whole block lies in the window: no range checks
+        for (int j = 0; j < kPre; ++j) {
+            const long long rb = abase + (long long)(r0 + j) * 128;
+            if (rb >= g1) break;
+            const long long i4 = rb + lane * 4;
+            const unsigned d[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            if (rb >= g0 && rb + 128 <= g1) {  // the whole row belongs to the segment
+                unsigned x[4];
 #pragma unroll
-                for (int j = 0; j < kRows; ++j) {
-                    const unsigned d[4] = {cur4[j].x, cur4[j].y, cur4[j].z, cur4[j].w};
-                    unsigned x[4];
+                for (int u = 0; u < 4; ++u) x[u] = lds8(tag_addr(tagv, d[u]));
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) x[u] = lds8(tag_addr(tagv, d[u]));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        DBG_NE(d[u], x[u], 1);
-                        if ((x[u] >> (d[u] & 3u)) & 1u) ne_hit(d[u], tag_addr(tagv, d[u]), t, i0 + j * 128 + lane * 4 + u, beg);
-                    }
-                }
+                for (int u = 0; u < 4; ++u)
+                    if ((x[u] >> (d[u] & 3u)) & 1u) ne_hit(d[u], tag_addr(tagv, d[u]), t, i4 + u, beg);
             } else {
-                int mx = -1;
 #pragma unroll
-                for (int j = 0; j < kRows; ++j) {
-                    const unsigned d[4] = {cur4[j].x, cur4[j].y, cur4[j].z, cur4[j].w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const long long idx = i0 + j * 128 + lane * 4 + u;
-                        if (full || (idx >= beg && idx < end)) {
-                            mx = max(mx, (int)d[u]);
-                            if ((unsigned)((int)d[u] - wbase) < wlen) {
-                                const unsigned x = lds8(tag_addr(tagv, d[u]));
-                                DBG_NE(d[u], x, 2);
-                                if ((x >> (d[u] & 3u)) & 1u) ne_hit(d[u], tag_addr(tagv, d[u]), t, idx, beg);
-                            }
-                        }
+                for (int u = 0; u < 4; ++u) {
+                    const long long idx = i4 + u;
+                    if (idx >= g0 && idx < g1) {
+                        const unsigned x = lds8(tag_addr(tagv, d[u]));
+                        if ((x >> (d[u] & 3u)) & 1u) ne_hit(d[u], tag_addr(tagv, d[u]), t, idx, beg);
                     }
                 }
-                if (!full) lastdoc = __reduce_max_sync(0xffffffffu, mx);
             }
-            if (lastdoc >= wend) break;  // the block reaches into the next window: revisit it there
-            r += NW;
-            i0 = n0;
-#pragma unroll
-            for (int j = 0; j < kRows; ++j) cur4[j] = nxt4[j];
         }
-        __syncwarp();
-        if (lane == 0) h->n_cur[cw][t] = r;
     }
 
-    // D on one segment: documents that are not MULTI score directly; the others go to the warp's slow list
+    // Re-sums one document in query-token order. use_hv: the hash entries' scores are in shared memory (D2),
+    // otherwise they are read from global memory.
+    __device__ __forceinline__ void resolve_one(int b, int T, uint32_t pool_s, float theta, int d, int myslot, bool use_hv) {
+        const bool over = h->h_over != 0u;
+        float sum = 0.0f;
+        int min_e = 99;
+        for (int t = 0; t < T; ++t) {
+            const int c = h->w_cnt[b][t];
+            if (c == 0) continue;
+            if (h->t_ne[b][t]) {
+                if (!over) {
+                    unsigned i = ((unsigned)d * 2654435761u) >> 22;
+                    for (;;) {
+                        const int kk = h->hk[i];
+                        if (kk == -1) break;
+                        if (kk == d && h->ht[i] == t) {
+                            sum = __fadd_rn(sum, use_hv ? h->hv[i] : p.data[h->t_beg[t] + h->hi[i]]);
+                            break;
+                        }
+                        i = (i + 1u) & (unsigned)(kHash - 1);
+                    }
+                } else {  // hash overflow in this window: search the column's window slice in global memory
+                    const long long g0 = h->w_goff[b][t];
+                    long long lo = g0, hi = g0 + c;
+                    while (lo < hi) { const long long m = (lo + hi) >> 1; if (p.indices[m] < d) lo = m + 1; else hi = m; }
+                    if (lo < g0 + c && p.indices[lo] == d) sum = __fadd_rn(sum, p.data[lo]);
+                }
+            } else {
+                const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
+                int lo = 0, hi = c;
+                while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < d) lo = m + 1; else hi = m; }
+                if (lo < c && (int)lds32(dt + 4u * lo) == d) {
+                    const float v = ldsf(pool_s + 4u * (unsigned)(h->w_sc[b][t] + lo));
+                    sum = __fadd_rn(sum, v);
+                    if (t < min_e && kept_posting(v, h->t_rest[t], theta)) min_e = t;
+                }
+            }
+        }
+        if (min_e == myslot && sum > theta) emit(sum, d);
+    }
+
+    // D1 on one segment: documents that are not MULTI score directly; the others go to the CTA's slow list
     __device__ __forceinline__ void pass_resolve(const Seg &g, float theta, bool allkept, uint32_t tagv, int lane, int b, int T,
-                                                 int cw, uint32_t pool_s, int &slow_n) {
+                                                 uint32_t pool_s) {
         const int iters = (g.n + 31) >> 5;
         uint32_t ad = g.docs + (lane << 2), as = g.sc + (lane << 2);
         int rem = g.n - lane;
@@ -549,72 +655,36 @@ struct Fast {
             unsigned act = 0, slow = 0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                DBG_E(d[u], x[u], v[u] ? 1 : 0);
                 if (!v[u]) continue;
                 if ((x[u] >> (4u + (d[u] & 3u))) & 1u) slow |= 1u << u;
                 else if (sv[u] > theta) act |= 1u << u;
             }
             if (__ballot_sync(0xffffffffu, (act | slow) != 0u)) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 4; ++u)
                     if ((act >> u) & 1u) emit(sv[u], (int)d[u]);
-                    const unsigned m = __ballot_sync(0xffffffffu, (slow >> u) & 1u);
-                    if (m) {
-                        const int cnt = __popc(m);
-                        slow_tot += cnt;
-                        if (slow_n + cnt > 32) { resolve_slow(b, T, cw, pool_s, theta, slow_n); slow_n = 0; }
-                        if ((slow >> u) & 1u) h->w_slow[cw][slow_n + __popc(m & ((1u << lane) - 1u))] = make_int2((int)d[u], g.t);
-                        slow_n += cnt;
-                        __syncwarp();
-                    }
-                }
-            }
-        }
-    }
-
-    // Slow list: one lane per listed (document, token slot) re-sums the document in query-token order.
-    __device__ void resolve_slow(int b, int T, int cw, uint32_t pool_s, float theta, int n) {
-        const int lane = threadIdx.x & 31;
-        __syncwarp();
-        if (lane < n) {
-            const int2 e = h->w_slow[cw][lane];
-            const int d = e.x, myslot = e.y;
-            const bool over = h->h_over != 0u;
-            float sum = 0.0f;
-            int min_e = 99;
-            for (int t = 0; t < T; ++t) {
-                if (h->t_ne[b][t]) {
-                    long long gi = -1;
-                    if (!over) {
-                        unsigned i = ((unsigned)d * 2654435761u) >> 22;
-                        for (;;) {
-                            const int kk = h->hk[i];
-                            if (kk == -1) break;
-                            if (kk == d && h->ht[i] == t) { gi = h->t_beg[t] + h->hi[i]; break; }
-                            i = (i + 1u) & (unsigned)(kHash - 1);
+                // slow entries of the whole group: one atomic per warp
+                const int mine = __popc(slow);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total) {
+                    unsigned base0 = 0;
+                    if (lane == 31) base0 = atomicAdd(&h->slow_cnt, (unsigned)total);
+                    base0 = __shfl_sync(0xffffffffu, base0, 31);
+                    unsigned at = base0 + (unsigned)(incl - mine);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if ((slow >> u) & 1u) {
+                            if (at < (unsigned)kSlowCap) h->slow[at] = make_int2((int)d[u], g.t);
+                            else resolve_one(b, T, pool_s, theta, (int)d[u], g.t, false);  // list full: on the spot
+                            ++at;
                         }
-                    } else {  // hash overflow in this window: search the column in global memory
-                        long long lo = h->w_goff[b][t], hi = h->t_end[t];
-                        while (lo < hi) { const long long m = (lo + hi) >> 1; if (p.indices[m] < d) lo = m + 1; else hi = m; }
-                        if (lo < h->t_end[t] && p.indices[lo] == d) gi = lo;
-                    }
-                    if (gi >= 0) sum = __fadd_rn(sum, p.data[gi]);
-                } else {
-                    const int c = h->w_cnt[b][t];
-                    if (c == 0) continue;
-                    const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
-                    int lo = 0, hi = c;
-                    while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < d) lo = m + 1; else hi = m; }
-                    if (lo < c && (int)lds32(dt + 4u * lo) == d) {
-                        const float v = ldsf(pool_s + 4u * (unsigned)(h->w_sc[b][t] + lo));
-                        sum = __fadd_rn(sum, v);
-                        if (t < min_e && kept_posting(v, h->t_rest[t], theta)) min_e = t;
                     }
                 }
             }
-            if (min_e == myslot && sum > theta) emit(sum, d);
         }
-        __syncwarp();
     }
 
     // ------------------------------------------------------------------------------------------ consumer warps
@@ -625,8 +695,6 @@ struct Fast {
         float theta = 0.0f;
         int b = 0;
         bool first_window = true;
-        if (lane < kTokArr) h->n_cur[cw][lane] = -1;
-        __syncwarp();
         PROF_DECL;
         for (;;) {
             PROF(0);
@@ -638,10 +706,25 @@ struct Fast {
             const float *bpf = reinterpret_cast<const float *>(bp);
             const uint32_t pool_s = smem_u32(bp);
             const int wbase = h->w_base[b], wend = h->w_end[b];
-            const uint32_t tagv = smem_u32(tag) - (uint32_t)(wbase >> 2);  // tag byte of document d: tagv + (d >> 2)
+            const uint32_t tag_s = smem_u32(tag);
+            const uint32_t tagv = tag_s - (uint32_t)(wbase >> 2);  // tag byte of document d: tagv + (d >> 2)
             const int last = h->w_last[b];
             const unsigned emask = h->w_emask[b], nmask = h->w_nmask[b];
-            const int ME = h->w_ME[b];
+            const int ME = h->w_ME[b], MN = h->w_MN[b];
+
+            // ---- this warp's first non-essential rows go in flight right away
+            const int nlo = (int)(((long long)MN * cw) / NW), nhi = (int)(((long long)MN * (cw + 1)) / NW);
+            uint4 pre[kPre];
+            long long pre_g0 = -1;
+            if (nmask && !(p.debug & 1)) {
+                bool got = false;
+                for_nsegs(b, nmask, nlo, nhi, [&](int t, long long g0, int n) {
+                    if (got) return;
+                    got = true;
+                    pre_g0 = g0;
+                    ne_load_rows(g0 & ~3ll, g0 + n, 0, lane, pre);
+                });
+            }
 
             if (first_window) {
                 // Seed theta: the k-th largest score among the staged postings of the token with the most postings in
@@ -650,7 +733,7 @@ struct Fast {
                 first_window = false;
                 int best_t = 0, best_c = 0;
                 for (int t = 0; t < T; ++t) {
-                    const int c = h->w_cnt[b][t];
+                    const int c = h->t_ne[b][t] ? 0 : h->w_cnt[b][t];
                     if (c > best_c) { best_c = c; best_t = t; }
                 }
                 const int m = min(best_c, p.cbcap);
@@ -666,22 +749,16 @@ struct Fast {
                 }
             }
             PROF(2);
-            PROF_CNT(17, ME);
-#ifdef BM25CU_PROFILE
-            if (ctid == 0 && p.dbg_doc >= wbase && p.dbg_doc < wend) {
-                p.ctrl->prof[16] = 0x4000000000000000ull | ((unsigned long long)nmask << 32) | emask;
-                p.ctrl->prof[17] = ((unsigned long long)(unsigned)wbase << 32) | (unsigned)wend;
-                p.ctrl->prof[18] = (unsigned long long)h->w_goff[b][0];
-                p.ctrl->prof[19] = ((unsigned long long)(unsigned)h->n_cur[2][0] << 32) | (unsigned)h->n_cur[1][0];
-                p.ctrl->prof[20] = ((unsigned long long)(unsigned)h->w_cnt[b][0] << 32) | (unsigned)h->w_cnt[b][1];
-                p.ctrl->prof[21] = ((unsigned long long)(unsigned)h->t_ne[b][0] << 32) | (unsigned)__float_as_uint(theta);
-                p.ctrl->prof[22] = (unsigned long long)h->t_cur[0];
-            }
-#endif
+            PROF_CNT(17, ME); PROF_CNT(18, MN);
+            PROF_CNT(19, MN >= 32768 ? 1 : 0); PROF_CNT(21, MN >= 32768 ? MN : 0);
             // this warp's share of the window's essential postings (flat index over the tokens of emask)
             const int lo = (int)(((long long)ME * cw) / NW), hi = (int)(((long long)ME * (cw + 1)) / NW);
 
-            // ---- A: claim
+            // ---- A: claim (and reset the hash left by the previous window)
+            if (hash_dirty) {
+                for (int i = ctid; i < kHash; i += CNT) h->hk[i] = -1;
+                hash_dirty = false;
+            }
             if (!(p.debug & 16))
                 for_segs(b, emask, lo, hi, pool_s, [&](const Seg &g) {
                     pass_claim(g, theta, kept_posting(0.0f, g.rest, theta), tagv, lane);
@@ -692,36 +769,72 @@ struct Fast {
             // ---- C: non-essential postings probe the tags
             if (nmask) {
                 if (!(p.debug & 1))
-                    for (unsigned m = nmask; m; m &= m - 1) ne_probe(b, __ffs(m) - 1, cw, lane, wbase, wend, tagv);
+                    for_nsegs(b, nmask, nlo, nhi, [&](int t, long long g0, int n) {
+                        const long long beg = h->t_beg[t], abase = g0 & ~3ll, g1 = g0 + n;
+                        const int rows = (int)((g1 - abase + 127) >> 7);
+                        int r0 = 0;
+                        if (g0 == pre_g0) { ne_probe_rows(t, beg, abase, g0, g1, 0, lane, tagv, pre); r0 = kPre; }
+                        for (; r0 < rows; r0 += kPre) {
+                            uint4 v[kPre];
+                            ne_load_rows(abase, g1, r0, lane, v);
+                            ne_probe_rows(t, beg, abase, g0, g1, r0, lane, tagv, v);
+                        }
+                    });
                 PROF(5);
                 bsync<true>();
                 PROF(6);
             }
-            // ---- D: resolve
-            int slow_n = 0;
-            slow_tot = 0;
+            // ---- D1: fetch the scores of the hash entries; resolve pass
+            const unsigned hits = h->h_cnt;
+            const bool fill = hits > 0u && h->h_over == 0u;
+            float hval[(kHash + CNT - 1) / CNT];
+            if (fill) {
+#pragma unroll
+                for (int j = 0; j < (kHash + CNT - 1) / CNT; ++j) {
+                    const int i = ctid + j * CNT;
+                    hval[j] = 0.0f;
+                    if (i < kHash && h->hk[i] != -1) hval[j] = p.data[h->t_beg[h->ht[i]] + h->hi[i]];
+                }
+            }
             if (!(p.debug & 4))
                 for_segs(b, emask, lo, hi, pool_s, [&](const Seg &g) {
-                    pass_resolve(g, theta, kept_posting(0.0f, g.rest, theta), tagv, lane, b, T, cw, pool_s, slow_n);
+                    pass_resolve(g, theta, kept_posting(0.0f, g.rest, theta), tagv, lane, b, T, pool_s);
                 });
+            if (fill) {
+#pragma unroll
+                for (int j = 0; j < (kHash + CNT - 1) / CNT; ++j) {
+                    const int i = ctid + j * CNT;
+                    if (i < kHash) h->hv[i] = hval[j];
+                }
+            }
+            if (hits > 0u) hash_dirty = true;
             PROF(20);
-            if (slow_n > 0) resolve_slow(b, T, cw, pool_s, theta, slow_n);
-            PROF(7);
-            PROF_CNT(18, h->h_cnt); PROF_CNT(19, h->h_over); PROF_CNT(23, slow_tot);
             bsync<true>();
             PROF(8);
-            // ---- E: clean the tags, reset the hash
-            if (!(p.debug & 8))
-                for_segs(b, emask, lo, hi, pool_s, [&](const Seg &g) {
-                    pass_clean(g, theta, kept_posting(0.0f, g.rest, theta), tagv, lane);
-                });
-            if (h->h_cnt > 0u) {
-                for (int i = ctid; i < kHash; i += CNT) h->hk[i] = -1;
+            // ---- D2: slow list (one thread per entry); clear the tags of the window
+            {
+                const int ns = (int)min(h->slow_cnt, (unsigned)kSlowCap);
+                PROF_CNT(23, ns); PROF_CNT(30, ns >= 480 ? 1 : 0); PROF_CNT(31, ns >= 480 ? ns : 0);
+                for (int i = ctid; i < ns; i += CNT) {
+                    const int2 e = h->slow[i];
+                    resolve_one(b, T, pool_s, theta, e.x, e.y, true);
+                }
+            }
+            PROF(7);
+            if (!(p.debug & 8)) {
+                const int nz = (((wend - wbase) >> 2) + 16) >> 4;  // 16-byte words covering the window's tag bytes
+                if (nz <= 8 * ME) {
+                    for (int i = ctid; i < nz; i += CNT) sts128z(tag_s + 16u * (unsigned)i);
+                } else {
+                    for_segs(b, emask, lo, hi, pool_s, [&](const Seg &g) {
+                        pass_clean(g, theta, kept_posting(0.0f, g.rest, theta), tagv, lane);
+                    });
+                }
             }
             PROF(9);
             bsync<true>();
             PROF(10);
-            if (ctid == 0) { mbar_arrive(&h->bar_free[b]); h->h_cnt = 0u; h->h_over = 0u; }
+            if (ctid == 0) { mbar_arrive(&h->bar_free[b]); h->h_cnt = 0u; h->h_over = 0u; h->slow_cnt = 0u; }
             if (h->cb_cnt >= (unsigned)trigger) { compact<true>(k, ctid, CNT); theta = fmaxf(theta, h->theta); PROF_CNT(22, 1); }
             PROF(11);
             if (last) break;
@@ -738,6 +851,7 @@ struct Fast {
             fence_mbar_init();
             h->h_cnt = 0u;
             h->h_over = 0u;
+            h->slow_cnt = 0u;
         }
         for (int i = tid * 16; i < p.tagcap; i += NT * 16) *reinterpret_cast<uint4 *>(tag + i) = make_uint4(0u, 0u, 0u, 0u);
         for (int i = tid; i < kHash; i += NT) h->hk[i] = -1;
@@ -864,6 +978,12 @@ __global__ void __launch_bounds__(NT, 1) retrieve_v6_kernel(const __grid_constan
     Fast<NT> f(p, smem);
     f.run();
 }
+// two CTAs per SM (256 threads each): two independent queries overlap each other's latencies
+__global__ void __launch_bounds__(256, 2) retrieve_v6_kernel_x2(const __grid_constant__ FastParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Fast<256> f(p, smem);
+    f.run();
+}
 
 }  // namespace v6
 
@@ -892,13 +1012,15 @@ int launch_retrieve_v6(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     const int cb_min = env_int6("BM25CU_CBMIN", 512);
     p.cbcap = 2 * kcap < cb_min ? next_pow2(cb_min) : 2 * kcap;
     p.route_all_general = (!ix->nonneg) || (a.mask != nullptr) || (a.k > 2048) || env_int6("BM25CU_FORCE_GENERAL", 0);
-    const int budget = ix->max_smem_optin;
+    const int ctas_per_sm = env_int6("BM25CU_CTAS_PER_SM", 1) == 2 ? 2 : 1;
+    if (ctas_per_sm == 2) threads = 256;
+    const int budget = ix->max_smem_optin / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
     p.nwarps = threads / 32 - 1;
     p.debug = env_int6("BM25CU_DEBUG_SKIP", 0);
     p.hash_max = env_int6("BM25CU_HASHMAX", v6::kHashMax);
     p.dbg_doc = env_int6("BM25CU_DEBUG_DOC", -1);
     if (p.hash_max < 0 || p.hash_max > v6::kHashMax) p.hash_max = v6::kHashMax;
-    int pool = env_int6("BM25CU_POOL", 10240);  // 4-byte slots per stage (two per essential posting)
+    int pool = env_int6("BM25CU_POOL", ctas_per_sm == 2 ? 4096 : 10240);  // 4-byte slots per stage (two per essential posting)
     pool = (pool + 3) & ~3;
     const int min_pool = kMaxTok * 2 * kMinCap + 256;
     if (pool < min_pool) pool = min_pool;
@@ -916,7 +1038,7 @@ int launch_retrieve_v6(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     if (tag_env > 0 && tag_env < tagcap) tagcap = tag_env;
     p.tagcap = (int)(tagcap & ~15ll);
     p.spillcap = 2 * p.poolcap;
-    const int grid = ix->sm_count;
+    const int grid = ix->sm_count * ctas_per_sm;
     int rc = ix->d_spill.reserve((size_t)grid * (size_t)p.spillcap * 8);
     if (rc) return rc;
     p.spill = ix->d_spill.as<unsigned long long>();
@@ -925,6 +1047,10 @@ int launch_retrieve_v6(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
 #define BM25CU_LAUNCH(NTV)                                                                                        \
     e = cudaFuncSetAttribute(v6::retrieve_v6_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e == cudaSuccess) v6::retrieve_v6_kernel<NTV><<<grid, NTV, smem, ix->stream>>>(p);
+    if (ctas_per_sm == 2) {
+        e = cudaFuncSetAttribute(v6::retrieve_v6_kernel_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) v6::retrieve_v6_kernel_x2<<<grid, 256, smem, ix->stream>>>(p);
+    } else
     switch (threads) {
         case 256: BM25CU_LAUNCH(256); break;
         case 1024: BM25CU_LAUNCH(1024); break;
