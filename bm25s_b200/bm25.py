@@ -6,6 +6,7 @@ identity of `self.scores`' arrays) and scoring + top-k run in the sm_100a kernel
 """
 from __future__ import annotations
 
+import itertools
 import json
 import logging
 import os
@@ -69,7 +70,7 @@ def _flatten(id_lists) -> Tuple[np.ndarray, np.ndarray]:
     total = int(ptr[-1])
     if total == 0:
         return np.zeros(0, dtype=np.int32), ptr
-    flat = np.fromiter((t for q in id_lists for t in q), dtype=np.int64, count=total)
+    flat = np.fromiter(itertools.chain.from_iterable(id_lists), dtype=np.int64, count=total)
     return flat, ptr
 
 
@@ -214,6 +215,68 @@ class BM25:
         vd = self.vocab_dict
         return [vd[token] for token in query_tokens if token in vd]
 
+    _EMPTY_QUERY_MSG = (
+        "The query does not contain any tokens that are in the vocabulary. "
+        "Please provide a query that contains at least one token that is in the vocabulary. "
+        "Alternatively, you can set `create_empty_token=True` when calling `index` to add an empty token to the vocabulary. "
+        "You can also manually add an empty token to the vocabulary by setting `retriever.vocab_dict[''] = max(retriever.vocab_dict.values()) + 1`. "
+        "Then, run `retriever.unique_token_ids_set = set(retriever.vocab_dict.values())` to update the unique token IDs."
+    )
+
+    def _membership_table(self) -> np.ndarray:
+        """Boolean table over token ids: True where the id is in `unique_token_ids_set` (cached per set object)."""
+        uts = self.unique_token_ids_set
+        key = (id(uts), len(uts))
+        cached = getattr(self, "_member_cache", None)
+        if cached is None or cached[0] != key:
+            ids = np.fromiter((t for t in uts if isinstance(t, (int, np.integer)) and t >= 0), dtype=np.int64)
+            table = np.zeros(int(ids.max()) + 1 if len(ids) else 0, dtype=bool)
+            table[ids] = True
+            self._member_cache = cached = (key, table)
+        return cached[1]
+
+    def _filter_int_queries(self, queries) -> Tuple[np.ndarray, np.ndarray]:
+        """list[list[int]] -> (flat, pointers) keeping ids of `unique_token_ids_set`; a query left empty becomes the
+        empty-token query, or raises as the reference does (bm25s/__init__.py:778-798)."""
+        flat, ptr = _flatten(queries)
+        member = self._membership_table()
+        keep = (flat >= 0) & (flat < len(member))
+        keep[keep] = member[flat[keep]]
+        csum = np.zeros(len(flat) + 1, dtype=np.int64)
+        np.cumsum(keep, out=csum[1:])
+        flat, ptr = flat[keep], csum[ptr]
+        empty = np.nonzero(np.diff(ptr) == 0)[0]
+        if len(empty):
+            if "" not in self.vocab_dict:
+                raise ValueError(self._EMPTY_QUERY_MSG)
+            flat = np.insert(flat, ptr[empty], self.vocab_dict[""])
+            add = np.zeros(len(ptr), dtype=np.int64)
+            add[empty + 1] = 1
+            ptr = ptr + np.cumsum(add)
+        return flat, ptr
+
+    def _remap_tokenized(self, tokenized: Tokenized) -> Tuple[np.ndarray, np.ndarray]:
+        """Tokenized(ids, vocab) -> (flat index ids, pointers) with out-of-vocabulary tokens dropped."""
+        vocab = tokenized.vocab
+        size = (max(vocab.values()) + 1) if len(vocab) else 0
+        remap = np.full(size, -2, dtype=np.int64)  # -2: id absent from the query vocabulary, -1: OOV for the index
+        get = self.vocab_dict.get
+        for token, qid in vocab.items():
+            remap[qid] = get(token, -1)
+        flat_q, ptr = _flatten(tokenized.ids)
+        if len(flat_q) == 0:
+            return flat_q.astype(np.int32), ptr
+        if int(flat_q.min()) < 0 or int(flat_q.max()) >= size:
+            bad = flat_q[(flat_q < 0) | (flat_q >= size)][0]
+            raise KeyError(int(bad))  # the reference fails in reverse_vocab[token_id]
+        mapped = remap[flat_q]
+        if (mapped == -2).any():
+            raise KeyError(int(flat_q[mapped == -2][0]))
+        keep = mapped >= 0
+        csum = np.zeros(len(mapped) + 1, dtype=np.int64)
+        np.cumsum(keep, out=csum[1:])
+        return mapped[keep], csum[ptr]
+
     def _check_max_token_id(self, ids: np.ndarray):
         max_token_id = int(ids.max(initial=0))
         if max_token_id >= len(self.scores["indptr"]) - 1:
@@ -277,28 +340,16 @@ class BM25:
         if return_as not in ["tuple", "documents"]:
             raise ValueError("`return_as` must be either 'tuple' or 'documents'")
 
+        int_flat = None
         if is_list_of_list_of_type(query_tokens, type_=int):
             if not hasattr(self, "unique_token_ids_set") or self.unique_token_ids_set is None:
                 raise ValueError(
                     "The unique_token_ids_set attribute is not found. Please run the `index` method first, or make sure"
                     "run retriever.load(load_vocab=True) before calling retrieve on list of list of token IDs (int)."
                 )
-            uts = self.unique_token_ids_set
-            filtered = []
-            for query in query_tokens:
-                qf = [t for t in query if t in uts]
-                if len(qf) == 0:
-                    if "" not in self.vocab_dict:
-                        raise ValueError(
-                            "The query does not contain any tokens that are in the vocabulary. "
-                            "Please provide a query that contains at least one token that is in the vocabulary. "
-                            "Alternatively, you can set `create_empty_token=True` when calling `index` to add an empty token to the vocabulary. "
-                            "You can also manually add an empty token to the vocabulary by setting `retriever.vocab_dict[''] = max(retriever.vocab_dict.values()) + 1`. "
-                            "Then, run `retriever.unique_token_ids_set = set(retriever.vocab_dict.values())` to update the unique token IDs."
-                        )
-                    qf = [self.vocab_dict[""]]
-                filtered.append(qf)
-            query_tokens = filtered
+            # reference :778-798 filters token by token against the set; here the batch is flattened first and
+            # filtered through a boolean membership table (same result, one numpy gather)
+            int_flat = self._filter_int_queries(query_tokens)
 
         if isinstance(query_tokens, tuple) and not _is_tuple_of_list_of_tokens(query_tokens):
             if len(query_tokens) != 2:
@@ -315,8 +366,12 @@ class BM25:
                 raise ValueError("The second element of the tuple passed to retrieve must be a dictionary.")
             query_tokens = Tokenized(ids=ids, vocab=vocab)
 
+        tokenized_flat = None
         if isinstance(query_tokens, Tokenized):
-            query_tokens = convert_tokenized_to_string_list(query_tokens)
+            # reference: ids -> strings -> ids, token by token (tokenization.py:513-521, __init__.py:572-579, 857-860);
+            # here: one remap table per call (query-vocabulary id -> index id, -1 = out of vocabulary), applied to the
+            # flattened ids by numpy. Same result: OOV tokens are dropped, order and duplicates are kept.
+            tokenized_flat = self._remap_tokenized(query_tokens)
 
         corpus = corpus if corpus is not None else self.corpus
 
@@ -329,8 +384,10 @@ class BM25:
                 raise ValueError("The length of the weight_mask must be the same as the length of the corpus.")
 
         # ---- the cuda branch sits where the numba branch is in the reference (:847-887)
-        if is_list_of_list_of_type(query_tokens, type_=int):
-            query_tokens_ids = query_tokens
+        if tokenized_flat is not None:
+            flat, ptr = tokenized_flat
+        elif int_flat is not None:
+            flat, ptr = int_flat
         elif isinstance(query_tokens, (list, tuple)) and all(isinstance(q, (list, tuple)) for q in query_tokens):
             query_tokens_ids = [
                 self.get_tokens_ids(q) if (len(q) and isinstance(q[0], str)) else list(q) for q in query_tokens
@@ -339,7 +396,8 @@ class BM25:
             raise ValueError(
                 "The query_tokens must be a list of list of tokens (str for stemmed words, int for token ids matching corpus) or a tuple of two lists: the first list is the list of unique token IDs, and the second list is the list of token IDs for each document."
             )
-        flat, ptr = _flatten(query_tokens_ids)
+        if tokenized_flat is None and int_flat is None:
+            flat, ptr = _flatten(query_tokens_ids)
         scores, indices = self.retrieve_flat(flat, ptr, k=k, weight_mask=weight_mask)
 
         if corpus is None:

@@ -411,12 +411,16 @@ struct Fast {
         bsync<CONS>();
         const unsigned int total = min(h->cb_cnt, (unsigned)(p.cbcap + p.spillcap));
         unsigned int n = min(total, (unsigned)p.cbcap);
-        unsigned int spilled = total - n, sp_done = 0;
+        const unsigned int spilled = total - n;
+        unsigned int sp_done = 0;
         for (;;) {
             const int P = next_pow2((int)(n > 0 ? n : 1));
             for (int i = (int)n + id; i < P; i += nthr) cb[i] = 0ull;
             sort_desc<CONS>(cb, P, id, nthr);
-            unsigned int keep = min(n, (unsigned)k);
+#ifdef BM25CU_PROFILE
+            if (id == 0) { atomicAdd(&p.ctrl->prof[30], 1ull); atomicAdd(&p.ctrl->prof[31], (unsigned long long)P); if (sp_done == 0) atomicAdd(&p.ctrl->prof[29], (unsigned long long)spilled); }
+#endif
+            const unsigned int keep = min(n, (unsigned)k);
             if (sp_done >= spilled) {
                 if (id == 0) {
                     h->cb_cnt = keep;
@@ -425,19 +429,25 @@ struct Fast {
                 bsync<CONS>();
                 return;
             }
-            // rare: merge the spilled candidates in chunks of (cbcap - keep)
+            // Spilled candidates: those that still beat the k-th key are poured into the free room tile by tile; the
+            // buffer is sorted again only when the room is (nearly) used up - most tiles are filtered out entirely.
             const unsigned long long th_key = (keep == (unsigned)k) ? cb[k - 1] : 0ull;  // full key: score, then lower doc id
-            const unsigned int room = (unsigned)p.cbcap - keep;
-            const unsigned int chunk = min(room, spilled - sp_done);
             if (id == 0) h->cb_cnt = keep;
-            bsync<CONS>();
-            for (unsigned int i = id; i < chunk; i += nthr) {
-                const unsigned long long c = spill[sp_done + i];
-                if (c > th_key) cb[atomicAdd(&h->cb_cnt, 1u)] = c;
+            unsigned int cur = keep;
+            for (;;) {
+                bsync<CONS>();  // cb_cnt settled and read by everyone before the next tile adds to it
+                const unsigned int chunk = min((unsigned)p.cbcap - cur, spilled - sp_done);
+                for (unsigned int i = id; i < chunk; i += nthr) {
+                    const unsigned long long c = spill[sp_done + i];
+                    if (c > th_key) cb[atomicAdd(&h->cb_cnt, 1u)] = c;
+                }
+                sp_done += chunk;
+                bsync<CONS>();
+                cur = h->cb_cnt;
+                if (sp_done >= spilled || (unsigned)p.cbcap - cur < 64u) break;
             }
             bsync<CONS>();
-            n = h->cb_cnt;
-            sp_done += chunk;
+            n = cur;
         }
     }
 
@@ -749,7 +759,8 @@ struct Fast {
         if (lane < n) {
             const int2 e = h->w_slow[cw][lane];
             const int d = e.x, myslot = e.y & 0xFF, rule = e.y >> 8;
-            float sum = 0.0f;
+            float sum = 0.0f, pend = 0.0f;  // the newest contribution is added one hit later: a score that comes from
+            bool has = false;               // global memory (non-essential token) is in flight during the next search
             int min_e = 99;
             for (int t = 0; t < T; ++t) {
                 const int o0 = h->s_lo[cw][t], o1 = h->s_hi[cw][t];
@@ -759,11 +770,13 @@ struct Fast {
                 while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < d) lo = m + 1; else hi = m; }
                 if (lo < o1 && (int)lds32(dt + 4u * lo) == d) {
                     const bool ne = h->t_ne[b][t] != 0;
-                    const float v = ne ? p.data[h->w_goff[b][t] + lo] : ldsf(pool_s + 4u * (unsigned)(h->w_sc[b][t] + lo));
-                    sum = __fadd_rn(sum, v);
+                    if (has) sum = __fadd_rn(sum, pend);
+                    pend = ne ? p.data[h->w_goff[b][t] + lo] : ldsf(pool_s + 4u * (unsigned)(h->w_sc[b][t] + lo));
+                    has = true;
                     if (!ne && t < min_e) min_e = t;
                 }
             }
+            if (has) sum = __fadd_rn(sum, pend);
             if ((rule == 0 || min_e == myslot) && sum > theta) emit(sum, d);
         }
         __syncwarp();

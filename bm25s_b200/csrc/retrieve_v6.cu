@@ -209,12 +209,13 @@ struct Fast {
         bsync<CONS>();
         const unsigned int total = min(h->cb_cnt, (unsigned)(p.cbcap + p.spillcap));
         unsigned int n = min(total, (unsigned)p.cbcap);
-        unsigned int spilled = total - n, sp_done = 0;
+        const unsigned int spilled = total - n;
+        unsigned int sp_done = 0;
         for (;;) {
             const int P = next_pow2((int)(n > 0 ? n : 1));
             for (int i = (int)n + id; i < P; i += nthr) cb[i] = 0ull;
             sort_desc<CONS>(cb, P, id, nthr);
-            unsigned int keep = min(n, (unsigned)k);
+            const unsigned int keep = min(n, (unsigned)k);
             if (sp_done >= spilled) {
                 if (id == 0) {
                     h->cb_cnt = keep;
@@ -223,18 +224,25 @@ struct Fast {
                 bsync<CONS>();
                 return;
             }
+            // Spilled candidates: those that still beat the k-th key are poured into the free room tile by tile; the
+            // buffer is sorted again only when the room is (nearly) used up - most tiles are filtered out entirely.
             const unsigned long long th_key = (keep == (unsigned)k) ? cb[k - 1] : 0ull;  // full key: score, then lower doc id
-            const unsigned int room = (unsigned)p.cbcap - keep;
-            const unsigned int chunk = min(room, spilled - sp_done);
             if (id == 0) h->cb_cnt = keep;
-            bsync<CONS>();
-            for (unsigned int i = id; i < chunk; i += nthr) {
-                const unsigned long long c = spill[sp_done + i];
-                if (c > th_key) cb[atomicAdd(&h->cb_cnt, 1u)] = c;
+            unsigned int cur = keep;
+            for (;;) {
+                bsync<CONS>();  // cb_cnt settled and read by everyone before the next tile adds to it
+                const unsigned int chunk = min((unsigned)p.cbcap - cur, spilled - sp_done);
+                for (unsigned int i = id; i < chunk; i += nthr) {
+                    const unsigned long long c = spill[sp_done + i];
+                    if (c > th_key) cb[atomicAdd(&h->cb_cnt, 1u)] = c;
+                }
+                sp_done += chunk;
+                bsync<CONS>();
+                cur = h->cb_cnt;
+                if (sp_done >= spilled || (unsigned)p.cbcap - cur < 64u) break;
             }
             bsync<CONS>();
-            n = h->cb_cnt;
-            sp_done += chunk;
+            n = cur;
         }
     }
 

@@ -159,3 +159,56 @@ def test_tokenized_round_trip():
 
     t = Tokenized(ids=[[0, 1], [1]], vocab={"a": 0, "b": 1})
     assert convert_tokenized_to_string_list(t) == [["a", "b"], ["b"]]
+
+
+def test_tokenized_remap_equals_string_round_trip():
+    """the one-table remap of Tokenized queries gives what the reference's id -> str -> id path gives
+    (tokenization.py:513-521 then bm25s/__init__.py:572-579): OOV dropped, order and duplicates kept."""
+    from bm25s_b200.bm25 import _flatten
+    from bm25s_b200.tokenization import Tokenized, convert_tokenized_to_string_list
+
+    r, g = _retriever_with_scores()
+    rng = np.random.default_rng(3)
+    words = [f"w{i}" for i in range(60)]
+    r.vocab_dict = {w: i for i, w in enumerate(words[:40])}       # index vocabulary: w0..w39
+    qvocab = {w: j for j, w in enumerate(rng.permutation(words[20:]).tolist())}  # query vocabulary: w20..w59, shuffled ids
+    ids = [rng.integers(0, len(qvocab), int(n)).tolist() for n in rng.integers(0, 12, 300)]
+    tok = Tokenized(ids=ids, vocab=qvocab)
+    flat, ptr = r._remap_tokenized(tok)
+    ref = [r.get_tokens_ids(q) for q in convert_tokenized_to_string_list(tok)]
+    ref_flat, ref_ptr = _flatten(ref)
+    np.testing.assert_array_equal(flat, ref_flat)
+    np.testing.assert_array_equal(ptr, ref_ptr)
+    assert any(len(q) == 0 for q in ref) and sum(len(q) for q in ref) < sum(len(q) for q in ids)  # OOV was exercised
+    with pytest.raises(KeyError):
+        r._remap_tokenized(Tokenized(ids=[[len(qvocab) + 5]], vocab=qvocab))
+    flat, ptr = r._remap_tokenized(Tokenized(ids=[], vocab=qvocab))
+    assert len(flat) == 0 and ptr.tolist() == [0]
+
+
+def test_int_query_filter_equals_reference_loop():
+    """The table-based filter of list[list[int]] queries equals the reference's per-token set filter + empty-token rule
+    (bm25s/__init__.py:778-798)."""
+    from bm25s_b200.bm25 import _flatten
+
+    r, g = _retriever_with_scores()
+    rng = np.random.default_rng(4)
+    r.vocab_dict = {f"w{i}": i for i in range(0, 50, 2)}
+    r.vocab_dict[""] = 51
+    r.unique_token_ids_set = set(r.vocab_dict.values())
+    queries = [rng.integers(-2, 60, int(n)).tolist() for n in rng.integers(0, 9, 400)]
+    flat, ptr = r._filter_int_queries(queries)
+    ref = []
+    for q in queries:
+        qf = [t for t in q if t in r.unique_token_ids_set]
+        ref.append(qf if qf else [r.vocab_dict[""]])
+    ref_flat, ref_ptr = _flatten(ref)
+    np.testing.assert_array_equal(flat, ref_flat)
+    np.testing.assert_array_equal(ptr, ref_ptr)
+    assert any(len([t for t in q if t in r.unique_token_ids_set]) == 0 for q in queries)
+    del r.vocab_dict[""]
+    r.unique_token_ids_set = set(r.vocab_dict.values())
+    with pytest.raises(ValueError, match="does not contain any tokens that are in the vocabulary"):
+        r._filter_int_queries([[1, 3]])
+    flat, ptr = r._filter_int_queries([[0, 1, 2, 2]])
+    assert flat.tolist() == [0, 2, 2] and ptr.tolist() == [0, 3]

@@ -29,4 +29,5 @@ for i in range(16):
 print('producer: loop-top', p[24], 'wait data', p[25], 'analysis+publish', p[26], 'wait free', p[27], 'issue', p[28])
 print('v6: resolve pass (excl. final slow)', p[20], 'hash hits', p[18], 'overflow windows', p[19], 'slow docs (warp 0)', p[23])
 print('v6: NE search', p[29], 'heavy NE windows (MN>=32K)', p[19], 'MN in them', p[21], 'windows with >=480 slow docs', p[30], 'slow docs in them', p[31])
+print('sorts', p[30], 'sum P', p[31], 'spilled', p[29])
 print('windows', p[16], 'ME', p[17], 'MN', p[18], 'active windows', p[19], 'keptE', p[20], 'R', p[21], 'compactions', p[22])
