@@ -103,7 +103,7 @@ struct bm25cu_index {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,
-        d_spill, d_order;
+        d_spill, d_order, d_theta;
     bm25cu::PinBuf h_in, h_out;
     int general_rows = 0;
 };

@@ -361,7 +361,7 @@ struct Fast {
         chunks = reinterpret_cast<uint4 *>(smem + o);
         o += (size_t)p.nwarps * kMaxChunk * 16;
         pool = reinterpret_cast<int *>(smem + o);
-        o += (size_t)2 * p.poolcap * 4;
+        o += (size_t)p.stages * p.poolcap * 4;
         tag = smem + o;
         spill = p.spill + (size_t)blockIdx.x * p.spillcap;
     }
@@ -370,7 +370,7 @@ struct Fast {
         o += (size_t)p.cbcap * 8;
         o = (o + 15) & ~size_t(15);
         o += (size_t)p.nwarps * kMaxChunk * 16;
-        o += (size_t)2 * p.poolcap * 4;
+        o += (size_t)p.stages * p.poolcap * 4;
         return o;
     }
 
@@ -617,6 +617,14 @@ struct Fast {
             PROF(26);
             ++nwin;
             if (!any_more) break;
+            if (p.stages == 1) {
+                // single stage: the next window is loaded into the same buffer once the consumers are done with this one
+                mbar_wait(&h->bar_free[0], ph_free0); ph_free0 ^= 1;
+                PROF(27);
+                issue_loads(0, T, L);
+                PROF(28);
+                continue;
+            }
             if (nwin >= 2) {  // the other stage was used by window nwin-2: wait until the consumers released it
                 if (b == 0) { mbar_wait(&h->bar_free[1], ph_free1); ph_free1 ^= 1; }
                 else { mbar_wait(&h->bar_free[0], ph_free0); ph_free0 ^= 1; }
@@ -628,6 +636,10 @@ struct Fast {
         }
         PROF_FLUSH(lane == 0);
         // consume the releases not waited for above (keeps the barrier parities in step across queries)
+        if (p.stages == 1) {
+            mbar_wait(&h->bar_free[0], ph_free0); ph_free0 ^= 1;
+            return;
+        }
         if (nwin >= 2) {
             const int bb = (nwin - 2) & 1;
             if (bb == 0) { mbar_wait(&h->bar_free[0], ph_free0); ph_free0 ^= 1; }
@@ -782,12 +794,98 @@ struct Fast {
         __syncwarp();
     }
 
+    // All passes of one warp and window when its essential postings fit four chunks (the common case): descriptors,
+    // document ids, scores and the kept predicate are loaded once and stay in registers from P1 to P5.
+    __device__ __forceinline__ void window_small(uint32_t chunk_s, int nch, float theta, int sh, unsigned gmask, uint32_t tagv,
+                                                 int lane, int b, int T, int cw, uint32_t pool_s, unsigned nmask) {
+        Chunk4 c;
+        load_chunks(chunk_s, 0, nch, c);
+        unsigned d[4], mine[4];
+        float sv[4];
+        bool v[4];
+        bool kept_any = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = lane < c.cnt[u];
+            sv[u] = v[u] ? ldsf(c.sc[u] + 4u * lane) : 0.0f;
+            if (v[u] && !c.allkept[u]) v[u] = kept_posting(sv[u], c.rest[u], theta);
+            d[u] = v[u] ? lds32(c.docs[u] + 4u * lane) : 0u;
+            mine[u] = tag_of(c.tbits[u], d[u], gmask);
+            kept_any |= v[u];
+        }
+        // P1
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v[u]) sts8(tagv + (d[u] >> sh), mine[u]);
+        const bool warp_kept = __ballot_sync(0xffffffffu, kept_any) != 0u;
+        __syncwarp();
+        if (!warp_kept) return;
+        // P2
+        {
+            unsigned x[4], bad = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = v[u] ? lds8(tagv + (d[u] >> sh)) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (v[u] && x[u] != mine[u]) bad |= 1u << u;
+            if (__ballot_sync(0xffffffffu, bad != 0u)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if ((bad >> u) & 1u) sts8(tagv + (d[u] >> sh), x[u] | kTagContested);
+            }
+        }
+        for (unsigned m = nmask; m; m &= m - 1) {
+            const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+            pass_probe_n_vec(g, sh, gmask, tagv, lane);
+        }
+        __syncwarp();
+        // P3
+        int slow_n = 0;
+        {
+            unsigned x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = v[u] ? lds8(tagv + (d[u] >> sh)) : 0u;
+            unsigned act = 0, slow = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!v[u]) continue;
+                if (x[u] == mine[u]) { if (sv[u] > theta) act |= 1u << u; }
+                else if ((x[u] & 0x7Fu) == mine[u] || ((x[u] ^ mine[u]) & gmask) != 0u) slow |= 1u << u;
+            }
+            if (__ballot_sync(0xffffffffu, (act | slow) != 0u)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if ((act >> u) & 1u) emit(sv[u], (int)d[u]);
+                    const unsigned m = __ballot_sync(0xffffffffu, (slow >> u) & 1u);
+                    if (m) {
+                        const int cnt = __popc(m);
+                        if (slow_n + cnt > 32) { resolve_slow(b, T, cw, pool_s, theta, slow_n); slow_n = 0; }
+                        if ((slow >> u) & 1u) {
+                            const int rule = ((x[u] & 0x7Fu) == mine[u]) ? 0 : 1;
+                            h->w_slow[cw][slow_n + __popc(m & ((1u << lane) - 1u))] =
+                                make_int2((int)d[u], (int)((c.tbits[u] >> 3) & 15u) | (rule << 8));
+                        }
+                        slow_n += cnt;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // P5
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v[u]) sts8(tagv + (d[u] >> sh), 0u);
+        // P4
+        if (slow_n > 0) resolve_slow(b, T, cw, pool_s, theta, slow_n);
+    }
+
     // ------------------------------------------------------------------------------------------ consumer warps
     __device__ void consumer(int T, int k, uint32_t &ph_meta0, uint32_t &ph_meta1) {
         const int ctid = threadIdx.x;  // consumers are warps 0..NW-1; the producer is the last warp (the scheduler favours it)
         const int cw = ctid >> 5, lane = ctid & 31;
         const int trigger = p.cbcap / 2;
-        float theta = 0.0f;
+        float theta = h->theta;
         int b = 0;
         bool first_window = true;
         PROF_DECL;
@@ -822,7 +920,7 @@ struct Fast {
                     for (int i = ctid; i < P; i += CNT) cb[i] = (i < m) ? ((unsigned long long)__float_as_uint(sc[i]) << 32) : 0ull;
                     sort_desc<true>(cb, P, ctid, CNT);
                     const unsigned int bits = (unsigned int)(cb[k - 1] >> 32);
-                    theta = bits > 0u ? __uint_as_float(bits - 1u) : 0.0f;  // next float below the k-th sampled score
+                    theta = fmaxf(theta, bits > 0u ? __uint_as_float(bits - 1u) : 0.0f);  // next float below the k-th sampled score
                     bsync<true>();
                     if (ctid == 0) h->theta = theta;
                 }
@@ -879,67 +977,71 @@ struct Fast {
                 nch += nc;
             }
             __syncwarp();
-            // ---- P1: essential postings that can still reach the threshold claim their document's group
-            bool kept_any = false;
-            if (p.debug & 16) {
-            } else if (chunk_ok) {
-                kept_any = chunks_claim(chunk_s, nch, theta, sh, gmask, tagv, lane);
+            if (chunk_ok && nch <= 4 && !(p.debug & 63)) {
+                window_small(chunk_s, nch, theta, sh, gmask, tagv, lane, b, T, cw, pool_s, nmask);
             } else {
-                for (unsigned m = emask; m; m &= m - 1) {
-                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                    kept_any |= pass_claim(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
-                }
-            }
-            const bool warp_kept = __ballot_sync(0xffffffffu, kept_any) != 0u;
-            PROF(3);
-            __syncwarp();
-            PROF_CNT(19, warp_kept ? 1 : 0);
-            if (warp_kept) {  // no surviving essential posting: nothing in this sub-range can score
-                // ---- P2: postings that do not read back their own claim set the contested bit; non-essential postings
-                //      that find their own document claimed do the same
-                if (p.debug & 2) {
+                // ---- P1: essential postings that can still reach the threshold claim their document's group
+                bool kept_any = false;
+                if (p.debug & 16) {
                 } else if (chunk_ok) {
-                    chunks_mark(chunk_s, nch, theta, sh, gmask, tagv, lane);
+                    kept_any = chunks_claim(chunk_s, nch, theta, sh, gmask, tagv, lane);
                 } else {
                     for (unsigned m = emask; m; m &= m - 1) {
                         const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                        pass_mark_e(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
+                        kept_any |= pass_claim(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
                     }
                 }
-                if (!(p.debug & 1))
-                for (unsigned m = nmask; m; m &= m - 1) {
-                    const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                    pass_probe_n_vec(g, sh, gmask, tagv, lane);
-                }
-                PROF(5);
+                const bool warp_kept = __ballot_sync(0xffffffffu, kept_any) != 0u;
+                PROF(3);
                 __syncwarp();
-                // ---- P3: sole hits score directly; contested winners and documents without a winner go to the slow list
-                int slow_n = 0;
-                if (p.debug & 4) {
-                } else if (chunk_ok) {
-                    chunks_resolve(chunk_s, nch, theta, sh, gmask, tagv, lane, b, T, cw, pool_s, slow_n);
-                } else {
-                    for (unsigned m = emask; m; m &= m - 1) {
-                        const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                        pass_resolve(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane, b, T, cw, pool_s, slow_n);
+                PROF_CNT(19, warp_kept ? 1 : 0);
+                if (warp_kept) {  // no surviving essential posting: nothing in this sub-range can score
+                    // ---- P2: postings that do not read back their own claim set the contested bit; non-essential postings
+                    //      that find their own document claimed do the same
+                    if (p.debug & 2) {
+                    } else if (chunk_ok) {
+                        chunks_mark(chunk_s, nch, theta, sh, gmask, tagv, lane);
+                    } else {
+                        for (unsigned m = emask; m; m &= m - 1) {
+                            const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                            pass_mark_e(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane);
+                        }
                     }
-                }
-                PROF(7);
-                __syncwarp();
-                // ---- P5: the claiming postings clean their tags (tags are all-clean between windows)
-                if (p.debug & 8) {
-                } else if (chunk_ok) {
-                    chunks_clean(chunk_s, nch, theta, sh, tagv, lane);
-                } else {
-                    for (unsigned m = emask; m; m &= m - 1) {
+                    if (!(p.debug & 1))
+                    for (unsigned m = nmask; m; m &= m - 1) {
                         const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                        pass_clean(g, theta, kept_posting(0.0f, g.rest, theta), sh, tagv, lane);
+                        pass_probe_n_vec(g, sh, gmask, tagv, lane);
                     }
+                    PROF(5);
+                    __syncwarp();
+                    // ---- P3: sole hits score directly; contested winners and documents without a winner go to the slow list
+                    int slow_n = 0;
+                    if (p.debug & 4) {
+                    } else if (chunk_ok) {
+                        chunks_resolve(chunk_s, nch, theta, sh, gmask, tagv, lane, b, T, cw, pool_s, slow_n);
+                    } else {
+                        for (unsigned m = emask; m; m &= m - 1) {
+                            const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                            pass_resolve(g, theta, kept_posting(0.0f, g.rest, theta), sh, gmask, tagv, lane, b, T, cw, pool_s, slow_n);
+                        }
+                    }
+                    PROF(7);
+                    __syncwarp();
+                    // ---- P5: the claiming postings clean their tags (tags are all-clean between windows)
+                    if (p.debug & 8) {
+                    } else if (chunk_ok) {
+                        chunks_clean(chunk_s, nch, theta, sh, tagv, lane);
+                    } else {
+                        for (unsigned m = emask; m; m &= m - 1) {
+                            const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
+                            pass_clean(g, theta, kept_posting(0.0f, g.rest, theta), sh, tagv, lane);
+                        }
+                    }
+                    PROF(9);
+                    // ---- P4: the rest of the slow list
+                    PROF_CNT(21, slow_n);
+                    if (slow_n > 0) resolve_slow(b, T, cw, pool_s, theta, slow_n);
                 }
-                PROF(9);
-                // ---- P4: the rest of the slow list
-                PROF_CNT(21, slow_n);
-                if (slow_n > 0) resolve_slow(b, T, cw, pool_s, theta, slow_n);
             }
             PROF(10);
             // the consumers meet once per window: stage b and its tags are released, the candidate buffer is checked
@@ -949,7 +1051,7 @@ struct Fast {
             if (h->cb_cnt >= (unsigned)trigger) { compact<true>(k, ctid, CNT); theta = fmaxf(theta, h->theta); PROF_CNT(22, 1); }
             PROF(11);
             if (last) break;
-            b ^= 1;
+            if (p.stages == 2) b ^= 1;
         }
         PROF_FLUSH(ctid == 0);
     }
@@ -991,7 +1093,7 @@ struct Fast {
                 h->t_df[tid] = end - beg;
                 h->t_max[tid] = mx;
             }
-            if (tid == 0) { h->cb_cnt = 0; h->theta = 0.0f; }
+            if (tid == 0) { h->cb_cnt = 0; h->theta = (p.theta_mode == 2) ? p.theta_io[q] : 0.0f; }
             __syncthreads();
             Layout lay;
             lay.cap = 0; lay.off = 0; lay.ne = -1; lay.live = -1; lay.sh = 0;  // forces the first share-out
@@ -1043,6 +1145,10 @@ struct Fast {
         const int k = p.a.k;
         compact<false>(k, tid, NT);  // leaves cb[0..n) sorted descending, n <= k
         const int n = (int)h->cb_cnt;
+        if (p.theta_mode == 1 && tid == 0) {
+            const unsigned int bits = (n == k) ? (unsigned int)(cb[k - 1] >> 32) : 0u;
+            p.theta_io[q] = bits > 0u ? __uint_as_float(bits - 1u) : 0.0f;
+        }
         const bool has_shift = (p.a.shift != nullptr) && T > 0;  // empty query: zeros, no shift (__init__.py:653-657)
         const float shift = has_shift ? p.a.shift[q] : 0.0f;
         int32_t *oi = p.a.out_ids + (size_t)q * k;
@@ -1080,7 +1186,7 @@ struct Fast {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(NT) retrieve_fast_kernel(const __grid_constant__ FastParams p) {
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) retrieve_fast_kernel(const __grid_constant__ FastParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     Fast<NT> f(p, smem);
     f.run();
@@ -1121,13 +1227,21 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.debug = env_int("BM25CU_DEBUG_SKIP", 0);
     p.hash_max = 0;
     p.dbg_doc = -1;
+    p.theta_mode = env_int("BM25CU_DEBUG_THETA", 0);
+    p.theta_io = nullptr;
+    if (p.theta_mode) {
+        int rc0 = ix->d_theta.reserve((size_t)(a.n_queries > 0 ? a.n_queries : 1) * sizeof(float));
+        if (rc0) return rc0;
+        p.theta_io = ix->d_theta.as<float>();
+    }
     // pool: 4-byte slots per stage
-    int pool = env_int("BM25CU_POOL", ctas_per_sm > 1 ? 6144 : 14336);
+    p.stages = env_int("BM25CU_STAGES", 2) == 1 ? 1 : 2;
+    int pool = env_int("BM25CU_POOL", ctas_per_sm > 1 ? 6144 : (p.stages == 1 ? 24576 : 14336));
     pool = (pool + 3) & ~3;
     const int min_pool = kMaxTok * 2 * kMinCap + 256;
     if (pool < min_pool) pool = min_pool;
     (void)nw;
-    if (pool > 32768) pool = 32768;
+    if (pool > 40960) pool = 40960;
     p.poolcap = pool;
     size_t fixed = Fast<512>::fixed_smem(p);
     long long tagcap = (long long)budget - (long long)fixed - 64;
@@ -1140,7 +1254,7 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     const int tag_env = env_int("BM25CU_TAG", 0);
     if (tag_env > 0 && tag_env < tagcap) tagcap = tag_env;
     p.tagcap = (int)(tagcap & ~15ll);
-    p.spillcap = 2 * p.poolcap;
+    p.spillcap = (p.stages == 1 ? 1 : 2) * p.poolcap;
     const int grid = ix->sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1);
     int rc = ix->d_spill.reserve((size_t)grid * (size_t)p.spillcap * 8);
     if (rc) return rc;

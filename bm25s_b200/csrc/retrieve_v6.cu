@@ -1027,6 +1027,9 @@ int launch_retrieve_v6(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.debug = env_int6("BM25CU_DEBUG_SKIP", 0);
     p.hash_max = env_int6("BM25CU_HASHMAX", v6::kHashMax);
     p.dbg_doc = env_int6("BM25CU_DEBUG_DOC", -1);
+    p.theta_mode = 0;
+    p.stages = 2;
+    p.theta_io = nullptr;
     if (p.hash_max < 0 || p.hash_max > v6::kHashMax) p.hash_max = v6::kHashMax;
     int pool = env_int6("BM25CU_POOL", ctas_per_sm == 2 ? 4096 : 10240);  // 4-byte slots per stage (two per essential posting)
     pool = (pool + 3) & ~3;
