@@ -794,44 +794,51 @@ struct Fast {
         __syncwarp();
     }
 
-    // All passes of one warp and window when its essential postings fit four chunks (the common case): descriptors,
+    // All passes of one warp and window when its essential postings fit 4 * G chunks (the common case): descriptors,
     // document ids, scores and the kept predicate are loaded once and stay in registers from P1 to P5.
+    template <int G>
     __device__ __forceinline__ void window_small(uint32_t chunk_s, int nch, float theta, int sh, unsigned gmask, uint32_t tagv,
                                                  int lane, int b, int T, int cw, uint32_t pool_s, unsigned nmask) {
-        Chunk4 c;
-        load_chunks(chunk_s, 0, nch, c);
-        unsigned d[4], mine[4];
-        float sv[4];
-        bool v[4];
+        constexpr int N = 4 * G;
+        unsigned d[N], mine[N], slot[N];
+        float sv[N];
+        bool v[N];
         bool kept_any = false;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            v[u] = lane < c.cnt[u];
-            sv[u] = v[u] ? ldsf(c.sc[u] + 4u * lane) : 0.0f;
-            if (v[u] && !c.allkept[u]) v[u] = kept_posting(sv[u], c.rest[u], theta);
-            d[u] = v[u] ? lds32(c.docs[u] + 4u * lane) : 0u;
-            mine[u] = tag_of(c.tbits[u], d[u], gmask);
-            kept_any |= v[u];
+        for (int g = 0; g < G; ++g) {
+            Chunk4 c;
+            load_chunks(chunk_s, 4 * g, nch, c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = 4 * g + u;
+                v[i] = lane < c.cnt[u];
+                sv[i] = v[i] ? ldsf(c.sc[u] + 4u * lane) : 0.0f;
+                if (v[i] && !c.allkept[u]) v[i] = kept_posting(sv[i], c.rest[u], theta);
+                d[i] = v[i] ? lds32(c.docs[u] + 4u * lane) : 0u;
+                mine[i] = tag_of(c.tbits[u], d[i], gmask);
+                slot[i] = (c.tbits[u] >> 3) & 15u;
+                kept_any |= v[i];
+            }
         }
         // P1
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (v[u]) sts8(tagv + (d[u] >> sh), mine[u]);
+        for (int i = 0; i < N; ++i)
+            if (v[i]) sts8(tagv + (d[i] >> sh), mine[i]);
         const bool warp_kept = __ballot_sync(0xffffffffu, kept_any) != 0u;
         __syncwarp();
         if (!warp_kept) return;
         // P2
         {
-            unsigned x[4], bad = 0;
+            unsigned x[N], bad = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = v[u] ? lds8(tagv + (d[u] >> sh)) : 0u;
+            for (int i = 0; i < N; ++i) x[i] = v[i] ? lds8(tagv + (d[i] >> sh)) : 0u;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (v[u] && x[u] != mine[u]) bad |= 1u << u;
+            for (int i = 0; i < N; ++i)
+                if (v[i] && x[i] != mine[i]) bad |= 1u << i;
             if (__ballot_sync(0xffffffffu, bad != 0u)) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if ((bad >> u) & 1u) sts8(tagv + (d[u] >> sh), x[u] | kTagContested);
+                for (int i = 0; i < N; ++i)
+                    if ((bad >> i) & 1u) sts8(tagv + (d[i] >> sh), x[i] | kTagContested);
             }
         }
         for (unsigned m = nmask; m; m &= m - 1) {
@@ -842,28 +849,27 @@ struct Fast {
         // P3
         int slow_n = 0;
         {
-            unsigned x[4];
+            unsigned x[N];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = v[u] ? lds8(tagv + (d[u] >> sh)) : 0u;
+            for (int i = 0; i < N; ++i) x[i] = v[i] ? lds8(tagv + (d[i] >> sh)) : 0u;
             unsigned act = 0, slow = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (!v[u]) continue;
-                if (x[u] == mine[u]) { if (sv[u] > theta) act |= 1u << u; }
-                else if ((x[u] & 0x7Fu) == mine[u] || ((x[u] ^ mine[u]) & gmask) != 0u) slow |= 1u << u;
+            for (int i = 0; i < N; ++i) {
+                if (!v[i]) continue;
+                if (x[i] == mine[i]) { if (sv[i] > theta) act |= 1u << i; }
+                else if ((x[i] & 0x7Fu) == mine[i] || ((x[i] ^ mine[i]) & gmask) != 0u) slow |= 1u << i;
             }
             if (__ballot_sync(0xffffffffu, (act | slow) != 0u)) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if ((act >> u) & 1u) emit(sv[u], (int)d[u]);
-                    const unsigned m = __ballot_sync(0xffffffffu, (slow >> u) & 1u);
+                for (int i = 0; i < N; ++i) {
+                    if ((act >> i) & 1u) emit(sv[i], (int)d[i]);
+                    const unsigned m = __ballot_sync(0xffffffffu, (slow >> i) & 1u);
                     if (m) {
                         const int cnt = __popc(m);
                         if (slow_n + cnt > 32) { resolve_slow(b, T, cw, pool_s, theta, slow_n); slow_n = 0; }
-                        if ((slow >> u) & 1u) {
-                            const int rule = ((x[u] & 0x7Fu) == mine[u]) ? 0 : 1;
-                            h->w_slow[cw][slow_n + __popc(m & ((1u << lane) - 1u))] =
-                                make_int2((int)d[u], (int)((c.tbits[u] >> 3) & 15u) | (rule << 8));
+                        if ((slow >> i) & 1u) {
+                            const int rule = ((x[i] & 0x7Fu) == mine[i]) ? 0 : 1;
+                            h->w_slow[cw][slow_n + __popc(m & ((1u << lane) - 1u))] = make_int2((int)d[i], (int)slot[i] | (rule << 8));
                         }
                         slow_n += cnt;
                         __syncwarp();
@@ -874,8 +880,8 @@ struct Fast {
         __syncwarp();
         // P5
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (v[u]) sts8(tagv + (d[u] >> sh), 0u);
+        for (int i = 0; i < N; ++i)
+            if (v[i]) sts8(tagv + (d[i] >> sh), 0u);
         // P4
         if (slow_n > 0) resolve_slow(b, T, cw, pool_s, theta, slow_n);
     }
@@ -978,7 +984,9 @@ struct Fast {
             }
             __syncwarp();
             if (chunk_ok && nch <= 4 && !(p.debug & 63)) {
-                window_small(chunk_s, nch, theta, sh, gmask, tagv, lane, b, T, cw, pool_s, nmask);
+                window_small<1>(chunk_s, nch, theta, sh, gmask, tagv, lane, b, T, cw, pool_s, nmask);
+            } else if (chunk_ok && nch <= 8 && !(p.debug & 63)) {
+                window_small<2>(chunk_s, nch, theta, sh, gmask, tagv, lane, b, T, cw, pool_s, nmask);
             } else {
                 // ---- P1: essential postings that can still reach the threshold claim their document's group
                 bool kept_any = false;
