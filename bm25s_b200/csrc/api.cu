@@ -24,8 +24,9 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
         // 6 = bit tags + streamed non-essential postings (retrieve_v6.cu)
         const char *kv = getenv("BM25CU_KERNEL");
         const int kernel = (kv && *kv) ? atoi(kv) : 5;
-        rc = (kernel == 6) ? launch_retrieve_v6(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
-                           : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
+        rc = (kernel == 7)   ? launch_retrieve_v7(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
+             : (kernel == 6) ? launch_retrieve_v6(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
+                             : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
         if (rc) return rc;
     }
     BM25CU_CHECK(cudaEventRecord(ix->ev[2], ix->stream));
