@@ -20,13 +20,12 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
     int launches = 0;
     BM25CU_CHECK(cudaEventRecord(ix->ev[1], ix->stream));
     {
-        // BM25CU_KERNEL selects the structure of K1: 5 = per-warp document sub-ranges (retrieve_fast.cu),
-        // 6 = bit tags + streamed non-essential postings (retrieve_v6.cu)
+        // BM25CU_KERNEL selects the structure of K1: 5 (default) = per-warp document sub-ranges (retrieve_fast.cu),
+        // 7 = bit tags + posting-index splits with barriers between the phases (retrieve_v7.cu, experimental)
         const char *kv = getenv("BM25CU_KERNEL");
         const int kernel = (kv && *kv) ? atoi(kv) : 5;
-        rc = (kernel == 7)   ? launch_retrieve_v7(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
-             : (kernel == 6) ? launch_retrieve_v6(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
-                             : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
+        rc = (kernel == 7) ? launch_retrieve_v7(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
+                           : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
         if (rc) return rc;
     }
     BM25CU_CHECK(cudaEventRecord(ix->ev[2], ix->stream));

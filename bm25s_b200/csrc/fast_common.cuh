@@ -45,7 +45,6 @@ struct FastParams {
     int max_shift; // largest log2(G)
     int nwarps;    // consumer warps of the launch configuration
     int debug;     // timing experiments only (BM25CU_DEBUG_SKIP bit mask; results are wrong when non-zero)
-    int dbg_doc;   // profile build: document traced through the v6 phases
     float *theta_io;  // experiment: per-query final threshold written (theta_mode 1) / used as the start value (2)
     int theta_mode;
     int stages;    // stage buffers of the posting pool (2: the next window loads while this one is processed)

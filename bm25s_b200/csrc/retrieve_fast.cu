@@ -1234,7 +1234,6 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.nwarps = nw;
     p.debug = env_int("BM25CU_DEBUG_SKIP", 0);
     p.hash_max = 0;
-    p.dbg_doc = -1;
     p.theta_mode = env_int("BM25CU_DEBUG_THETA", 0);
     p.theta_io = nullptr;
     if (p.theta_mode) {

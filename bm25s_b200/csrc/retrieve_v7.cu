@@ -1,5 +1,5 @@
-// K1, third structure: the bit-tag / flat-split consumer of retrieve_v6.cu on top of the posting pool of
-// retrieve_fast.cu.
+// K1, alternative structure (BM25CU_KERNEL=7, experimental): bit tags and posting-index splits on top of the
+// posting pool of retrieve_fast.cu.
 //
 // The producer warp stages, per window and double-buffered, the document ids of EVERY live token and the scores of
 // the essential ones (bulk async copies); a window is what the pool covers for all tokens, capped by the tag span
@@ -9,7 +9,7 @@
 //   A   surviving essential postings set PRESENT with an atomic OR; a second hit of the same document sets MULTI
 //   C   non-essential postings (read from the pool, 16 bytes per lane) whose document is PRESENT set MULTI and file
 //       (doc, token, posting index) in a small hash table
-//   D1  the scores of the hash entries are fetched from global memory (all loads in flight together); essential
+//   D1  (the hash entries' scores arrive by asynchronous 4-byte copies issued at hit time); essential
 //       postings read their document's bits: not MULTI -> the posting's score is the document's score (0 + s = s
 //       exactly); MULTI -> the CTA's slow list
 //   D2  slow list, one thread per entry: the document is re-summed in query-token order (the reference's float32
@@ -57,7 +57,8 @@ struct Hdr {
     int w_MN[2];              // non-essential postings in the window
     unsigned int w_emask[2];  // tokens with essential postings in the window
     unsigned int w_nmask[2];  // tokens with non-essential postings in the window
-    unsigned int h_cnt, h_over, slow_cnt;
+    unsigned int h_cnt_w[kMaxWarps];  // hash inserts per consumer warp (a warp may file hash_max / NW entries per window)
+    unsigned int h_any, h_over, slow_cnt;
     unsigned int q_slot;
     unsigned int cb_cnt;
     float theta;
@@ -451,16 +452,19 @@ struct Fast {
         }
     }
 
-    // C, one hit: the document is PRESENT and a non-essential posting contributes to it
+    // C, one hit: the document is PRESENT and a non-essential posting contributes to it. The entry's score is copied
+    // from global memory straight into the table by an asynchronous 4-byte copy (waited for at the end of D1).
     __device__ __forceinline__ void ne_hit(unsigned d, uint32_t a, int t, long long gidx, long long beg) {
         reds_or(a & ~3u, 16u << tag_bit(a, d));
-        const unsigned slot = atomicAdd(&h->h_cnt, 1u);
+        const int cw = threadIdx.x >> 5;
+        const unsigned slot = atomicAdd(&h->h_cnt_w[cw], 1u);
+        if (slot == 0u) h->h_any = 1u;
         if (slot >= (unsigned)p.hash_max) { h->h_over = 1u; return; }
         unsigned i = (d * 2654435761u) >> 22;
         while (atomicCAS(&h->hk[i], -1, (int)d) != -1) i = (i + 1u) & (unsigned)(kHash - 1);
         h->ht[i] = t;
         h->hi[i] = (int)(gidx - beg);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.data + gidx));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&h->hv[i])), "l"(p.data + gidx) : "memory");
     }
 
     // C: probes four document ids (one 16-byte shared load); gi = global posting index of the first
@@ -677,29 +681,13 @@ struct Fast {
                 PROF(6);
             }
             // ---- D1: fetch the scores of the hash entries; resolve pass
-            const unsigned hits = h->h_cnt;
-            const bool fill = hits > 0u && h->h_over == 0u;
-            float hval[(kHash + CNT - 1) / CNT];
-            if (fill) {
-#pragma unroll
-                for (int j = 0; j < (kHash + CNT - 1) / CNT; ++j) {
-                    const int i = ctid + j * CNT;
-                    hval[j] = 0.0f;
-                    if (i < kHash && h->hk[i] != -1) hval[j] = p.data[h->t_beg[h->ht[i]] + h->hi[i]];
-                }
-            }
+            const bool hits = h->h_any != 0u;
             if (!(p.debug & 4))
                 for_segs(b, emask, lo, hi, pool_s, [&](const Seg &g) {
                     pass_resolve(g, theta, kept_posting(0.0f, g.rest, theta), tagv, lane, b, T, pool_s);
                 });
-            if (fill) {
-#pragma unroll
-                for (int j = 0; j < (kHash + CNT - 1) / CNT; ++j) {
-                    const int i = ctid + j * CNT;
-                    if (i < kHash) h->hv[i] = hval[j];
-                }
-            }
-            if (hits > 0u) hash_dirty = true;
+            asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's score copies have landed (visible after the barrier)
+            if (hits) hash_dirty = true;
             PROF(20);
             bsync<true>();
             PROF(8);
@@ -726,7 +714,8 @@ struct Fast {
             PROF(9);
             bsync<true>();
             PROF(10);
-            if (ctid == 0) { mbar_arrive(&h->bar_free[b]); h->h_cnt = 0u; h->h_over = 0u; h->slow_cnt = 0u; }
+            if (ctid == 0) { mbar_arrive(&h->bar_free[b]); h->h_any = 0u; h->h_over = 0u; h->slow_cnt = 0u; }
+            if (lane == 0) h->h_cnt_w[cw] = 0u;
             if (h->cb_cnt >= (unsigned)trigger) { compact<true>(k, ctid, CNT); theta = fmaxf(theta, h->theta); PROF_CNT(22, 1); }
             PROF(11);
             if (last) break;
@@ -741,8 +730,9 @@ struct Fast {
         if (tid == 0) {
             for (int i = 0; i < 2; ++i) { mbar_init(&h->bar_data[i], 1); mbar_init(&h->bar_meta[i], 1); mbar_init(&h->bar_free[i], 1); }
             fence_mbar_init();
-            h->h_cnt = 0u;
+            h->h_any = 0u;
             h->h_over = 0u;
+            for (int i = 0; i < kMaxWarps; ++i) h->h_cnt_w[i] = 0u;
             h->slow_cnt = 0u;
         }
         for (int i = tid * 16; i < p.tagcap; i += NT * 16) *reinterpret_cast<uint4 *>(tag + i) = make_uint4(0u, 0u, 0u, 0u);
@@ -910,11 +900,11 @@ int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.nwarps = threads / 32 - 1;
     p.debug = env_int7("BM25CU_DEBUG_SKIP", 0);
     p.hash_max = env_int7("BM25CU_HASHMAX", v7::kHashMax);
-    p.dbg_doc = env_int7("BM25CU_DEBUG_DOC", -1);
     p.theta_mode = 0;
     p.stages = 2;
     p.theta_io = nullptr;
     if (p.hash_max < 0 || p.hash_max > v7::kHashMax) p.hash_max = v7::kHashMax;
+    p.hash_max /= (threads / 32 - 1);  // per consumer warp
     int pool = env_int7("BM25CU_POOL", ctas_per_sm == 2 ? 6144 : 14336);  // 4-byte slots per stage (two per essential posting)
     pool = (pool + 3) & ~3;
     const int min_pool = kMaxTok * 2 * kMinCap + 256;

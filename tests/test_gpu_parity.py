@@ -202,6 +202,40 @@ def test_random_corpus_vs_c_oracle(k):
     dev.close()
 
 
+@pytest.mark.parametrize("k", [1, 10, 200])
+def test_alternative_kernel_structure_is_bit_identical(k):
+    """BM25CU_KERNEL=7 (bit tags, posting-index splits, hash of non-essential hits) returns exactly what the default
+    kernel returns: scores bit-equal, ids equal (same deterministic tie rule), also with tiny tag / pool / hash settings."""
+    from bm25s_b200 import DeviceIndex, synth
+
+    n_docs, n_vocab = 120_000, 20_000
+    corp = synth.make_corpus(n_docs, 30, n_vocab, seed=7)
+    data, indices, indptr, nonocc = O.build_index(corp.to_lists(), n_vocab, "bm25+")
+    queries = synth.make_queries(64, n_vocab, seed=8).to_lists() + [[0, 1, 2], [0, 0], list(range(12)), [5]]
+    ptr = np.zeros(len(queries) + 1, np.int64)
+    np.cumsum([len(q) for q in queries], out=ptr[1:])
+    flat = np.array([t for q in queries for t in q], np.int32)
+    sh = np.array([O.query_shift(nonocc, q) for q in queries], np.float32)
+    dev = DeviceIndex.upload(data, indices, indptr, n_docs, nonocc=nonocc)
+    ids, sc = dev.retrieve(flat, ptr, k, shift=sh)
+    for env in ({}, {"BM25CU_TAG": "4096"}, {"BM25CU_POOL": "1024"}, {"BM25CU_HASHMAX": "0"}, {"BM25CU_THREADS": "256"},
+                {"BM25CU_PRUNE": "0"}):
+        env = dict(env, BM25CU_KERNEL="7")
+        old = {kk: os.environ.get(kk) for kk in env}
+        os.environ.update(env)
+        try:
+            ids2, sc2 = dev.retrieve(flat, ptr, k, shift=sh)
+        finally:
+            for kk, v in old.items():
+                if v is None:
+                    os.environ.pop(kk, None)
+                else:
+                    os.environ[kk] = v
+        np.testing.assert_array_equal(sc2, sc, err_msg=str(env))
+        np.testing.assert_array_equal(ids2, ids, err_msg=str(env))
+    dev.close()
+
+
 def test_doc_range_shards_merge_to_unsharded():
     """shard by contiguous doc range, local top-k per shard, merge == unsharded result."""
     from bm25s_b200 import DeviceIndex, topk_merge

@@ -1,4 +1,4 @@
-"""Debug helper: random test corpus, v6 kernel under several settings, details of mismatching queries."""
+"""Debug helper: random test corpus, the kernel named by BM25CU_KERNEL_UNDER_TEST under several settings, details of mismatching queries."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,7 +20,7 @@ rid, rsc = CO.retrieve(data, indices, indptr, n_docs, flat, ptr, k)
 colmax = np.array([data[indptr[t]:indptr[t + 1]].max() if indptr[t + 1] > indptr[t] else 0 for t in range(n_vocab)])
 for env in ({}, {"BM25CU_PRUNE": "0"}, {"BM25CU_HASHMAX": "0"}, {"BM25CU_TAG": "4096"}, {"BM25CU_POOL": "1024"},
             {"BM25CU_TAG": "65536", "BM25CU_HASHMAX": "0"}, {"BM25CU_THREADS": "256"}):
-    os.environ["BM25CU_KERNEL"] = os.environ.get("BM25CU_KERNEL_UNDER_TEST", "6")
+    os.environ["BM25CU_KERNEL"] = os.environ.get("BM25CU_KERNEL_UNDER_TEST", "7")
     for kk in ("BM25CU_PRUNE", "BM25CU_HASHMAX", "BM25CU_TAG", "BM25CU_POOL", "BM25CU_THREADS"):
         os.environ.pop(kk, None)
     os.environ.update(env)
