@@ -66,6 +66,7 @@ struct SmemHdr {
     int s_hi[kMaxWarps][kTokArr];          // document sub-range (computed by the warp itself for the current window)
     int w_end[2];                          // one past the last document of the window
     int2 w_slow[kMaxWarps][32];            // per-warp slow list (doc, slot | rule << 8)
+    float w_slow_s[kMaxWarps][32];         //                    score of the listing posting
     int w_base[2];            // first document of the window, rounded down to a multiple of G
     int w_shift[2];           // log2(G) of the window
     int w_last[2];            // 1 if this is the query's last window
@@ -704,7 +705,7 @@ struct Fast {
                         if ((slow >> u) & 1u) {
                             const unsigned mine = tag_of(tbits, d[u], gmask);
                             const int rule = ((x[u] & 0x7Fu) == mine) ? 0 : 1;  // 0: contested winner, 1: another document won
-                            h->w_slow[cw][slow_n + __popc(m & ((1u << lane) - 1u))] = make_int2((int)d[u], g.t | (rule << 8));
+                            { const int at = slow_n + __popc(m & ((1u << lane) - 1u)); h->w_slow[cw][at] = make_int2((int)d[u], g.t | (rule << 8)); h->w_slow_s[cw][at] = sv[u]; }
                         }
                         slow_n += cnt;
                         __syncwarp();
@@ -751,8 +752,9 @@ struct Fast {
                         if ((slow >> u) & 1u) {
                             const unsigned mine = tag_of(c.tbits[u], d[u], gmask);
                             const int rule = ((x[u] & 0x7Fu) == mine) ? 0 : 1;
-                            h->w_slow[cw][slow_n + __popc(m & ((1u << lane) - 1u))] =
-                                make_int2((int)d[u], (int)((c.tbits[u] >> 3) & 15u) | (rule << 8));
+                            const int at = slow_n + __popc(m & ((1u << lane) - 1u));
+                            h->w_slow[cw][at] = make_int2((int)d[u], (int)((c.tbits[u] >> 3) & 15u) | (rule << 8));
+                            h->w_slow_s[cw][at] = sv[u];
                         }
                         slow_n += cnt;
                         __syncwarp();
@@ -774,7 +776,15 @@ struct Fast {
             float sum = 0.0f, pend = 0.0f;  // the newest contribution is added one hit later: a score that comes from
             bool has = false;               // global memory (non-essential token) is in flight during the next search
             int min_e = 99;
+            const float own = h->w_slow_s[cw][lane];
             for (int t = 0; t < T; ++t) {
+                if (t == myslot) {  // the listing posting itself (essential): no search
+                    if (has) sum = __fadd_rn(sum, pend);
+                    pend = own;
+                    has = true;
+                    if (t < min_e) min_e = t;
+                    continue;
+                }
                 const int o0 = h->s_lo[cw][t], o1 = h->s_hi[cw][t];
                 if (o1 == o0) continue;
                 const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
@@ -869,7 +879,7 @@ struct Fast {
                         if (slow_n + cnt > 32) { resolve_slow(b, T, cw, pool_s, theta, slow_n); slow_n = 0; }
                         if ((slow >> i) & 1u) {
                             const int rule = ((x[i] & 0x7Fu) == mine[i]) ? 0 : 1;
-                            h->w_slow[cw][slow_n + __popc(m & ((1u << lane) - 1u))] = make_int2((int)d[i], (int)slot[i] | (rule << 8));
+                            { const int at = slow_n + __popc(m & ((1u << lane) - 1u)); h->w_slow[cw][at] = make_int2((int)d[i], (int)slot[i] | (rule << 8)); h->w_slow_s[cw][at] = sv[i]; }
                         }
                         slow_n += cnt;
                         __syncwarp();
@@ -936,29 +946,32 @@ struct Fast {
 
             // ---- this warp's document sub-range [bnd(cw), bnd(cw + 1)), boundaries on multiples of G: lane t finds the
             //      first posting of token t at or after the lower bound, lane 16 + t does the same for the upper bound
+            unsigned emask, nmask;  // tokens with a non-empty essential / non-essential slice (warp-uniform)
             {
                 const int wbase = h->w_base[b], wendd = h->w_end[b];
-                const long long wspan = (long long)wendd - wbase;
+                const unsigned wspan = (unsigned)(wendd - wbase);
+                const unsigned step = ((wspan / (unsigned)NW) + gmask + 1u) & ~gmask;  // multiple of G; NW steps cover the window
                 const int t = lane & 15, side = lane >> 4;
                 const int wq = cw + side;
-                const int bnd = (wq == NW) ? wendd : (int)(wbase + (((wspan * wq) / NW) & ~(long long)gmask));
+                const long long bl = (long long)wbase + (long long)step * wq;
+                const int bnd = (wq == NW || bl > wendd) ? wendd : (int)bl;
+                int pos = 0, ne = 0;
                 if (t < T) {
                     const int c = h->w_cnt[b][t];
                     const uint32_t dt = pool_s + 4u * (unsigned)h->w_doc[b][t];
+                    ne = h->t_ne[b][t];
                     int lo = 0, hi = c;
                     if (wq == 0) hi = 0;
                     else if (wq == NW) lo = c;
                     while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)lds32(dt + 4u * m) < bnd) lo = m + 1; else hi = m; }
+                    pos = lo;
                     if (side == 0) h->s_lo[cw][t] = lo; else h->s_hi[cw][t] = lo;
                 }
+                const int upper = __shfl_down_sync(0xffffffffu, pos, 16);
+                const bool nonempty = (side == 0) && (t < T) && (upper > pos);
+                emask = __ballot_sync(0xffffffffu, nonempty && !ne);
+                nmask = __ballot_sync(0xffffffffu, nonempty && ne);
                 __syncwarp();
-            }
-            // ---- this warp's slice of every token
-            unsigned emask = 0, nmask = 0;  // tokens with a non-empty essential / non-essential slice (warp-uniform)
-            for (int t = 0; t < T; ++t) {
-                if (h->s_hi[cw][t] > h->s_lo[cw][t]) {
-                    if (h->t_ne[b][t]) nmask |= 1u << t; else emask |= 1u << t;
-                }
             }
             // ---- chunk list of this warp's essential postings (<= 32 consecutive postings of one token per chunk)
             const uint32_t chunk_s = smem_u32(chunks + (size_t)cw * kMaxChunk);
