@@ -73,6 +73,14 @@ int finish_stats(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, i
 extern "C" {
 
 // debug: copy the phase counters of the last retrieve call (32 x uint64); zeros unless built with -DBM25CU_PROFILE
+// debugging / tests only (not part of include/bm25cu.h): the per-column 10th / 100th / 1000th largest scores, f32[3][n_vocab]
+int bm25cu_debug_colkth(bm25cu_index *ix, float *out) {
+    BM25CU_REQUIRE(ix && out && ix->d_colkth, "bm25cu_debug_colkth: no table");
+    BM25CU_CHECK(cudaSetDevice(ix->device));
+    BM25CU_CHECK(cudaMemcpy(out, ix->d_colkth, (size_t)3 * ix->n_vocab * sizeof(float), cudaMemcpyDeviceToHost));
+    return BM25CU_OK;
+}
+
 int bm25cu_debug_prof(bm25cu_index *ix, unsigned long long *out) {
     BM25CU_REQUIRE(ix && out && ix->d_ctrl.p, "bm25cu_debug_prof: no retrieve call yet");
     BM25CU_CHECK(cudaSetDevice(ix->device));

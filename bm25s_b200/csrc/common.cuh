@@ -95,6 +95,8 @@ struct bm25cu_index {
     int64_t *d_indptr = nullptr;   // i64[n_vocab + 1]
     float *d_nonocc = nullptr;     // f32[n_vocab] or null (kept for download only)
     float *d_colmax = nullptr;     // f32[n_vocab] largest score of every column (upper bounds for pruning)
+    float *d_colkth = nullptr;     // f32[3][n_vocab] 10th / 100th / 1000th largest score of every column (0: fewer postings);
+                                   // a query's k-th best document scores at least the k-th largest posting of any of its tokens
     bool nonneg = true;            // all data >= 0 and finite: the fused streaming kernel is exact
     int sm_count = 148;
     int max_smem_optin = 0;

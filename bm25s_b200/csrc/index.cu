@@ -1,6 +1,7 @@
 // Index residency: upload of the reference's CSC arrays (bm25s/__init__.py:432-438, :1121-1127) into HBM,
 // doc-range shard extraction on the device, download, free.
 #include "common.cuh"
+#include "select.cuh"
 #include "scan.cuh"
 
 namespace bm25cu {
@@ -67,6 +68,64 @@ __global__ void column_max_kernel(const float *__restrict__ data, const int64_t 
     if (lane == 0) colmax[warp] = m;
 }
 
+// colkth[r][t] = the 10th (r = 0), 100th (r = 1), 1000th (r = 2) largest score of column t, 0 if the column is shorter.
+// One warp per column: MSB-first radix select on order-preserving keys with a per-warp shared-memory histogram.
+__global__ void __launch_bounds__(256) column_kth_kernel(const float *__restrict__ data, const int64_t *__restrict__ indptr,
+                                                         int32_t n_vocab, float *colkth) {
+    __shared__ unsigned int hist_all[8][256];
+    const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (col >= n_vocab) return;
+    unsigned int *hist = hist_all[threadIdx.x >> 5];
+    const int64_t s = indptr[col], e = indptr[col + 1];
+    const int64_t n = e - s;
+    const int ranks[3] = {10, 100, 1000};
+    for (int r = 0; r < 3; ++r) {
+        float out = 0.0f;
+        if (n >= ranks[r]) {
+            uint32_t prefix = 0, mask = 0;
+            unsigned int need = (unsigned int)ranks[r];
+            for (int pass = 3; pass >= 0; --pass) {
+                const int shift = 8 * pass;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
+                __syncwarp();
+                for (int64_t i = s + lane; i < e; i += 32) {
+                    const uint32_t key = f32_key(data[i]);
+                    if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+                }
+                __syncwarp();
+                // lane L owns bins 8 L .. 8 L + 7; the wanted bin is found from the top
+                unsigned int cnt[8], lane_sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { cnt[j] = hist[lane * 8 + j]; lane_sum += cnt[j]; }
+                unsigned int above = lane_sum;  // inclusive suffix sum over lanes >= L
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_down_sync(0xffffffffu, above, o); if (lane + o < 32) above += y; }
+                above -= lane_sum;  // elements in bins of higher lanes
+                const bool here = above < need && need <= above + lane_sum;
+                int sel = 0;
+                unsigned int acc = above;
+                if (here) {
+                    for (int j = 7; j >= 0; --j) {
+                        if (acc + cnt[j] >= need) { sel = lane * 8 + j; break; }
+                        acc += cnt[j];
+                    }
+                }
+                const int src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+                sel = __shfl_sync(0xffffffffu, sel, src);
+                acc = __shfl_sync(0xffffffffu, acc, src);
+                prefix |= (uint32_t)sel << shift;
+                mask |= 0xFFu << shift;
+                need -= acc;
+                __syncwarp();
+            }
+            out = __uint_as_float((prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix);
+        }
+        if (lane == 0) colkth[(size_t)r * n_vocab + col] = out;
+    }
+}
+
 int finalize_index(bm25cu_index *ix) {
     cudaDeviceProp prop;
     BM25CU_CHECK(cudaGetDeviceProperties(&prop, ix->device));
@@ -84,6 +143,12 @@ int finalize_index(bm25cu_index *ix) {
     if (ix->n_vocab > 0) {
         const int64_t threads = (int64_t)ix->n_vocab * 32;
         column_max_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ix->stream>>>(ix->d_data, ix->d_indptr, ix->n_vocab, ix->d_colmax);
+        BM25CU_CHECK(cudaGetLastError());
+    }
+    BM25CU_CHECK(cudaMalloc(&ix->d_colkth, (size_t)3 * (ix->n_vocab > 0 ? ix->n_vocab : 1) * sizeof(float)));
+    if (ix->n_vocab > 0) {
+        const int64_t threads = (int64_t)ix->n_vocab * 32;
+        column_kth_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ix->stream>>>(ix->d_data, ix->d_indptr, ix->n_vocab, ix->d_colkth);
         BM25CU_CHECK(cudaGetLastError());
     }
     unsigned int flag = 0;
@@ -111,6 +176,7 @@ static void destroy(bm25cu_index *ix) {
     cudaFree(ix->d_indptr);
     cudaFree(ix->d_nonocc);
     cudaFree(ix->d_colmax);
+    cudaFree(ix->d_colkth);
     bm25cu::DevBuf *bufs[] = {&ix->d_qtok, &ix->d_qptr, &ix->d_shift, &ix->d_mask, &ix->d_out_ids, &ix->d_out_scores,
                               &ix->d_ctrl, &ix->d_general_list, &ix->d_scratch, &ix->d_spill, &ix->d_order, &ix->d_theta};
     for (auto *b : bufs) b->release();

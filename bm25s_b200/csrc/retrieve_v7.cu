@@ -38,6 +38,7 @@ struct Hdr {
     long long t_df[kTokArr];
     long long w_goff[2][kTokArr];  // global posting index of the token's first posting in the window
     float t_max[kTokArr];     // largest score of the token's column
+    float t_kth[kTokArr];     // k-th largest score of the token's column (0: unknown / fewer than k postings)
     float t_rest[kTokArr];    // upper bound of what the OTHER query tokens can add to a document
     float t_nebound[kTokArr]; // upper bound of a document hit only by this token and tokens with smaller maxima
     int t_n[2][kTokArr];      // staged postings of stage b (essential tokens)
@@ -608,7 +609,7 @@ struct Fast {
         const int ctid = threadIdx.x;  // consumers are warps 0..NW-1; the producer is the last warp
         const int cw = ctid >> 5, lane = ctid & 31;
         const int trigger = p.cbcap / 2;
-        float theta = 0.0f;
+        float theta = h->theta;
         int b = 0;
         bool first_window = true;
         PROF_DECL;
@@ -647,7 +648,7 @@ struct Fast {
                     for (int i = ctid; i < P; i += CNT) cb[i] = (i < m) ? ((unsigned long long)__float_as_uint(sc[i]) << 32) : 0ull;
                     sort_desc<true>(cb, P, ctid, CNT);
                     const unsigned int bits = (unsigned int)(cb[k - 1] >> 32);
-                    theta = bits > 0u ? __uint_as_float(bits - 1u) : 0.0f;  // next float below the k-th sampled score
+                    theta = fmaxf(theta, bits > 0u ? __uint_as_float(bits - 1u) : 0.0f);  // next float below the k-th sampled score
                     bsync<true>();
                     if (ctid == 0) h->theta = theta;
                 }
@@ -758,14 +759,18 @@ struct Fast {
             if (tid < T) {
                 const int tok = p.a.q_tokens[qs + tid];
                 long long beg = 0, end = 0;
-                float mx = 0.0f;
+                float mx = 0.0f, kth = 0.0f;
                 if ((unsigned)tok >= (unsigned)p.n_vocab) atomicOr(&p.ctrl->error, 1u);
-                else { beg = p.indptr[tok]; end = p.indptr[tok + 1]; mx = p.colmax[tok]; }
+                else {
+                    beg = p.indptr[tok]; end = p.indptr[tok + 1]; mx = p.colmax[tok];
+                    if (p.colkth) kth = p.colkth[tok];
+                }
                 h->t_beg[tid] = beg;
                 h->t_cur[tid] = beg;
                 h->t_end[tid] = end;
                 h->t_df[tid] = end - beg;
                 h->t_max[tid] = mx;
+                h->t_kth[tid] = kth;
             }
             if (tid == 0) { h->cb_cnt = 0; h->theta = 0.0f; }
             __syncthreads();
@@ -791,6 +796,12 @@ struct Fast {
                     // float32 sums of <= 15 non-negative terms exceed the exact sum by < 2^-19 relative: pad by 2^-15
                     h->t_rest[lane] = __double2float_ru((msum - (double)mx) * 1.00003);
                     h->t_nebound[lane] = __double2float_ru(below * 1.00003);
+                }
+                // Start threshold: the k-th largest posting of one token is reached by k distinct documents, and a
+                // document scores at least each of its postings (non-negative terms) - the next float below it is safe.
+                {
+                    const unsigned kb = __reduce_max_sync(0xffffffffu, (lane < T) ? __float_as_uint(h->t_kth[lane]) : 0u);
+                    if (lane == 0 && kb > 0u) h->theta = fmaxf(h->theta, __uint_as_float(kb - 1u));
                 }
                 if (lane == 0) {
                     h->total_df = (unsigned long long)tot;
@@ -880,6 +891,14 @@ int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.indices = ix->d_indices;
     p.indptr = ix->d_indptr;
     p.colmax = ix->d_colmax;
+    // the k-th-largest table holds ranks 10 / 100 / 1000: rank r bounds every k <= r (k = 1 uses the column maxima)
+    p.colkth = nullptr;
+    if (env_int7("BM25CU_SEED_KTH", 1) && ix->d_colkth) {
+        if (a.k == 1) p.colkth = ix->d_colmax;
+        else if (a.k <= 10) p.colkth = ix->d_colkth;
+        else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
+        else if (a.k <= 1000) p.colkth = ix->d_colkth + 2 * (size_t)ix->n_vocab;
+    }
     p.prune = env_int7("BM25CU_PRUNE", 1);
     p.max_shift = 2;
     p.n_docs = ix->n_docs;

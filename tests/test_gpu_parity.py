@@ -202,6 +202,46 @@ def test_random_corpus_vs_c_oracle(k):
     dev.close()
 
 
+def test_kth_largest_table_and_seeded_threshold():
+    """The upload-time table of per-column 10th / 100th / 1000th largest scores (start value of the pruning threshold)
+    equals numpy's, and results with and without the seeded threshold are identical."""
+    import ctypes as C
+
+    from bm25s_b200 import DeviceIndex, synth, _lib
+
+    n_docs, n_vocab = 60_000, 200_000
+    corp = synth.make_corpus(n_docs, 40, n_vocab, seed=11)
+    data, indices, indptr, nonocc = O.build_index(corp.to_lists(), n_vocab, "lucene")
+    dev = DeviceIndex.upload(data, indices, indptr, n_docs)
+    out = np.zeros((3, n_vocab), np.float32)
+    _lib.check(_lib.lib().bm25cu_debug_colkth(dev._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+    for ri, r in enumerate((10, 100, 1000)):
+        ref = np.zeros(n_vocab, np.float32)
+        for t in range(n_vocab):
+            col = data[indptr[t]:indptr[t + 1]]
+            if len(col) >= r:
+                ref[t] = np.partition(col, len(col) - r)[len(col) - r]
+        np.testing.assert_array_equal(out[ri], ref, err_msg=f"rank {r}")
+    assert (out[2] > 0).any() and (out[0] == 0).any()  # both long and short columns were exercised
+    queries = synth.make_queries(200, n_vocab, seed=12).to_lists() + [[0, 1, 2, 3], [7, 7]]
+    ptr = np.zeros(len(queries) + 1, np.int64)
+    np.cumsum([len(q) for q in queries], out=ptr[1:])
+    flat = np.array([t for q in queries for t in q], np.int32)
+    for k in (1, 5, 10, 50, 100, 700, 1000, 1500):
+        ids, sc = dev.retrieve(flat, ptr, k)
+        os.environ["BM25CU_SEED_KTH"] = "0"
+        try:
+            ids0, sc0 = dev.retrieve(flat, ptr, k)
+        finally:
+            os.environ.pop("BM25CU_SEED_KTH", None)
+        np.testing.assert_array_equal(sc, sc0, err_msg=f"k={k}")
+        np.testing.assert_array_equal(ids, ids0, err_msg=f"k={k}")
+    rid, rsc = CO.retrieve(data, indices, indptr, n_docs, flat, ptr, 10)
+    ids, sc = dev.retrieve(flat, ptr, 10)
+    np.testing.assert_array_equal(sc, rsc)
+    dev.close()
+
+
 @pytest.mark.parametrize("k", [1, 10, 200])
 def test_alternative_kernel_structure_is_bit_identical(k):
     """BM25CU_KERNEL=7 (bit tags, posting-index splits, hash of non-essential hits) returns exactly what the default
