@@ -1258,7 +1258,7 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     if (threads != 128 && threads != 256 && threads != 1024) threads = 512;
     const int ctas_per_sm = env_int("BM25CU_CTAS_PER_SM", 1);
     const int kcap = next_pow2(a.k < 1 ? 1 : a.k);
-    const int cb_min = env_int("BM25CU_CBMIN", 512);
+    const int cb_min = env_int("BM25CU_CBMIN", 32);  // candidate buffer: 2 * next_pow2(k) entries unless raised (small buffers compact often and keep theta fresh)
     p.cbcap = 2 * kcap < cb_min ? next_pow2(cb_min) : 2 * kcap;
     p.route_all_general = (!ix->nonneg) || (a.mask != nullptr) || (a.k > 2048) || env_int("BM25CU_FORCE_GENERAL", 0);
     const int budget = ix->max_smem_optin / (ctas_per_sm > 0 ? ctas_per_sm : 1) - (ctas_per_sm > 1 ? 1024 : 0);

@@ -910,7 +910,7 @@ int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     int threads = env_int7("BM25CU_THREADS", 512);
     if (threads != 256 && threads != 1024) threads = 512;
     const int kcap = next_pow2(a.k < 1 ? 1 : a.k);
-    const int cb_min = env_int7("BM25CU_CBMIN", 512);
+    const int cb_min = env_int7("BM25CU_CBMIN", 32);
     p.cbcap = 2 * kcap < cb_min ? next_pow2(cb_min) : 2 * kcap;
     p.route_all_general = (!ix->nonneg) || (a.mask != nullptr) || (a.k > 2048) || env_int7("BM25CU_FORCE_GENERAL", 0);
     const int ctas_per_sm = env_int7("BM25CU_CTAS_PER_SM", 1) == 2 ? 2 : 1;
