@@ -9,6 +9,34 @@ using namespace bm25cu;
 
 namespace {
 
+// K0: pull order of the batch - queries bucketed by log2 of their posting count, longest first, so that the persistent
+// CTAs of K1 do not end on a long query (longest-processing-time-first; the order inside a bucket is arbitrary and does
+// not affect results). One CTA; `bucket` is n_queries bytes of scratch behind the order array.
+__global__ void __launch_bounds__(1024) order_queries_kernel(const int32_t *__restrict__ q_tokens, const int64_t *__restrict__ q_ptr,
+                                                             int32_t n_queries, const int64_t *__restrict__ indptr, int32_t n_vocab,
+                                                             unsigned int *order, unsigned char *bucket) {
+    __shared__ unsigned int hist[64], base[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int q = threadIdx.x; q < n_queries; q += blockDim.x) {
+        unsigned long long cost = 0;
+        for (int64_t i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
+            const int tok = q_tokens[i];
+            if ((unsigned)tok < (unsigned)n_vocab) cost += (unsigned long long)(indptr[tok + 1] - indptr[tok]);
+        }
+        const int bk = cost ? 64 - __clzll((long long)cost) : 0;  // 0 .. 63
+        bucket[q] = (unsigned char)bk;
+        atomicAdd(&hist[bk], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int bk = 63; bk >= 0; --bk) { base[bk] = acc; acc += hist[bk]; }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < n_queries; q += blockDim.x) order[atomicAdd(&base[bucket[q]], 1u)] = (unsigned int)q;
+}
+
 int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, int64_t n_query_tokens,
                            bool time_total_already_started) {
     (void)time_total_already_started;
@@ -19,6 +47,19 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
     BM25CU_CHECK(cudaMemsetAsync(d_ctrl, 0, sizeof(Ctrl), ix->stream));
     int launches = 0;
     BM25CU_CHECK(cudaEventRecord(ix->ev[1], ix->stream));
+    {
+        const char *ov = getenv("BM25CU_ORDER");
+        ix->order_valid = false;
+        if (a.n_queries > 1 && !(ov && *ov && atoi(ov) == 0)) {
+            if ((rc = ix->d_order.reserve((size_t)a.n_queries * 5))) return rc;
+            order_queries_kernel<<<1, 1024, 0, ix->stream>>>(a.q_tokens, a.q_ptr, a.n_queries, ix->d_indptr, ix->n_vocab,
+                                                             ix->d_order.as<unsigned int>(),
+                                                             ix->d_order.as<unsigned char>() + (size_t)a.n_queries * 4);
+            BM25CU_CHECK(cudaGetLastError());
+            ix->order_valid = true;
+            ++launches;
+        }
+    }
     {
         // BM25CU_KERNEL selects the structure of K1: 5 (default) = per-warp document sub-ranges (retrieve_fast.cu),
         // 7 = bit tags + posting-index splits with barriers between the phases (retrieve_v7.cu, experimental)

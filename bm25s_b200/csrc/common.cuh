@@ -106,6 +106,7 @@ struct bm25cu_index {
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,
         d_spill, d_order, d_theta;
+    bool order_valid = false;      // d_order holds the pull order of the current batch
     bm25cu::PinBuf h_in, h_out;
     int general_rows = 0;
 };

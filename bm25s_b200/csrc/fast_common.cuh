@@ -31,6 +31,7 @@ struct FastParams {
     const int32_t *indices;
     const int64_t *indptr;
     const float *colmax;
+    const unsigned int *order;  // queries in the order the CTAs pull them (longest first); nullptr: index order
     const float *colkth;  // column of the k-th-largest table that is valid for this k (nullptr: no seed)
     int32_t n_docs, n_vocab, doc_base;
     RetrieveArgs a;

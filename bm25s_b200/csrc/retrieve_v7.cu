@@ -747,7 +747,7 @@ struct Fast {
             __syncthreads();
             const unsigned int slot = h->q_slot;
             if (slot >= (unsigned)p.a.n_queries) break;
-            const int q = (int)slot;
+            const int q = p.order ? (int)p.order[slot] : (int)slot;
             const long long qs = p.a.q_ptr[q], qe = p.a.q_ptr[q + 1];
             const long long Tl = qe - qs;
             if (p.route_all_general || Tl > kMaxTok) {
@@ -891,6 +891,7 @@ int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.indices = ix->d_indices;
     p.indptr = ix->d_indptr;
     p.colmax = ix->d_colmax;
+    p.order = ix->order_valid ? ix->d_order.as<unsigned int>() : nullptr;
     // the k-th-largest table holds ranks 10 / 100 / 1000: rank r bounds every k <= r (k = 1 uses the column maxima)
     p.colkth = nullptr;
     if (env_int7("BM25CU_SEED_KTH", 1) && ix->d_colkth) {
