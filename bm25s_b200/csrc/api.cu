@@ -50,7 +50,7 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
     {
         const char *ov = getenv("BM25CU_ORDER");
         ix->order_valid = false;
-        if (a.n_queries > 1 && !(ov && *ov && atoi(ov) == 0)) {
+        if (a.n_queries >= 4 * ix->sm_count && !(ov && *ov && atoi(ov) == 0)) {  // small batches: every CTA gets at most a few queries
             if ((rc = ix->d_order.reserve((size_t)a.n_queries * 5))) return rc;
             order_queries_kernel<<<1, 1024, 0, ix->stream>>>(a.q_tokens, a.q_ptr, a.n_queries, ix->d_indptr, ix->n_vocab,
                                                              ix->d_order.as<unsigned int>(),
