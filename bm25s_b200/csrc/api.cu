@@ -37,6 +37,17 @@ __global__ void __launch_bounds__(1024) order_queries_kernel(const int32_t *__re
     for (int q = threadIdx.x; q < n_queries; q += blockDim.x) order[atomicAdd(&base[bucket[q]], 1u)] = (unsigned int)q;
 }
 
+// A weight mask with all values in [0, 1] only lowers scores, so the pruning bounds of K1 stay valid and the mask is
+// applied where a candidate is emitted; anything else (negative, > 1, NaN) sends the batch to the dense kernel.
+__global__ void mask_check_kernel(const double *__restrict__ mask, int64_t n, Ctrl *ctrl) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double m = mask[i];
+        if (!(m >= 0.0 && m <= 1.0)) bad = true;
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) ctrl->mask_bad = 1u;
+}
+
 int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, int64_t n_query_tokens,
                            bool time_total_already_started) {
     (void)time_total_already_started;
@@ -47,6 +58,11 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
     BM25CU_CHECK(cudaMemsetAsync(d_ctrl, 0, sizeof(Ctrl), ix->stream));
     int launches = 0;
     BM25CU_CHECK(cudaEventRecord(ix->ev[1], ix->stream));
+    if (a.mask && ix->n_docs > 0) {
+        mask_check_kernel<<<ix->sm_count * 2, 512, 0, ix->stream>>>(a.mask, ix->n_docs, d_ctrl);
+        BM25CU_CHECK(cudaGetLastError());
+        ++launches;
+    }
     {
         const char *ov = getenv("BM25CU_ORDER");
         ix->order_valid = false;

@@ -132,7 +132,8 @@ struct Ctrl {
     unsigned int general_next;
     unsigned int error;          // bit 0: token id out of range
     unsigned long long posting_count;
-    unsigned int pad[2];
+    unsigned int mask_bad;       // weight mask has values outside [0, 1] (or NaN): every query takes the general kernel
+    unsigned int pad;
     unsigned long long prof[32];  // phase cycle counters / event counts of the fused kernel (BM25CU_PROFILE builds)
 };
 

@@ -175,6 +175,10 @@ struct Fast {
     }
 
     __device__ __forceinline__ void emit(float s, int d) {
+        if (p.a.mask) {  // weight mask in [0, 1]: numpy multiplies in the promoted type and rounds back to float32
+            s = (float)((double)s * p.a.mask[d]);
+            if (!(s > *reinterpret_cast<volatile float *>(&h->theta))) return;
+        }
         const unsigned int slot = atomicAdd(&h->cb_cnt, 1u);
         const unsigned long long c = pack_cand(s, d);
         if (slot < (unsigned)p.cbcap) cb[slot] = c;
@@ -642,7 +646,7 @@ struct Fast {
                     if (c > best_c) { best_c = c; best_t = t; }
                 }
                 const int m = min(best_c, p.cbcap);
-                if (m >= k) {
+                if (m >= k && p.a.mask == nullptr) {
                     const int P = next_pow2(m);
                     const float *sc = bpf + h->w_sc[b][best_t];
                     for (int i = ctid; i < P; i += CNT) cb[i] = (i < m) ? ((unsigned long long)__float_as_uint(sc[i]) << 32) : 0ull;
@@ -750,7 +754,7 @@ struct Fast {
             const int q = p.order ? (int)p.order[slot] : (int)slot;
             const long long qs = p.a.q_ptr[q], qe = p.a.q_ptr[q + 1];
             const long long Tl = qe - qs;
-            if (p.route_all_general || Tl > kMaxTok) {
+            if (p.route_all_general || Tl > kMaxTok || (p.a.mask && p.ctrl->mask_bad)) {
                 if (tid == 0) p.general_list[atomicAdd(&p.ctrl->general_count, 1u)] = (unsigned)q;
                 __syncthreads();
                 continue;
@@ -894,7 +898,7 @@ int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.order = ix->order_valid ? ix->d_order.as<unsigned int>() : nullptr;
     // the k-th-largest table holds ranks 10 / 100 / 1000: rank r bounds every k <= r (k = 1 uses the column maxima)
     p.colkth = nullptr;
-    if (env_int7("BM25CU_SEED_KTH", 1) && ix->d_colkth) {
+    if (env_int7("BM25CU_SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {  // a mask may remove the documents behind the bound
         if (a.k == 1) p.colkth = ix->d_colmax;
         else if (a.k <= 10) p.colkth = ix->d_colkth;
         else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
@@ -913,7 +917,8 @@ int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     const int kcap = next_pow2(a.k < 1 ? 1 : a.k);
     const int cb_min = env_int7("BM25CU_CBMIN", 32);
     p.cbcap = 2 * kcap < cb_min ? next_pow2(cb_min) : 2 * kcap;
-    p.route_all_general = (!ix->nonneg) || (a.mask != nullptr) || (a.k > 2048) || env_int7("BM25CU_FORCE_GENERAL", 0);
+    p.route_all_general = (!ix->nonneg) || (a.k > 2048) || env_int7("BM25CU_FORCE_GENERAL", 0) ||
+                          (a.mask != nullptr && env_int7("BM25CU_MASK_FAST", 1) == 0);
     const int ctas_per_sm = env_int7("BM25CU_CTAS_PER_SM", 1) == 2 ? 2 : 1;
     if (ctas_per_sm == 2) threads = 256;
     const int budget = ix->max_smem_optin / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);

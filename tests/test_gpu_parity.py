@@ -202,6 +202,45 @@ def test_random_corpus_vs_c_oracle(k):
     dev.close()
 
 
+def test_weight_mask_fast_path():
+    """masks with values in [0, 1] stay on the fused kernel (applied where a candidate is emitted, numpy
+    order: mask before shift); results equal the C oracle's and the dense general kernel's. Other masks are routed."""
+    from bm25s_b200 import DeviceIndex, synth
+
+    n_docs, n_vocab = 120_000, 20_000
+    corp = synth.make_corpus(n_docs, 30, n_vocab, seed=21)
+    data, indices, indptr, nonocc = O.build_index(corp.to_lists(), n_vocab, "bm25l")
+    queries = synth.make_queries(96, n_vocab, seed=22).to_lists() + [[0, 1, 2], [3, 3], list(range(10))]
+    ptr = np.zeros(len(queries) + 1, np.int64)
+    np.cumsum([len(q) for q in queries], out=ptr[1:])
+    flat = np.array([t for q in queries for t in q], np.int32)
+    sh = np.array([O.query_shift(nonocc, q) for q in queries], np.float32)
+    rng = np.random.default_rng(23)
+    dev = DeviceIndex.upload(data, indices, indptr, n_docs, nonocc=nonocc)
+    masks = {"01": (rng.random(n_docs) < 0.3).astype(np.float64), "unit": rng.random(n_docs),
+             "sparse": (rng.random(n_docs) < 0.0005).astype(np.float64), "zeros": np.zeros(n_docs)}
+    for name, mask in masks.items():
+        for k in (1, 10, 300):
+            ids, sc, st = dev.retrieve(flat, ptr, k, shift=sh, mask=mask, with_stats=True)
+            assert st["n_general"] == 0, name
+            rid, rsc = CO.retrieve(data, indices, indptr, n_docs, flat, ptr, k, shift=sh, mask=mask)
+            dense_fn = lambda qi: CO.scores_dense(data, indices, indptr, n_docs, queries[qi], shift=sh[qi], mask=mask)  # noqa: E731
+            check_topk_rows(ids, sc, rid, rsc, dense_fn if k <= 10 else None, what=f"mask {name} k={k}")
+            os.environ["BM25CU_MASK_FAST"] = "0"
+            try:
+                ids_g, sc_g, st_g = dev.retrieve(flat, ptr, k, shift=sh, mask=mask, with_stats=True)
+            finally:
+                os.environ.pop("BM25CU_MASK_FAST", None)
+            assert st_g["n_general"] == len(queries)
+            np.testing.assert_array_equal(sc, sc_g, err_msg=f"mask {name} k={k}")
+    for bad in (np.where(rng.random(n_docs) < 0.5, 2.0, 0.5), np.where(rng.random(n_docs) < 0.01, -1.0, 1.0)):
+        ids, sc, st = dev.retrieve(flat, ptr, 10, shift=sh, mask=bad, with_stats=True)
+        assert st["n_general"] == len(queries)  # values outside [0, 1]: the dense kernel
+        rid, rsc = CO.retrieve(data, indices, indptr, n_docs, flat, ptr, 10, shift=sh, mask=bad)
+        np.testing.assert_array_equal(sc, rsc)
+    dev.close()
+
+
 def test_kth_largest_table_and_seeded_threshold():
     """The upload-time table of per-column 10th / 100th / 1000th largest scores (start value of the pruning threshold)
     equals numpy's, and results with and without the seeded threshold are identical."""
