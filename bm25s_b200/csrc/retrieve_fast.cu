@@ -73,6 +73,8 @@ struct SmemHdr {
     int w_last[2];            // 1 if this is the query's last window
     int w_ME[2], w_MN[2];     // essential / non-essential postings in the window
     unsigned int w_kept[2];   // warps with essential postings that survived the upper-bound filter
+    unsigned int sel_hist[256];  // radix-select histogram of the candidate cut (large k)
+    unsigned int sel_bin, sel_need, sel_cnt;
     unsigned int q_slot;
     unsigned int cb_cnt;
     unsigned int r_cnt;
@@ -410,34 +412,88 @@ struct Fast {
         bsync<CONS>();
     }
 
-    // Cut the candidate buffer back to the k best (key order: score desc, doc asc); theta = k-th best score.
-    // Leaves cb[0..cb_cnt) sorted descending.
+    // Keeps the min(n, k) largest of cb[0..n) in cb[0..min(n, k)) and returns the k-th largest key (0 if n < k).
+    // Small buffers (or want_sorted) are sorted; large ones are cut by an MSB-first radix select on the 64-bit keys
+    // (keys are unique, so exactly k survive) followed by an in-place partition - no sort until the query's final cut.
     template <bool CONS>
-    __device__ void compact(int k, int id, int nthr) {
+    __device__ unsigned long long cut_to_k(unsigned int n, int k, int id, int nthr, bool want_sorted) {
+        const int P = next_pow2((int)(n > 0 ? n : 1));
+        if (want_sorted || P < 512 || n <= (unsigned)k) {
+            for (int i = (int)n + id; i < P; i += nthr) cb[i] = 0ull;
+            sort_desc<CONS>(cb, P, id, nthr);
+            return (n >= (unsigned)k) ? cb[k - 1] : 0ull;
+        }
+        unsigned long long prefix = 0ull, mask = 0ull;
+        unsigned int need = (unsigned int)k;
+        for (int pass = 7; pass >= 0; --pass) {
+            const int shift = 8 * pass;
+            for (int i = id; i < 256; i += nthr) h->sel_hist[i] = 0u;
+            bsync<CONS>();
+            for (unsigned int i = id; i < n; i += nthr) {
+                const unsigned long long key = cb[i];
+                if ((key & mask) == prefix) atomicAdd(&h->sel_hist[(unsigned int)(key >> shift) & 0xFFu], 1u);
+            }
+            bsync<CONS>();
+            if (id < 32) {  // lane L owns bins 8 L .. 8 L + 7; the bin holding the need-th largest live key, from the top
+                unsigned int cnt[8], lane_sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { cnt[j] = h->sel_hist[id * 8 + j]; lane_sum += cnt[j]; }
+                unsigned int above = lane_sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_down_sync(0xffffffffu, above, o); if (id + o < 32) above += y; }
+                above -= lane_sum;
+                if (above < need && need <= above + lane_sum) {
+                    unsigned int acc = above;
+                    for (int j = 7; j >= 0; --j) {
+                        if (acc + cnt[j] >= need) { h->sel_bin = (unsigned int)(id * 8 + j); h->sel_need = need - acc; break; }
+                        acc += cnt[j];
+                    }
+                }
+            }
+            bsync<CONS>();
+            prefix |= (unsigned long long)h->sel_bin << shift;
+            mask |= 0xFFull << shift;
+            need = h->sel_need;
+        }
+        const unsigned long long thr = prefix;  // the k-th largest key
+        if (id == 0) h->sel_cnt = 0u;
+        bsync<CONS>();
+        // in-place partition, one chunk of nthr elements at a time: a survivor is written below the number of elements
+        // already read, so nothing unread is overwritten
+        for (unsigned int base = 0; base < n; base += (unsigned int)nthr) {
+            const unsigned int i = base + (unsigned int)id;
+            const unsigned long long key = (i < n) ? cb[i] : 0ull;
+            bsync<CONS>();
+            if (i < n && key >= thr) cb[atomicAdd(&h->sel_cnt, 1u)] = key;
+        }
+        bsync<CONS>();
+        return thr;
+    }
+
+    // Cut the candidate buffer back to the k best (key order: score desc, doc asc); theta = k-th best score.
+    // want_sorted: leaves cb[0..cb_cnt) sorted descending (the query's final cut).
+    template <bool CONS>
+    __device__ void compact(int k, int id, int nthr, bool want_sorted = false) {
         bsync<CONS>();
         const unsigned int total = min(h->cb_cnt, (unsigned)(p.cbcap + p.spillcap));
         unsigned int n = min(total, (unsigned)p.cbcap);
         const unsigned int spilled = total - n;
         unsigned int sp_done = 0;
         for (;;) {
-            const int P = next_pow2((int)(n > 0 ? n : 1));
-            for (int i = (int)n + id; i < P; i += nthr) cb[i] = 0ull;
-            sort_desc<CONS>(cb, P, id, nthr);
-#ifdef BM25CU_PROFILE
-            if (id == 0) { atomicAdd(&p.ctrl->prof[30], 1ull); atomicAdd(&p.ctrl->prof[31], (unsigned long long)P); if (sp_done == 0) atomicAdd(&p.ctrl->prof[29], (unsigned long long)spilled); }
-#endif
+            const bool final_cut = sp_done >= spilled;
+            const unsigned long long kth = cut_to_k<CONS>(n, k, id, nthr, want_sorted && final_cut);
             const unsigned int keep = min(n, (unsigned)k);
-            if (sp_done >= spilled) {
+            if (final_cut) {
                 if (id == 0) {
                     h->cb_cnt = keep;
-                    if (keep == (unsigned)k) h->theta = fmaxf(h->theta, cand_score(cb[k - 1]));
+                    if (keep == (unsigned)k) h->theta = fmaxf(h->theta, cand_score(kth));
                 }
                 bsync<CONS>();
                 return;
             }
             // Spilled candidates: those that still beat the k-th key are poured into the free room tile by tile; the
-            // buffer is sorted again only when the room is (nearly) used up - most tiles are filtered out entirely.
-            const unsigned long long th_key = (keep == (unsigned)k) ? cb[k - 1] : 0ull;  // full key: score, then lower doc id
+            // buffer is cut again only when the room is (nearly) used up - most tiles are filtered out entirely.
+            const unsigned long long th_key = (keep == (unsigned)k) ? kth : 0ull;  // full key: score, then lower doc id
             if (id == 0) h->cb_cnt = keep;
             unsigned int cur = keep;
             for (;;) {
@@ -1179,7 +1235,7 @@ struct Fast {
     __device__ void finalize(int q, int T) {
         const int tid = threadIdx.x;
         const int k = p.a.k;
-        compact<false>(k, tid, NT);  // leaves cb[0..n) sorted descending, n <= k
+        compact<false>(k, tid, NT, true);  // leaves cb[0..n) sorted descending, n <= k
         const int n = (int)h->cb_cnt;
         if (p.theta_mode == 1 && tid == 0) {
             const unsigned int bits = (n == k) ? (unsigned int)(cb[k - 1] >> 32) : 0u;

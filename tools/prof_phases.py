@@ -13,7 +13,7 @@ data, indices, indptr, nonocc = synth.csc_from_tokens_torch(tokens, ptr, n_vocab
 del tokens, ptr
 qt, qp = synth.make_queries_torch(n_queries, n_vocab, seed=1, device=dev)
 ix = DeviceIndex.upload_device(data.data_ptr(), indices.data_ptr(), indptr.data_ptr(), data.numel(), n_vocab, n_docs)
-k = 10
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 oi = torch.empty((n_queries, k), dtype=torch.int32, device=dev); os_ = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
 for it in range(3):
     st = ix.retrieve_device(qt.data_ptr(), qp.data_ptr(), n_queries, int(qp[-1]), k, oi.data_ptr(), os_.data_ptr())
