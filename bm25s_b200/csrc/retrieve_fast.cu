@@ -1320,7 +1320,10 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     const int ctas_per_sm = env_int("BM25CU_CTAS_PER_SM", 1);
     const int kcap = next_pow2(a.k < 1 ? 1 : a.k);
     const int cb_min = env_int("BM25CU_CBMIN", 32);  // candidate buffer: 2 * next_pow2(k) entries unless raised (small buffers compact often and keep theta fresh)
-    p.cbcap = 2 * kcap < cb_min ? next_pow2(cb_min) : 2 * kcap;
+    // 2 * next_pow2(k) keys for small k; four times for larger k (fewer cuts), never more than 4096 unless k needs it
+    int cb_auto = kcap <= 64 ? 2 * kcap : 4 * kcap;
+    if (cb_auto > 4096) cb_auto = 2 * kcap > 4096 ? 2 * kcap : 4096;
+    p.cbcap = cb_auto < cb_min ? next_pow2(cb_min) : cb_auto;
     p.route_all_general = (!ix->nonneg) || (a.k > 2048) || env_int("BM25CU_FORCE_GENERAL", 0) ||
                           (a.mask != nullptr && env_int("BM25CU_MASK_FAST", 1) == 0);
     const int budget = ix->max_smem_optin / (ctas_per_sm > 0 ? ctas_per_sm : 1) - (ctas_per_sm > 1 ? 1024 : 0);

@@ -976,7 +976,10 @@ int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     if (threads != 256 && threads != 1024) threads = 512;
     const int kcap = next_pow2(a.k < 1 ? 1 : a.k);
     const int cb_min = env_int7("BM25CU_CBMIN", 32);
-    p.cbcap = 2 * kcap < cb_min ? next_pow2(cb_min) : 2 * kcap;
+    // 2 * next_pow2(k) keys for small k; four times for larger k (fewer cuts), never more than 4096 unless k needs it
+    int cb_auto = kcap <= 64 ? 2 * kcap : 4 * kcap;
+    if (cb_auto > 4096) cb_auto = 2 * kcap > 4096 ? 2 * kcap : 4096;
+    p.cbcap = cb_auto < cb_min ? next_pow2(cb_min) : cb_auto;
     p.route_all_general = (!ix->nonneg) || (a.k > 2048) || env_int7("BM25CU_FORCE_GENERAL", 0) ||
                           (a.mask != nullptr && env_int7("BM25CU_MASK_FAST", 1) == 0);
     const int ctas_per_sm = env_int7("BM25CU_CTAS_PER_SM", 1) == 2 ? 2 : 1;
