@@ -1135,7 +1135,7 @@ struct Fast {
             if (last) break;
             if (p.stages == 2) b ^= 1;
         }
-        PROF_FLUSH(ctid == 0);
+        PROF_FLUSH(ctid == 32 * (p.debug >> 8));
     }
 
     __device__ void run() {
