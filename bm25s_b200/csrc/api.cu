@@ -104,6 +104,14 @@ int finish_stats(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, i
         set_error("The maximum token ID in the query is higher than the number of tokens in the index.");
         return BM25CU_EINVAL;
     }
+    if (h.error & 4u) {
+        set_error("internal error: candidate buffer overflow in the fused kernel");
+        return BM25CU_ECUDA;
+    }
+    if (h.error & 2u) {
+        set_error("internal error: search did not converge in the fused kernel");
+        return BM25CU_ECUDA;
+    }
     if (stats) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[3]);

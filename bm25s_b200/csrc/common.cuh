@@ -130,7 +130,7 @@ struct Ctrl {
     unsigned int fast_next;      // work-queue cursor of the fused kernel
     unsigned int general_count;  // number of queries routed to the general kernel
     unsigned int general_next;
-    unsigned int error;          // bit 0: token id out of range
+    unsigned int error;          // bit 0: token id out of range; bits 1-2: internal invariants of the fused kernel
     unsigned long long posting_count;
     unsigned int mask_bad;       // weight mask has values outside [0, 1] (or NaN): every query takes the general kernel
     unsigned int pad;

@@ -49,6 +49,7 @@ struct FastParams {
     int debug;     // timing experiments only (BM25CU_DEBUG_SKIP bit mask; results are wrong when non-zero)
     float *theta_io;  // experiment: per-query final threshold written (theta_mode 1) / used as the start value (2)
     int theta_mode;
+    int trigger;   // candidate count at a window end that starts a cut of the buffer
     int stages;    // stage buffers of the posting pool (2: the next window loads while this one is processed)
     int hash_max;  // v6: inserts into the per-window contribution hash before falling back to global searches
 };

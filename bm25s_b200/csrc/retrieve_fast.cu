@@ -394,6 +394,7 @@ struct Fast {
         const unsigned long long c = pack_cand(s, d);
         if (slot < (unsigned)p.cbcap) cb[slot] = c;
         else if (slot - p.cbcap < (unsigned)p.spillcap) spill[slot - p.cbcap] = c;
+        else atomicOr(&p.ctrl->error, 4u);  // cannot happen: a window emits at most poolcap / 2 candidates between two cuts
     }
 
     // bitonic sort of key[0..P) descending (P power of two, <= cbcap), shared memory
@@ -961,7 +962,7 @@ struct Fast {
     __device__ void consumer(int T, int k, uint32_t &ph_meta0, uint32_t &ph_meta1) {
         const int ctid = threadIdx.x;  // consumers are warps 0..NW-1; the producer is the last warp (the scheduler favours it)
         const int cw = ctid >> 5, lane = ctid & 31;
-        const int trigger = p.cbcap / 2;
+        const int trigger = p.trigger;
         float theta = h->theta;
         int b = 0;
         bool first_window = true;
@@ -1340,6 +1341,7 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     }
     // pool: 4-byte slots per stage
     p.stages = env_int("BM25CU_STAGES", 2) == 1 ? 1 : 2;
+    p.trigger = 0;
     int pool = env_int("BM25CU_POOL", ctas_per_sm > 1 ? 6144 : (p.stages == 1 ? 24576 : 14336));
     pool = (pool + 3) & ~3;
     const int min_pool = kMaxTok * 2 * kMinCap + 256;
@@ -1358,6 +1360,9 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     const int tag_env = env_int("BM25CU_TAG", 0);
     if (tag_env > 0 && tag_env < tagcap) tagcap = tag_env;
     p.tagcap = (int)(tagcap & ~15ll);
+    p.trigger = env_int("BM25CU_TRIGGER", p.cbcap / 2);  // candidates that start a cut of the buffer at a window end
+    if (p.trigger <= a.k) p.trigger = a.k + 1;
+    if (p.trigger > p.cbcap) p.trigger = p.cbcap;
     p.spillcap = (p.stages == 1 ? 1 : 2) * p.poolcap;
     const int grid = ix->sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1);
     int rc = ix->d_spill.reserve((size_t)grid * (size_t)p.spillcap * 8);

@@ -185,6 +185,7 @@ struct Fast {
         const unsigned long long c = pack_cand(s, d);
         if (slot < (unsigned)p.cbcap) cb[slot] = c;
         else if (slot - p.cbcap < (unsigned)p.spillcap) spill[slot - p.cbcap] = c;
+        else atomicOr(&p.ctrl->error, 4u);  // cannot happen: a window emits at most poolcap / 2 candidates between two cuts
     }
     // bitonic sort of key[0..P) descending (P power of two, <= cbcap), shared memory
     template <bool CONS>
@@ -672,7 +673,7 @@ struct Fast {
     __device__ void consumer(int T, int k, uint32_t &ph_meta0, uint32_t &ph_meta1) {
         const int ctid = threadIdx.x;  // consumers are warps 0..NW-1; the producer is the last warp
         const int cw = ctid >> 5, lane = ctid & 31;
-        const int trigger = p.cbcap / 2;
+        const int trigger = p.trigger;
         float theta = h->theta;
         int b = 0;
         bool first_window = true;
@@ -1010,6 +1011,9 @@ int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     const int tag_env = env_int7("BM25CU_TAG", 0);
     if (tag_env > 0 && tag_env < tagcap) tagcap = tag_env;
     p.tagcap = (int)(tagcap & ~15ll);
+    p.trigger = env_int7("BM25CU_TRIGGER", p.cbcap / 2);
+    if (p.trigger <= a.k) p.trigger = a.k + 1;
+    if (p.trigger > p.cbcap) p.trigger = p.cbcap;
     p.spillcap = 2 * p.poolcap;
     const int grid = ix->sm_count * ctas_per_sm;
     int rc = ix->d_spill.reserve((size_t)grid * (size_t)p.spillcap * 8);
