@@ -992,7 +992,7 @@ struct Fast {
                     if (c > best_c) { best_c = c; best_t = t; }
                 }
                 const int m = min(best_c, p.cbcap);
-                if (m >= k && p.a.mask == nullptr) {
+                if (m >= k && p.a.mask == nullptr && theta == 0.0f) {  // only when the k-th-largest table gave no start value
                     const int P = next_pow2(m);
                     const float *sc = bpf + h->w_sc[b][best_t];
                     for (int i = ctid; i < P; i += CNT) cb[i] = (i < m) ? ((unsigned long long)__float_as_uint(sc[i]) << 32) : 0ull;

@@ -7,6 +7,8 @@ import torch
 from bm25s_b200 import synth, DeviceIndex
 shape = sys.argv[1] if len(sys.argv) > 1 else 'msmarco'
 n_docs, avg_len, n_vocab, n_queries = synth.SHAPES[shape]
+if len(sys.argv) > 3:
+    n_docs = int(sys.argv[3])  # emulates one doc-range shard
 dev = torch.device('cuda')
 tokens, ptr = synth.make_corpus_torch(n_docs, avg_len, n_vocab, seed=0, device=dev)
 data, indices, indptr, nonocc = synth.csc_from_tokens_torch(tokens, ptr, n_vocab)
