@@ -301,8 +301,10 @@ __device__ __forceinline__ void chunks_clean(uint32_t chunk_s, int nch, float th
     }
 }
 
-// P2 (non-essential), vectorised: each lane probes four consecutive document ids per 16-byte load
-__device__ __forceinline__ void probe4(const uint4 dv, int sh, unsigned gmask, uint32_t tagv) {
+// P2 (non-essential), vectorised: each lane probes four consecutive document ids per 16-byte load. `gs` points to the
+// global score of the first of the four postings: a hit prefetches its score into L2, the slow path reads it later.
+__device__ __forceinline__ void prefetch_l2(const float *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ void probe4(const uint4 dv, int sh, unsigned gmask, uint32_t tagv, const float *gs) {
     const unsigned d[4] = {dv.x, dv.y, dv.z, dv.w};
     unsigned x[4];
 #pragma unroll
@@ -314,33 +316,34 @@ __device__ __forceinline__ void probe4(const uint4 dv, int sh, unsigned gmask, u
     if (hit) {  // rare
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if ((hit >> u) & 1u) sts8(tagv + (d[u] >> sh), x[u] | kTagContested);
+            if ((hit >> u) & 1u) { sts8(tagv + (d[u] >> sh), x[u] | kTagContested); prefetch_l2(gs + u); }
     }
 }
-__device__ __forceinline__ void pass_probe_n_vec(const Seg &g, int sh, unsigned gmask, uint32_t tagv, int lane) {
+__device__ __forceinline__ void pass_probe_n_vec(const Seg &g, int sh, unsigned gmask, uint32_t tagv, int lane, const float *gs) {
     // head: scalar elements up to the first 16-byte boundary
     const int head = min(g.n, (int)((4u - ((g.docs >> 2) & 3u)) & 3u));
     if (lane < head) {
         const unsigned d = lds32(g.docs + 4u * lane);
         const unsigned x = lds8(tagv + (d >> sh));
-        if ((x & 7u) == (kTagValid | (d & gmask))) sts8(tagv + (d >> sh), x | kTagContested);
+        if ((x & 7u) == (kTagValid | (d & gmask))) { sts8(tagv + (d >> sh), x | kTagContested); prefetch_l2(gs + lane); }
     }
     const int nbody = g.n - head;
     const int nv = nbody >> 2;  // full vectors
     const uint32_t vb = g.docs + 4u * head;
+    const float *gv = gs + head;
     int i = lane;
     for (; i + 32 < nv; i += 64) {  // two vectors per lane in flight
         const uint4 a = lds128(vb + 16u * i), b2 = lds128(vb + 16u * (i + 32));
-        probe4(a, sh, gmask, tagv);
-        probe4(b2, sh, gmask, tagv);
+        probe4(a, sh, gmask, tagv, gv + 4 * i);
+        probe4(b2, sh, gmask, tagv, gv + 4 * (i + 32));
     }
-    if (i < nv) probe4(lds128(vb + 16u * i), sh, gmask, tagv);
+    if (i < nv) probe4(lds128(vb + 16u * i), sh, gmask, tagv, gv + 4 * i);
     // tail
     const int tail0 = head + (nv << 2);
     if (lane < g.n - tail0) {
         const unsigned d = lds32(g.docs + 4u * (tail0 + lane));
         const unsigned x = lds8(tagv + (d >> sh));
-        if ((x & 7u) == (kTagValid | (d & gmask))) sts8(tagv + (d >> sh), x | kTagContested);
+        if ((x & 7u) == (kTagValid | (d & gmask))) { sts8(tagv + (d >> sh), x | kTagContested); prefetch_l2(gs + tail0 + lane); }
     }
 }
 
@@ -831,6 +834,7 @@ struct Fast {
     // (several postings of the same document may be listed).
     __device__ void resolve_slow(int b, int T, int cw, uint32_t pool_s, float theta, int n) {
         const int lane = threadIdx.x & 31;
+        if (p.debug & 64) return;  // timing experiment: what the slow path costs
         __syncwarp();
         if (lane < n) {
             const int2 e = h->w_slow[cw][lane];
@@ -915,7 +919,7 @@ struct Fast {
         }
         for (unsigned m = nmask; m; m &= m - 1) {
             const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-            pass_probe_n_vec(g, sh, gmask, tagv, lane);
+            pass_probe_n_vec(g, sh, gmask, tagv, lane, p.data + h->w_goff[b][g.t] + h->s_lo[cw][g.t]);
         }
         __syncwarp();
         // P3
@@ -1093,7 +1097,7 @@ struct Fast {
                     if (!(p.debug & 1))
                     for (unsigned m = nmask; m; m &= m - 1) {
                         const Seg g = slice_of(b, __ffs(m) - 1, cw, pool_s);
-                        pass_probe_n_vec(g, sh, gmask, tagv, lane);
+                        pass_probe_n_vec(g, sh, gmask, tagv, lane, p.data + h->w_goff[b][g.t] + h->s_lo[cw][g.t]);
                     }
                     PROF(5);
                     __syncwarp();
