@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--n-docs", type=int, default=0, help="override the shape's document count (debugging)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--local-shards", action="store_true",
+                    help="N > 1: every rank generates only its own doc range (seed 1000 + rank); implied by --shape 100m")
     return ap.parse_args()
 
 
@@ -98,12 +100,21 @@ def shape_of(args):
     return n_docs, avg_len, n_vocab, n_queries
 
 
-def build_corpus(args, device):
+def local_shards(args, world):
+    return world > 1 and (args.local_shards or args.shape == "100m")
+
+
+def build_corpus(args, device, rank=0, world=1):
     """Synthetic corpus + queries on the GPU (setup, untimed)."""
     from bm25s_b200 import synth
+    from bm25s_b200.sharded import shard_bounds
 
     n_docs, avg_len, n_vocab, n_queries = shape_of(args)
-    tokens, ptr = synth.make_corpus_torch(n_docs, avg_len, n_vocab, seed=0, device=device)
+    if local_shards(args, world):  # corpora too large to generate whole on every rank: this rank's doc range only
+        lo, hi = shard_bounds(n_docs, world, rank)
+        tokens, ptr = synth.make_corpus_torch(hi - lo, avg_len, n_vocab, seed=1000 + rank, device=device)
+    else:
+        tokens, ptr = synth.make_corpus_torch(n_docs, avg_len, n_vocab, seed=0, device=device)
     q_tok, q_ptr = synth.make_queries_torch(n_queries, n_vocab, seed=1, device=device)
     return (tokens, ptr), (q_tok, q_ptr)
 
@@ -124,9 +135,13 @@ def build_index(args, tokens, ptr, rank, world, local_rank):
                                        1.5, 0.75, 0.5, device=local_rank)
     else:
         lo, hi = shard_bounds(n_docs, world, rank)
-        t_lo, t_hi = int(ptr[lo].item()), int(ptr[hi].item())
-        tok_l = tokens[t_lo:t_hi].contiguous()
-        ptr_l = (ptr[lo:hi + 1] - t_lo).contiguous()
+        if local_shards(args, world):
+            t_lo, t_hi = 0, int(ptr[-1].item())
+            tok_l, ptr_l = tokens, ptr
+        else:
+            t_lo, t_hi = int(ptr[lo].item()), int(ptr[hi].item())
+            tok_l = tokens[t_lo:t_hi].contiguous()
+            ptr_l = (ptr[lo:hi + 1] - t_lo).contiguous()
         sh = ShardedIndex.build(tok_l.data_ptr(), ptr_l.data_ptr(), n_vocab, method=args.method, rank=rank, world=world,
                                 device=local_rank, doc_lo=lo, on_device=True, n_docs_local=hi - lo,
                                 total_len_local=t_hi - t_lo)
@@ -188,13 +203,14 @@ def main():
     config = {"workload": f"{args.shape}-shape synthetic Zipf corpus ({n_docs} docs, avg len {avg_len}, vocab {n_vocab}), "
                           f"{n_queries} queries of 1+Poisson(3) tokens, k={k}, method={args.method}",
               "l2": "inputs larger than L2 (index 3.9 GB vs 126 MB L2), no flush between steps",
-              "sharding": f"doc-range x{world}" if world > 1 else "single shard"}
+              "sharding": (f"doc-range x{world}" + (", every rank generates its own range" if local_shards(args, world) else ""))
+              if world > 1 else "single shard"}
 
     import torch.distributed as dist
 
     if world > 1 and args.impl == "ours":
         dist.init_process_group("nccl", device_id=device)
-    (tokens, ptr), (q_tok, q_ptr) = build_corpus(args, device)
+    (tokens, ptr), (q_tok, q_ptr) = build_corpus(args, device, rank if args.impl == "ours" else 0, world if args.impl == "ours" else 1)
     dev, build_s = build_index(args, tokens, ptr, rank if args.impl == "ours" else 0, world if args.impl == "ours" else 1,
                                local_rank)
     del tokens, ptr
