@@ -28,11 +28,11 @@ class Stats(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_float), ("fast_kernel_ms", C.c_float), ("total_ms", C.c_float),
         ("posting_bytes", C.c_int64), ("algorithmic_bytes", C.c_int64),
-        ("n_fast", C.c_int32), ("n_general", C.c_int32), ("launches", C.c_int32), ("reserved", C.c_int32),
+        ("n_fast", C.c_int32), ("n_general", C.c_int32), ("launches", C.c_int32), ("ms_kernel_ms", C.c_float),
     ]
 
     def as_dict(self):
-        return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
+        return {f: getattr(self, f) for f, _ in self._fields_ }
 
 
 _lib = None

@@ -81,8 +81,22 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
         // 7 = bit tags + posting-index splits with barriers between the phases (retrieve_v7.cu, experimental)
         const char *kv = getenv("BM25CU_KERNEL");
         const int kernel = (kv && *kv) ? atoi(kv) : 5;
-        rc = (kernel == 7) ? launch_retrieve_v7(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
-                           : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
+        // BM25CU_MS (default 1): queries go to the list-at-a-time kernel first (retrieve_ms.cu); what it hands on is
+        // served by the streaming kernel from a device-side list
+        const char *mv = getenv("BM25CU_MS");
+        ix->ms_ran = false;
+        const bool ms = kernel == 5 && !(mv && *mv && atoi(mv) == 0);
+        if (ms) {
+            if ((rc = ix->d_fb_list.reserve((size_t)a.n_queries * sizeof(unsigned int)))) return rc;
+            if ((rc = launch_retrieve_ms(ix, a, d_ctrl, ix->d_fb_list.as<unsigned int>(), &launches))) return rc;
+            BM25CU_CHECK(cudaEventRecord(ix->ev[5], ix->stream));
+            ix->ms_ran = true;
+            rc = launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches,
+                                      ix->d_fb_list.as<unsigned int>(), &d_ctrl->fb_count);
+        } else {
+            rc = (kernel == 7) ? launch_retrieve_v7(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
+                               : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
+        }
         if (rc) return rc;
     }
     BM25CU_CHECK(cudaEventRecord(ix->ev[2], ix->stream));
@@ -91,7 +105,6 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         stats->launches = launches;
-        stats->reserved = (int32_t)n_query_tokens;
     }
     return BM25CU_OK;
 }
@@ -128,7 +141,10 @@ int finish_stats(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, i
         stats->algorithmic_bytes = stats->posting_bytes + 20 * n_query_tokens + (int64_t)8 * a.k * a.n_queries;
         stats->n_general = (int32_t)h.general_count;
         stats->n_fast = a.n_queries - (int32_t)h.general_count;
-        stats->reserved = 0;
+        if (ix->ms_ran) {
+            cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[5]);
+            stats->ms_kernel_ms = ms;
+        }
     }
     return BM25CU_OK;
 }
@@ -137,7 +153,7 @@ int finish_stats(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, i
 
 extern "C" {
 
-// debug: copy the phase counters of the last retrieve call (32 x uint64); zeros unless built with -DBM25CU_PROFILE
+// debug: copy the phase counters of the last retrieve call (48 x uint64); zeros unless built with -DBM25CU_PROFILE
 // debugging / tests only (not part of include/bm25cu.h): the per-column 10th / 100th / 1000th largest scores, f32[3][n_vocab]
 int bm25cu_debug_colkth(bm25cu_index *ix, float *out) {
     BM25CU_REQUIRE(ix && out && ix->d_colkth, "bm25cu_debug_colkth: no table");
@@ -149,7 +165,7 @@ int bm25cu_debug_colkth(bm25cu_index *ix, float *out) {
 int bm25cu_debug_prof(bm25cu_index *ix, unsigned long long *out) {
     BM25CU_REQUIRE(ix && out && ix->d_ctrl.p, "bm25cu_debug_prof: no retrieve call yet");
     BM25CU_CHECK(cudaSetDevice(ix->device));
-    BM25CU_CHECK(cudaMemcpy(out, ix->d_ctrl.as<Ctrl>()->prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    BM25CU_CHECK(cudaMemcpy(out, ix->d_ctrl.as<Ctrl>()->prof, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return BM25CU_OK;
 }
 

@@ -97,6 +97,13 @@ struct bm25cu_index {
     float *d_colmax = nullptr;     // f32[n_vocab] largest score of every column (upper bounds for pruning)
     float *d_colkth = nullptr;     // f32[3][n_vocab] 10th / 100th / 1000th largest score of every column (0: fewer postings);
                                    // a query's k-th best document scores at least the k-th largest posting of any of its tokens
+    unsigned int *d_btab = nullptr;     // bucket tables of the long columns: posting offset of every 2^sh-document bucket
+    long long *d_btab_off = nullptr;    // i64[n_vocab] start of a column's table in d_btab, -1: none (short column)
+    unsigned char *d_btab_sh = nullptr; // u8[n_vocab] log2 of the bucket width in documents
+    unsigned int *d_pbm = nullptr;      // presence bitmaps of the long columns (one bit per 2^s documents)
+    long long *d_pbm_off = nullptr;     // i64[n_vocab] start (in 32-bit words) of a column's bitmap, -1: none
+    unsigned char *d_pbm_sh = nullptr;  // u8[n_vocab] s
+    size_t aux_bytes = 0;               // bytes of the lookup structures derived at upload (bucket tables + presence bitmaps)
     bool nonneg = true;            // all data >= 0 and finite: the fused streaming kernel is exact
     int sm_count = 148;
     int max_smem_optin = 0;
@@ -105,7 +112,8 @@ struct bm25cu_index {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,
-        d_spill, d_order, d_theta;
+        d_spill, d_order, d_theta, d_fb_list;
+    bool ms_ran = false;           // the last call ran retrieve_ms.cu (ev[5] is recorded behind it)
     bool order_valid = false;      // d_order holds the pull order of the current batch
     bm25cu::PinBuf h_in, h_out;
     int general_rows = 0;
@@ -133,12 +141,16 @@ struct Ctrl {
     unsigned int error;          // bit 0: token id out of range; bits 1-2: internal invariants of the fused kernel
     unsigned long long posting_count;
     unsigned int mask_bad;       // weight mask has values outside [0, 1] (or NaN): every query takes the general kernel
+    unsigned int ms_next;        // work-queue cursor of the list-at-a-time kernel (retrieve_ms.cu)
+    unsigned int fb_count;       // queries that kernel handed on to the streaming kernel
     unsigned int pad;
-    unsigned long long prof[32];  // phase cycle counters / event counts of the fused kernel (BM25CU_PROFILE builds)
+    unsigned long long prof[48];  // phase cycle counters / event counts of the fused kernel (BM25CU_PROFILE builds)
 };
 
+// qlist/qcount non-null: serve only the *qcount queries listed in qlist (what retrieve_ms.cu handed on)
 int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_general_list,
-                         int *launches);
+                         int *launches, const unsigned int *qlist = nullptr, const unsigned int *qcount = nullptr);
+int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_fb_list, int *launches);
 int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_general_list,
                          int *launches);
 int launch_retrieve_general(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl,

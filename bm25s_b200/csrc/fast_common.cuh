@@ -32,6 +32,7 @@ struct FastParams {
     const int64_t *indptr;
     const float *colmax;
     const unsigned int *order;  // queries in the order the CTAs pull them (longest first); nullptr: index order
+    const unsigned int *qcount;  // non-null: `order` lists *qcount queries (the rest of the batch was served by retrieve_ms.cu)
     const float *colkth;  // column of the k-th-largest table that is valid for this k (nullptr: no seed)
     int32_t n_docs, n_vocab, doc_base;
     RetrieveArgs a;

@@ -2,6 +2,8 @@
 // doc-range shard extraction on the device, download, free.
 #include "common.cuh"
 #include "select.cuh"
+#include <cstdlib>
+
 #include "scan.cuh"
 
 namespace bm25cu {
@@ -126,6 +128,162 @@ __global__ void __launch_bounds__(256) column_kth_kernel(const float *__restrict
     }
 }
 
+// ---- bucket tables of the long columns (lookups of retrieve_ms.cu) ------------------------------------------------
+// A column with df >= kBtabMinDf gets a table over buckets of 2^sh consecutive document ids, sh chosen so that a bucket
+// holds 16..32 postings on average: tab[b] = number of postings with doc < b * 2^sh, (n_docs >> sh) + 2 entries.
+// A lookup of document d reads tab[d >> sh], tab[(d >> sh) + 1] and searches that slice of `indices` (one or two
+// sectors) instead of log2(df) scattered ones. Size: at most nnz / 4 bytes. Derived at upload, not part of the index.
+constexpr int kBtabMinDf = 16;
+
+__device__ __forceinline__ int btab_shift_of(long long df, int n_docs) {
+    int sh = 0;
+    while (sh < 31 && ((df << sh) < 16ll * (long long)n_docs)) ++sh;  // smallest sh with df * 2^sh >= 16 * n_docs
+    return sh;
+}
+
+__global__ void btab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_vocab, int32_t n_docs, long long *sizes,
+                                 unsigned char *shifts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_vocab) return;
+    const long long df = indptr[t + 1] - indptr[t];
+    long long sz = 0;
+    int sh = 0;
+    if (df >= kBtabMinDf) {
+        sh = btab_shift_of(df, n_docs);
+        sz = (long long)(n_docs >> sh) + 2;
+    }
+    sizes[t] = sz;
+    shifts[t] = (unsigned char)sh;
+}
+
+// one warp per column: every lane finds the lower bound of its bucket boundaries
+__global__ void btab_fill_kernel(const int32_t *__restrict__ indices, const int64_t *__restrict__ indptr, int32_t n_vocab,
+                                 int32_t n_docs, const unsigned char *__restrict__ shifts, long long *offs /* in: scan, out: -1 for none */,
+                                 unsigned int *tab) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_vocab) return;
+    const long long beg = indptr[warp], df = indptr[warp + 1] - beg;
+    if (df < kBtabMinDf) {
+        __syncwarp();
+        if (lane == 0) offs[warp] = -1;
+        return;
+    }
+    const int sh = shifts[warp];
+    const long long nb = (long long)(n_docs >> sh) + 2;
+    const long long off = offs[warp];
+    const int32_t *col = indices + beg;
+    for (long long b = lane; b < nb; b += 32) {
+        const long long bound = b << sh;  // first document of bucket b
+        long long lo = 0, hi = df;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if ((long long)col[mid] < bound) lo = mid + 1; else hi = mid;
+        }
+        tab[off + b] = (unsigned int)lo;
+    }
+}
+
+static int build_bucket_tables(bm25cu_index *ix) {
+    if (ix->n_vocab <= 0 || ix->nnz <= 0 || ix->n_docs <= 0) return BM25CU_OK;
+    const char *ev = getenv("BM25CU_BTAB");
+    if (ev && *ev && atoi(ev) == 0) return BM25CU_OK;
+    long long *d_sizes = nullptr, *d_tmp = nullptr;
+    const int V = ix->n_vocab;
+    BM25CU_CHECK(cudaMalloc(&d_sizes, (size_t)V * sizeof(long long)));
+    BM25CU_CHECK(cudaMalloc(&d_tmp, scan_tmp_elems(V) * sizeof(long long)));
+    BM25CU_CHECK(cudaMalloc(&ix->d_btab_off, (size_t)(V + 1) * sizeof(long long)));
+    BM25CU_CHECK(cudaMalloc(&ix->d_btab_sh, (size_t)V));
+    btab_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, d_sizes, ix->d_btab_sh);
+    BM25CU_CHECK(cudaGetLastError());
+    BM25CU_CHECK(exclusive_scan<long long>(d_sizes, V, ix->d_btab_off, d_tmp, ix->stream));
+    long long total = 0;
+    BM25CU_CHECK(cudaMemcpyAsync(&total, ix->d_btab_off + V, sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+    BM25CU_CHECK(cudaStreamSynchronize(ix->stream));
+    cudaFree(d_sizes);
+    cudaFree(d_tmp);
+    BM25CU_CHECK(cudaMalloc(&ix->d_btab, (size_t)(total > 0 ? total : 1) * sizeof(unsigned int)));
+    const long long threads = (long long)V * 32;
+    btab_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ix->stream>>>(ix->d_indices, ix->d_indptr, V, ix->n_docs,
+                                                                                ix->d_btab_sh, ix->d_btab_off, ix->d_btab);
+    BM25CU_CHECK(cudaGetLastError());
+    ix->aux_bytes += (size_t)total * 4;
+    return BM25CU_OK;
+}
+
+// ---- presence bitmaps of the long columns (negative lookups of retrieve_ms.cu in one load) ------------------------
+// A column with df >= kBtabMinDf gets one bit per 2^s consecutive documents, "a posting of this column falls in here",
+// with s the largest shift that keeps at least 8 bits per posting (s = 0, an exact bitmap, for columns denser than
+// n_docs / 8). A document that is not in the column - the usual outcome of a lookup - is recognised by one load with
+// probability >= exp(-1/8). Size: at most 2 bytes per posting. Derived at upload, not part of the saved index.
+__device__ __forceinline__ int pbm_shift_of(long long df, int n_docs) {
+    int s = 0;
+    while (s < 30 && ((8ll * df) << (s + 1)) <= (long long)n_docs) ++s;
+    return s;
+}
+
+__global__ void pbm_size_kernel(const int64_t *__restrict__ indptr, int32_t n_vocab, int32_t n_docs, long long *sizes,
+                                unsigned char *shifts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_vocab) return;
+    const long long df = indptr[t + 1] - indptr[t];
+    long long sz = 0;
+    int sh = 0;
+    if (df >= kBtabMinDf) {
+        sh = pbm_shift_of(df, n_docs);
+        sz = ((((long long)(n_docs - 1) >> sh) + 32) >> 5) + 1;  // 32-bit words
+    }
+    sizes[t] = sz;
+    shifts[t] = (unsigned char)sh;
+}
+
+__global__ void pbm_fill_kernel(const int32_t *__restrict__ indices, const int64_t *__restrict__ indptr, int32_t n_vocab,
+                                const unsigned char *__restrict__ shifts, long long *offs, unsigned int *bits) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_vocab) return;
+    const long long beg = indptr[warp], df = indptr[warp + 1] - beg;
+    if (df < kBtabMinDf) {
+        __syncwarp();
+        if (lane == 0) offs[warp] = -1;
+        return;
+    }
+    const int sh = shifts[warp];
+    unsigned int *b = bits + offs[warp];
+    for (long long i = lane; i < df; i += 32) {
+        const unsigned int x = (unsigned int)indices[beg + i] >> sh;
+        atomicOr(&b[x >> 5], 1u << (x & 31u));
+    }
+}
+
+static int build_presence_bitmaps(bm25cu_index *ix) {
+    if (ix->n_vocab <= 0 || ix->nnz <= 0 || ix->n_docs <= 0) return BM25CU_OK;
+    const char *ev = getenv("BM25CU_PBM");
+    if (ev && *ev && atoi(ev) == 0) return BM25CU_OK;
+    long long *d_sizes = nullptr, *d_tmp = nullptr;
+    const int V = ix->n_vocab;
+    BM25CU_CHECK(cudaMalloc(&d_sizes, (size_t)V * sizeof(long long)));
+    BM25CU_CHECK(cudaMalloc(&d_tmp, scan_tmp_elems(V) * sizeof(long long)));
+    BM25CU_CHECK(cudaMalloc(&ix->d_pbm_off, (size_t)(V + 1) * sizeof(long long)));
+    BM25CU_CHECK(cudaMalloc(&ix->d_pbm_sh, (size_t)V));
+    pbm_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, d_sizes, ix->d_pbm_sh);
+    BM25CU_CHECK(cudaGetLastError());
+    BM25CU_CHECK(exclusive_scan<long long>(d_sizes, V, ix->d_pbm_off, d_tmp, ix->stream));
+    long long total = 0;
+    BM25CU_CHECK(cudaMemcpyAsync(&total, ix->d_pbm_off + V, sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+    BM25CU_CHECK(cudaStreamSynchronize(ix->stream));
+    cudaFree(d_sizes);
+    cudaFree(d_tmp);
+    BM25CU_CHECK(cudaMalloc(&ix->d_pbm, (size_t)(total > 0 ? total : 1) * sizeof(unsigned int)));
+    BM25CU_CHECK(cudaMemsetAsync(ix->d_pbm, 0, (size_t)(total > 0 ? total : 1) * sizeof(unsigned int), ix->stream));
+    const long long threads = (long long)V * 32;
+    pbm_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ix->stream>>>(ix->d_indices, ix->d_indptr, V, ix->d_pbm_sh,
+                                                                               ix->d_pbm_off, ix->d_pbm);
+    BM25CU_CHECK(cudaGetLastError());
+    ix->aux_bytes += (size_t)total * 4;
+    return BM25CU_OK;
+}
+
 int finalize_index(bm25cu_index *ix) {
     cudaDeviceProp prop;
     BM25CU_CHECK(cudaGetDeviceProperties(&prop, ix->device));
@@ -150,6 +308,11 @@ int finalize_index(bm25cu_index *ix) {
         const int64_t threads = (int64_t)ix->n_vocab * 32;
         column_kth_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ix->stream>>>(ix->d_data, ix->d_indptr, ix->n_vocab, ix->d_colkth);
         BM25CU_CHECK(cudaGetLastError());
+    }
+    {
+        int rc_bt = build_bucket_tables(ix);
+        if (rc_bt) return rc_bt;
+        if ((rc_bt = build_presence_bitmaps(ix))) return rc_bt;
     }
     unsigned int flag = 0;
     BM25CU_CHECK(cudaMemcpyAsync(&flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost, ix->stream));
@@ -177,8 +340,14 @@ static void destroy(bm25cu_index *ix) {
     cudaFree(ix->d_nonocc);
     cudaFree(ix->d_colmax);
     cudaFree(ix->d_colkth);
+    cudaFree(ix->d_btab);
+    cudaFree(ix->d_btab_off);
+    cudaFree(ix->d_btab_sh);
+    cudaFree(ix->d_pbm);
+    cudaFree(ix->d_pbm_off);
+    cudaFree(ix->d_pbm_sh);
     bm25cu::DevBuf *bufs[] = {&ix->d_qtok, &ix->d_qptr, &ix->d_shift, &ix->d_mask, &ix->d_out_ids, &ix->d_out_scores,
-                              &ix->d_ctrl, &ix->d_general_list, &ix->d_scratch, &ix->d_spill, &ix->d_order, &ix->d_theta};
+                              &ix->d_ctrl, &ix->d_general_list, &ix->d_scratch, &ix->d_spill, &ix->d_order, &ix->d_theta, &ix->d_fb_list};
     for (auto *b : bufs) b->release();
     ix->h_in.release();
     ix->h_out.release();

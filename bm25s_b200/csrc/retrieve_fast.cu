@@ -1159,7 +1159,7 @@ struct Fast {
             if (tid == 0) h->q_slot = atomicAdd(&p.ctrl->fast_next, 1u);
             __syncthreads();
             const unsigned int slot = h->q_slot;
-            if (slot >= (unsigned)p.a.n_queries) break;
+            if (slot >= (p.qcount ? *p.qcount : (unsigned)p.a.n_queries)) break;
             const int q = p.order ? (int)p.order[slot] : (int)slot;
             const long long qs = p.a.q_ptr[q], qe = p.a.q_ptr[q + 1];
             const long long Tl = qe - qs;
@@ -1295,13 +1295,14 @@ static int env_int(const char *name, int dflt) {
 }
 
 int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_general_list,
-                         int *launches) {
+                         int *launches, const unsigned int *qlist, const unsigned int *qcount) {
     FastParams p;
     p.data = ix->d_data;
     p.indices = ix->d_indices;
     p.indptr = ix->d_indptr;
     p.colmax = ix->d_colmax;
-    p.order = ix->order_valid ? ix->d_order.as<unsigned int>() : nullptr;
+    p.order = qlist ? qlist : (ix->order_valid ? ix->d_order.as<unsigned int>() : nullptr);
+    p.qcount = qlist ? qcount : nullptr;
     // the k-th-largest table holds ranks 10 / 100 / 1000: rank r bounds every k <= r (k = 1 uses the column maxima)
     p.colkth = nullptr;
     if (env_int("BM25CU_SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {  // a mask may remove the documents behind the bound

@@ -1,0 +1,456 @@
+// K1m: list-at-a-time scoring + top-k with exact upper-bound pruning and skipping (sm_100a).
+//
+// Replaces, per query, BM25._compute_relevance_from_scores (bm25s/__init__.py:312-318), the weight mask and the
+// BM25L/BM25+ shift of get_scores_from_ids (:610-618) and selection.topk (bm25s/selection.py:14-64) - the same
+// contract as retrieve_fast.cu, reached with far fewer postings touched:
+//
+//   * the query's distinct tokens are ordered by their upper bound ub = multiplicity * column maximum, largest first
+//     (rare tokens first). List i is STREAMED - only its float32 scores, 16 bytes per load - and a posting (d, v) is a
+//     survivor when  mult*v + sum of ub over the lists after i  can still reach theta, the k-th best key so far.
+//     Documents that contain a token of an earlier list were scored when that list was streamed.
+//   * a survivor is looked up in the other lists (binary search, or the per-column bucket table of index.cu), the
+//     bound is re-checked after every lookup, and a document that passes is summed in QUERY-TOKEN ORDER, duplicates
+//     added again at their position - the reference's float32 order, so scores are bit-identical to numpy's.
+//   * when the upper bounds of the lists not yet streamed sum below theta, no unseen document can enter the top-k and
+//     the query ends: the long lists of frequent tokens are usually never streamed, only probed.
+//   * candidates are 64-bit keys (score bits, ~doc): order = score descending, doc ascending, as in retrieve_fast.cu;
+//     pruning keeps everything whose bound is >= theta's score, acceptance is key > theta, so the result does not
+//     depend on the order in which documents are met. For k <= 32 the top list lives in one warp's registers.
+//
+// Queries this kernel does not take (empty, > 15 tokens, k > 32, fewer than k positive matches, cost rule) are
+// appended to `fb_list` and served by retrieve_fast_kernel in the same call.
+#include "fast_common.cuh"
+
+namespace bm25cu {
+
+struct MsParams {
+    const float *data;
+    const int32_t *indices;
+    const int64_t *indptr;
+    const float *colmax;
+    const float *colkth;        // start value table valid for this k (nullptr: none)
+    const unsigned int *order;  // pull order (longest first) or nullptr
+    const unsigned int *btab;   // bucket tables (index.cu) or nullptr: binary search
+    const long long *btab_off;  // per column: offset into btab, -1 = no table
+    const unsigned char *btab_sh;
+    const unsigned int *pbm;    // presence bitmaps (index.cu) or nullptr
+    const long long *pbm_off;
+    const unsigned char *pbm_sh;
+    int32_t n_docs, n_vocab, doc_base;
+    RetrieveArgs a;
+    Ctrl *ctrl;
+    unsigned int *fb_list;
+    int route_all;
+    long long max_first;  // cost rule: hand the query on when its first (rarest) list is longer than this
+    unsigned int budget;  // survivors a query may look up before it is handed on (bounds the time one CTA spends on a query)
+};
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ unsigned long long shfl64_xor(unsigned long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+
+// 32 keys, one per lane, sorted descending by lane (bitonic network on shuffles)
+__device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long x, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long o = shfl64_xor(x, stride);
+            const bool lower = (lane & stride) == 0;
+            const bool desc = (lane & size) == 0;
+            x = (lower == desc) ? umax64(x, o) : umin64(x, o);
+        }
+    }
+    return x;
+}
+
+__device__ __forceinline__ bool reaches(float acc, float rest, float th) {
+    return __fmul_ru(__fadd_ru(acc, rest), 1.00002f) >= th;
+}
+
+template <int NT, int UNROLL, int R>
+struct Ms {
+    static constexpr int CHUNK = NT * 4 * UNROLL;
+    static constexpr int QCAP = CHUNK + NT * R;
+    struct Sh {
+        long long beg[16];
+        unsigned long long top[32];
+        unsigned long long pend[NT * R];
+        unsigned long long theta_key;
+        int df[16];
+        float ub[16];
+        float mult[16];
+        float suf[17];
+        int bt_sh[16];
+        long long bt_off[16];
+        long long pb_off[16];
+        int pb_sh[16];
+        unsigned char pos2u[16];
+        unsigned int pend_cnt, q_cnt, q_slot, work;
+        int U, T, route;
+        unsigned long long tot;
+        unsigned int queue[QCAP];
+    };
+    const MsParams &p;
+    Sh &s;
+#ifdef BM25CU_PROFILE
+    // 0 postings streamed, 1 survivors queued, 2 survivors probed, 3 lookups, 4 lookup steps, 5 candidates accepted,
+    // 6 probe rounds, 7 merges, 8 lists streamed, 9 lists skipped, 10 queries served, 11 queries handed on
+    unsigned long long cnt[16] = {0};  // 12 survivors of dense lists (df >= n_docs/64), 13 lookups that passed a presence bitmap, 14 steps in dense lists, 15 found
+#define MS_CNT(i, v) (cnt[i] += (unsigned long long)(v))
+#else
+#define MS_CNT(i, v)
+#endif
+    __device__ Ms(const MsParams &p_, Sh &s_) : p(p_), s(s_) {}
+
+    // is document d in list j? (val = its score)
+    __device__ __forceinline__ bool lookup(int j, int d, float &val) {
+        MS_CNT(3, 1);
+        const long long po = s.pb_off[j];
+        if (po >= 0) {
+            const unsigned x = (unsigned)d >> s.pb_sh[j];
+            if (!((__ldg(p.pbm + po + (x >> 5)) >> (x & 31u)) & 1u)) return false;
+            MS_CNT(13, 1);
+        }
+        const long long beg = s.beg[j];
+        int lo = 0, hi = s.df[j];
+        const long long bo = s.bt_off[j];
+        if (bo >= 0) {
+            const unsigned b = (unsigned)d >> s.bt_sh[j];
+            lo = (int)__ldg(p.btab + bo + b);
+            hi = (int)__ldg(p.btab + bo + b + 1);
+        }
+        const int32_t *col = p.indices + beg;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const int x = __ldg(col + mid);
+            MS_CNT(4, 1);
+            if (s.df[j] >= p.n_docs / 64) MS_CNT(14, 1);
+            if (x < d) lo = mid + 1;
+            else if (x > d) hi = mid;
+            else { val = __ldg(p.data + beg + mid); MS_CNT(15, 1); return true; }
+        }
+        return false;
+    }
+
+    __device__ void merge_pending(int lane, int k) {
+        const unsigned cnt = s.pend_cnt;
+        unsigned long long t = s.top[lane];
+        for (unsigned base = 0; base < cnt; base += 32) {
+            unsigned long long b = (base + lane < cnt) ? s.pend[base + lane] : 0ull;
+            if (cnt - base > 1) b = warp_sort_desc(b, lane);
+            t = umax64(t, shfl64(b, 31 - lane));  // bitonic: the 32 largest of the union
+#pragma unroll
+            for (int stride = 16; stride > 0; stride >>= 1) {
+                const unsigned long long o = shfl64_xor(t, stride);
+                t = ((lane & stride) == 0) ? umax64(t, o) : umin64(t, o);
+            }
+        }
+        s.top[lane] = t;
+        const unsigned long long kth = shfl64(t, k - 1);
+        if (lane == 0) {
+            if (kth > s.theta_key) s.theta_key = kth;
+            s.pend_cnt = 0;
+        }
+    }
+
+    // Survivor (d, v) of list i: look it up in the other lists, largest upper bound first, until its bound falls below
+    // theta; `first_absent`: the presence bitmap of list i + 1 already said no.
+    __device__ void probe_one(int i, int d, float v, unsigned long long tk, bool first_absent) {
+        MS_CNT(2, 1);
+        if (s.df[i] >= p.n_docs / 64) MS_CNT(12, 1);
+        const float th = cand_score(tk);
+        float acc = __fmul_ru(s.mult[i], v);
+        float vals[16];
+        unsigned found = 1u << i;
+        vals[i] = v;
+        const int U = s.U;
+        for (int j = i + 1; j < U; ++j) {
+            float val;
+            if (!(first_absent && j == i + 1) && lookup(j, d, val)) {
+                vals[j] = val;
+                found |= 1u << j;
+                acc = __fadd_ru(acc, __fmul_ru(s.mult[j], val));
+            }
+            if (!reaches(acc, s.suf[j + 1], th)) return;
+        }
+        float dummy;
+        for (int j = i - 1; j >= 0; --j)
+            if (lookup(j, d, dummy)) return;  // contains an earlier list's token: scored when that list was streamed
+        float sc = 0.0f;
+        const int T = s.T;
+        for (int t = 0; t < T; ++t) {  // the reference's order: token by token, duplicates again (__init__.py:316-318)
+            const unsigned u = s.pos2u[t];
+            if (u < 16u && ((found >> u) & 1u)) sc = __fadd_rn(sc, vals[u]);
+        }
+        if (p.a.mask) sc = (float)((double)sc * p.a.mask[d]);
+        const unsigned long long key = pack_cand(sc, d);
+        if (key > tk) { s.pend[atomicAdd(&s.pend_cnt, 1u)] = key; MS_CNT(5, 1); }
+    }
+
+    // A round: every thread takes R survivors; their (doc, score) loads and the presence test of the next list are
+    // issued together (the usual survivor is absent there and ends on that test).
+    __device__ void probe_rounds(int i, unsigned n, int tid, int k) {
+        const long long beg = s.beg[i];
+        const float m = s.mult[i], rest = s.suf[i + 1];
+        const bool has_next = i + 1 < s.U;
+        const long long po = has_next ? s.pb_off[i + 1] : -1;
+        const int psh = has_next ? s.pb_sh[i + 1] : 0;
+        for (unsigned base = 0; base < n; base += NT * R) {
+            const unsigned long long tk = s.theta_key;
+            const float th = cand_score(tk);
+            if (tid == 0) MS_CNT(6, 1);
+            int d[R];
+            float v[R];
+            unsigned w[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const unsigned idx = base + r * NT + tid;
+                const long long at = beg + ((idx < n) ? s.queue[idx] : 0u);
+                d[r] = __ldg(p.indices + at);
+                v[r] = __ldg(p.data + at);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const unsigned x = (unsigned)d[r] >> psh;
+                w[r] = (po >= 0) ? ((__ldg(p.pbm + po + (x >> 5)) >> (x & 31u)) & 1u) : 1u;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (base + r * NT + tid < n && reaches(__fmul_ru(m, v[r]), rest, th)) probe_one(i, d[r], v[r], tk, w[r] == 0u);
+            }
+            __syncthreads();
+            if (s.pend_cnt > 0) {
+                if (tid == 0) MS_CNT(7, 1);
+                if (tid < 32) merge_pending(tid, k);
+                __syncthreads();
+            }
+        }
+        if (tid == 0) { s.q_cnt = 0; s.work += n; }
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ void check(float v, int pos, int df, float m, float rest, float th) {
+        if (__fmul_ru(__fmaf_ru(m, v, rest), 1.00002f) >= th && (unsigned)pos < (unsigned)df)
+        { s.queue[atomicAdd(&s.q_cnt, 1u)] = (unsigned)pos; MS_CNT(1, 1); }
+    }
+
+    __device__ bool stream(int i, int tid, int k) {
+        const long long beg = s.beg[i];
+        const int df = s.df[i];
+        const float m = s.mult[i], rest = s.suf[i + 1];
+        const int head = (int)(beg & 3);
+        const int nvec = (df + head + 3) >> 2;
+        const float4 *vp = reinterpret_cast<const float4 *>(p.data + (beg - head));
+        if (tid == 0) { MS_CNT(0, df); MS_CNT(8, 1); }
+        for (int v0 = 0; v0 < nvec; v0 += NT * UNROLL) {
+            const float th = cand_score(s.theta_key);
+            float4 x[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int v = v0 + u * NT + tid;
+                x[u] = (v < nvec) ? __ldcs(vp + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int v = v0 + u * NT + tid;
+                const int pos = 4 * v - head;
+                if (v < nvec) {
+                    check(x[u].x, pos, df, m, rest, th);
+                    check(x[u].y, pos + 1, df, m, rest, th);
+                    check(x[u].z, pos + 2, df, m, rest, th);
+                    check(x[u].w, pos + 3, df, m, rest, th);
+                }
+            }
+            __syncthreads();
+            const unsigned n = s.q_cnt;
+            __syncthreads();  // nobody pushes the next chunk's survivors before everybody read the count
+            const bool last = v0 + NT * UNROLL >= nvec;
+            if (n >= (unsigned)(NT * R) || (last && n > 0)) {
+                probe_rounds(i, n, tid, k);
+                if (s.work > p.budget) return false;  // too many survivors: the streaming kernel does this query
+            }
+        }
+        return true;
+    }
+
+    // warp 0: tokens -> distinct lists ordered by upper bound, suffix sums, start threshold
+    __device__ void prologue(int q, int lane) {
+        const long long qs = p.a.q_ptr[q], qe = p.a.q_ptr[q + 1];
+        const long long Tl = qe - qs;
+        bool route = p.route_all || Tl > kMaxTok || Tl == 0 || (p.a.mask && p.ctrl->mask_bad);
+        if (!route) {
+            const int T = (int)Tl;
+            const int tok = (lane < T) ? p.a.q_tokens[qs + lane] : -1 - lane;
+            long long beg = 0;
+            int df = 0;
+            float mx = 0.0f, kth = 0.0f;
+            if (lane < T) {
+                if ((unsigned)tok >= (unsigned)p.n_vocab) atomicOr(&p.ctrl->error, 1u);
+                else {
+                    beg = p.indptr[tok];
+                    df = (int)(p.indptr[tok + 1] - beg);
+                    mx = p.colmax[tok];
+                    if (p.colkth) kth = p.colkth[tok];
+                }
+            }
+            int first = lane, mult = 0;
+            for (int j = 0; j < T; ++j) {
+                const int tj = __shfl_sync(0xffffffffu, tok, j);
+                if (tj == tok) { ++mult; if (j < first) first = j; }
+            }
+            const int uniq = (lane < T && first == lane && df > 0) ? 1 : 0;
+            const float ub = uniq ? __fmul_ru((float)mult, mx) : 0.0f;
+            int rank = 0;
+            for (int j = 0; j < T; ++j) {
+                const float ubj = __shfl_sync(0xffffffffu, ub, j);
+                const int uj = __shfl_sync(0xffffffffu, uniq, j);
+                if (uj && j != lane && (ubj > ub || (ubj == ub && j < lane))) ++rank;
+            }
+            const int U = __popc(__ballot_sync(0xffffffffu, uniq));
+            if (uniq) {
+                s.beg[rank] = beg;
+                s.df[rank] = df;
+                s.ub[rank] = ub;
+                s.mult[rank] = (float)mult;
+                long long bo = -1;
+                int bsh = 0;
+                if (p.btab) { bo = p.btab_off[tok]; bsh = p.btab_sh[tok]; }
+                s.bt_off[rank] = bo;
+                s.bt_sh[rank] = bsh;
+                long long po = -1;
+                int psh = 0;
+                if (p.pbm) { po = p.pbm_off[tok]; psh = p.pbm_sh[tok]; }
+                s.pb_off[rank] = po;
+                s.pb_sh[rank] = psh;
+            }
+            const int myrank = uniq ? rank : 255;
+            const int rf = __shfl_sync(0xffffffffu, myrank, first & 31);
+            if (lane < T) s.pos2u[lane] = (unsigned char)rf;
+            unsigned long long tot = (lane < T) ? (unsigned long long)df : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            const unsigned kb = __reduce_max_sync(0xffffffffu, __float_as_uint(kth));
+            __syncwarp();
+            if (lane == 0) {
+                float acc = 0.0f;
+                s.suf[U] = 0.0f;
+                for (int j = U - 1; j >= 0; --j) { acc = __fadd_ru(acc, s.ub[j]); s.suf[j] = acc; }
+                // the k-th largest posting of one token is reached by k distinct documents and a document scores at
+                // least each of its postings: the float below it is a safe start value (as in retrieve_fast.cu)
+                s.theta_key = kb > 0u ? ((unsigned long long)(kb - 1u) << 32) : 0ull;
+                s.U = U;
+                s.T = T;
+                s.tot = tot;
+                s.pend_cnt = 0;
+                s.q_cnt = 0;
+                s.work = 0;
+            }
+            s.top[lane] = 0ull;
+            __syncwarp();
+            if (tot == 0 || (long long)s.df[0] > p.max_first) route = true;
+        }
+        if (lane == 0) s.route = route ? 1 : 0;
+    }
+
+    __device__ void run() {
+        const int tid = threadIdx.x;
+        const int k = p.a.k;
+        for (;;) {
+            if (tid == 0) s.q_slot = atomicAdd(&p.ctrl->ms_next, 1u);
+            __syncthreads();
+            const unsigned slot = s.q_slot;
+            if (slot >= (unsigned)p.a.n_queries) break;
+            const int q = p.order ? (int)p.order[slot] : (int)slot;
+            if (tid < 32) prologue(q, tid);
+            __syncthreads();
+            if (!s.route) {
+                const int U = s.U;
+                for (int i = 0; i < U; ++i) {
+                    const float th = cand_score(s.theta_key);
+                    if (__fmul_ru(s.suf[i], 1.00002f) < th) { if (tid == 0) MS_CNT(9, U - i); break; }  // no unseen document can reach theta
+                    if (!stream(i, tid, k)) break;
+                }
+                if (s.work > p.budget) {
+                    if (tid == 0) s.route = 1;
+                } else if (tid < 32) {
+                    const unsigned long long t = s.top[tid];
+                    const unsigned long long kth = shfl64(t, k - 1);
+                    if (kth != 0ull && cand_score(kth) > 0.0f) {
+                        const bool has_shift = p.a.shift != nullptr;
+                        if (tid < k) {
+                            float sc = cand_score(t);
+                            if (has_shift) sc = __fadd_rn(sc, p.a.shift[q]);
+                            p.a.out_ids[(size_t)q * k + tid] = cand_doc(t) + p.doc_base;
+                            p.a.out_scores[(size_t)q * k + tid] = sc;
+                        }
+                        if (tid == 0) atomicAdd(&p.ctrl->posting_count, s.tot);
+                    } else if (tid == 0) {
+                        s.route = 1;  // fewer than k positive matches: padding rules live in retrieve_fast.cu
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) MS_CNT(s.route ? 11 : 10, 1);
+            if (s.route && tid == 0) p.fb_list[atomicAdd(&p.ctrl->fb_count, 1u)] = (unsigned)q;
+            __syncthreads();
+        }
+#ifdef BM25CU_PROFILE
+        for (int i = 0; i < 16; ++i)
+            if (cnt[i]) atomicAdd(&p.ctrl->prof[32 + i], cnt[i]);
+#endif
+    }
+};
+
+template <int NT, int UNROLL, int R, int MINB>
+__global__ void __launch_bounds__(NT, MINB) retrieve_ms_kernel(const __grid_constant__ MsParams p) {
+    __shared__ typename Ms<NT, UNROLL, R>::Sh sh;
+    Ms<NT, UNROLL, R> m(p, sh);
+    m.run();
+}
+
+static int env_int_ms(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_fb_list, int *launches) {
+    MsParams p;
+    p.data = ix->d_data;
+    p.indices = ix->d_indices;
+    p.indptr = ix->d_indptr;
+    p.colmax = ix->d_colmax;
+    p.colkth = nullptr;
+    if (env_int_ms("BM25CU_SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {
+        if (a.k == 1) p.colkth = ix->d_colmax;
+        else if (a.k <= 10) p.colkth = ix->d_colkth;
+        else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
+    }
+    p.order = ix->order_valid ? ix->d_order.as<unsigned int>() : nullptr;
+    const bool use_bt = env_int_ms("BM25CU_MS_BTAB", 1) && ix->d_btab != nullptr;
+    p.btab = use_bt ? ix->d_btab : nullptr;
+    p.btab_off = ix->d_btab_off;
+    p.btab_sh = ix->d_btab_sh;
+    p.pbm = (env_int_ms("BM25CU_MS_PBM", 1) && ix->d_pbm) ? ix->d_pbm : nullptr;
+    p.pbm_off = ix->d_pbm_off;
+    p.pbm_sh = ix->d_pbm_sh;
+    p.n_docs = ix->n_docs;
+    p.n_vocab = ix->n_vocab;
+    p.doc_base = ix->doc_base;
+    p.a = a;
+    p.ctrl = d_ctrl;
+    p.fb_list = d_fb_list;
+    p.route_all = (!ix->nonneg) || a.k > 32 || (a.mask != nullptr && env_int_ms("BM25CU_MASK_FAST", 1) == 0) ||
+                  env_int_ms("BM25CU_FORCE_GENERAL", 0);
+    p.max_first = (long long)env_int_ms("BM25CU_MS_MAXFIRST", 0x7fffffff);
+    p.budget = (unsigned int)env_int_ms("BM25CU_MS_BUDGET", 32768);
+    const int per_sm = env_int_ms("BM25CU_MS_CTAS", 8);
+    const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 8);
+    retrieve_ms_kernel<128, 4, 4, 8><<<grid, 128, 0, ix->stream>>>(p);
+    BM25CU_CHECK(cudaGetLastError());
+    if (launches) ++*launches;
+    return BM25CU_OK;
+}
+
+}  // namespace bm25cu

@@ -957,6 +957,7 @@ int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.indptr = ix->d_indptr;
     p.colmax = ix->d_colmax;
     p.order = ix->order_valid ? ix->d_order.as<unsigned int>() : nullptr;
+    p.qcount = nullptr;
     // the k-th-largest table holds ranks 10 / 100 / 1000: rank r bounds every k <= r (k = 1 uses the column maxima)
     p.colkth = nullptr;
     if (env_int7("BM25CU_SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {  // a mask may remove the documents behind the bound

@@ -48,7 +48,7 @@ typedef struct bm25cu_stats {
     int32_t n_fast;            /* queries served by the fused streaming kernel                              */
     int32_t n_general;         /* queries served by the dense general kernel (exotic inputs) */
     int32_t launches;          /* kernels launched by the call                                              */
-    int32_t reserved;
+    float ms_kernel_ms;        /* ... of the list-at-a-time kernel alone (part of fast_kernel_ms)            */
 } bm25cu_stats;
 
 const char *bm25cu_last_error(void);

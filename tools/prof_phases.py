@@ -19,7 +19,7 @@ k = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 oi = torch.empty((n_queries, k), dtype=torch.int32, device=dev); os_ = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
 for it in range(3):
     st = ix.retrieve_device(qt.data_ptr(), qp.data_ptr(), n_queries, int(qp[-1]), k, oi.data_ptr(), os_.data_ptr())
-prof = (C.c_ulonglong * 32)()
+prof = (C.c_ulonglong * 48)()
 L.check(L.lib().bm25cu_debug_prof(ix._h, prof))
 p = list(prof)
 names = {0:'loop-top',1:'wait meta',2:'seed',3:'P1',4:'bar P1',5:'P2',6:'bar P2',7:'P3',8:'bar P3',9:'P5',10:'P4',11:'free+compact',12:'run: finalize->next',13:'run: prologue',14:'run: prod/cons body',15:'run: finalize'}
