@@ -63,9 +63,26 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
         BM25CU_CHECK(cudaGetLastError());
         ++launches;
     }
-    {
+    // BM25CU_KERNEL selects the structure of K1: 5 (default) = per-warp document sub-ranges (retrieve_fast.cu),
+    // 7 = bit tags + posting-index splits with barriers between the phases (retrieve_v7.cu, experimental).
+    // BM25CU_MS (default 1): queries go to the list-at-a-time kernel first (retrieve_ms.cu: plan, parts, merge); what it
+    // hands on is served by the streaming kernel from a device-side list.
+    const char *kv = getenv("BM25CU_KERNEL");
+    const int kernel = (kv && *kv) ? atoi(kv) : 5;
+    const char *mv = getenv("BM25CU_MS");
+    const bool ms = kernel == 5 && !(mv && *mv && atoi(mv) == 0);
+    ix->ms_ran = false;
+    ix->order_valid = false;
+    if (ms) {
+        if ((rc = ix->d_fb_list.reserve((size_t)a.n_queries * sizeof(unsigned int)))) return rc;
+        if ((rc = launch_retrieve_ms(ix, a, d_ctrl, ix->d_fb_list.as<unsigned int>(), &launches))) return rc;
+        BM25CU_CHECK(cudaEventRecord(ix->ev[5], ix->stream));
+        ix->ms_ran = true;
+        if ((rc = launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches,
+                                       ix->d_fb_list.as<unsigned int>(), &d_ctrl->fb_count)))
+            return rc;
+    } else {
         const char *ov = getenv("BM25CU_ORDER");
-        ix->order_valid = false;
         if (a.n_queries >= 4 * ix->sm_count && !(ov && *ov && atoi(ov) == 0)) {  // small batches: every CTA gets at most a few queries
             if ((rc = ix->d_order.reserve((size_t)a.n_queries * 5))) return rc;
             order_queries_kernel<<<1, 1024, 0, ix->stream>>>(a.q_tokens, a.q_ptr, a.n_queries, ix->d_indptr, ix->n_vocab,
@@ -75,28 +92,8 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
             ix->order_valid = true;
             ++launches;
         }
-    }
-    {
-        // BM25CU_KERNEL selects the structure of K1: 5 (default) = per-warp document sub-ranges (retrieve_fast.cu),
-        // 7 = bit tags + posting-index splits with barriers between the phases (retrieve_v7.cu, experimental)
-        const char *kv = getenv("BM25CU_KERNEL");
-        const int kernel = (kv && *kv) ? atoi(kv) : 5;
-        // BM25CU_MS (default 1): queries go to the list-at-a-time kernel first (retrieve_ms.cu); what it hands on is
-        // served by the streaming kernel from a device-side list
-        const char *mv = getenv("BM25CU_MS");
-        ix->ms_ran = false;
-        const bool ms = kernel == 5 && !(mv && *mv && atoi(mv) == 0);
-        if (ms) {
-            if ((rc = ix->d_fb_list.reserve((size_t)a.n_queries * sizeof(unsigned int)))) return rc;
-            if ((rc = launch_retrieve_ms(ix, a, d_ctrl, ix->d_fb_list.as<unsigned int>(), &launches))) return rc;
-            BM25CU_CHECK(cudaEventRecord(ix->ev[5], ix->stream));
-            ix->ms_ran = true;
-            rc = launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches,
-                                      ix->d_fb_list.as<unsigned int>(), &d_ctrl->fb_count);
-        } else {
-            rc = (kernel == 7) ? launch_retrieve_v7(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
-                               : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
-        }
+        rc = (kernel == 7) ? launch_retrieve_v7(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
+                           : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
         if (rc) return rc;
     }
     BM25CU_CHECK(cudaEventRecord(ix->ev[2], ix->stream));

@@ -112,7 +112,7 @@ struct bm25cu_index {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,
-        d_spill, d_order, d_theta, d_fb_list;
+        d_spill, d_order, d_theta, d_fb_list, d_ms_items, d_ms_rows, d_ms_q, d_ms_partial;
     bool ms_ran = false;           // the last call ran retrieve_ms.cu (ev[5] is recorded behind it)
     bool order_valid = false;      // d_order holds the pull order of the current batch
     bm25cu::PinBuf h_in, h_out;
@@ -143,7 +143,7 @@ struct Ctrl {
     unsigned int mask_bad;       // weight mask has values outside [0, 1] (or NaN): every query takes the general kernel
     unsigned int ms_next;        // work-queue cursor of the list-at-a-time kernel (retrieve_ms.cu)
     unsigned int fb_count;       // queries that kernel handed on to the streaming kernel
-    unsigned int pad;
+    unsigned int ms_items;       // work items (query parts) of that kernel
     unsigned long long prof[48];  // phase cycle counters / event counts of the fused kernel (BM25CU_PROFILE builds)
 };
 

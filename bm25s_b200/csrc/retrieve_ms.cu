@@ -20,6 +20,7 @@
 // Queries this kernel does not take (empty, > 15 tokens, k > 32, fewer than k positive matches, cost rule) are
 // appended to `fb_list` and served by retrieve_fast_kernel in the same call.
 #include "fast_common.cuh"
+#include "scan.cuh"
 
 namespace bm25cu {
 
@@ -42,7 +43,13 @@ struct MsParams {
     unsigned int *fb_list;
     int route_all;
     long long max_first;  // cost rule: hand the query on when its first (rarest) list is longer than this
-    unsigned int budget;  // survivors a query may look up before it is handed on (bounds the time one CTA spends on a query)
+    unsigned int budget;  // survivors a work item may look up before its query is handed on (safety valve)
+    // work items: a query is cut into P doc-range parts served by different CTAs (MsPlan below)
+    const unsigned long long *items;  // q | part << 32 | P << 40, longest first
+    const unsigned int *part_base;    // first row of a query's parts in `partial`
+    unsigned int *gtheta;             // per query: score bits every part may prune with (max of the parts' k-th best)
+    unsigned int *qstat;              // per query: 1 = handed on
+    unsigned long long *partial;      // [row][k] sorted keys of a part's top list
 };
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -87,8 +94,9 @@ struct Ms {
         long long pb_off[16];
         int pb_sh[16];
         unsigned char pos2u[16];
-        unsigned int pend_cnt, q_cnt, q_slot, work;
+        unsigned int pend_cnt, q_cnt, q_slot, work, gth, abort;
         int U, T, route;
+        int lo[16], hi[16];   // the part's slice of every list
         unsigned long long tot;
         unsigned int queue[QCAP];
     };
@@ -134,7 +142,7 @@ struct Ms {
         return false;
     }
 
-    __device__ void merge_pending(int lane, int k) {
+    __device__ void merge_pending(int lane, int k, unsigned int *gq) {
         const unsigned cnt = s.pend_cnt;
         unsigned long long t = s.top[lane];
         for (unsigned base = 0; base < cnt; base += 32) {
@@ -150,17 +158,19 @@ struct Ms {
         s.top[lane] = t;
         const unsigned long long kth = shfl64(t, k - 1);
         if (lane == 0) {
-            if (kth > s.theta_key) s.theta_key = kth;
+            if (kth > s.theta_key) {
+                s.theta_key = kth;
+                if (gq) atomicMax(gq, (unsigned int)(kth >> 32));  // k documents of this part score at least this much
+            }
             s.pend_cnt = 0;
         }
     }
 
     // Survivor (d, v) of list i: look it up in the other lists, largest upper bound first, until its bound falls below
     // theta; `first_absent`: the presence bitmap of list i + 1 already said no.
-    __device__ void probe_one(int i, int d, float v, unsigned long long tk, bool first_absent) {
+    __device__ void probe_one(int i, int d, float v, unsigned long long tk, float th, bool first_absent) {
         MS_CNT(2, 1);
         if (s.df[i] >= p.n_docs / 64) MS_CNT(12, 1);
-        const float th = cand_score(tk);
         float acc = __fmul_ru(s.mult[i], v);
         float vals[16];
         unsigned found = 1u << i;
@@ -186,12 +196,21 @@ struct Ms {
         }
         if (p.a.mask) sc = (float)((double)sc * p.a.mask[d]);
         const unsigned long long key = pack_cand(sc, d);
-        if (key > tk) { s.pend[atomicAdd(&s.pend_cnt, 1u)] = key; MS_CNT(5, 1); }
+        if (key > tk && sc >= th) { s.pend[atomicAdd(&s.pend_cnt, 1u)] = key; MS_CNT(5, 1); }
     }
 
     // A round: every thread takes R survivors; their (doc, score) loads and the presence test of the next list are
     // issued together (the usual survivor is absent there and ends on that test).
-    __device__ void probe_rounds(int i, unsigned n, int tid, int k) {
+    // Pruning threshold: this part's k-th best score or what the other parts of the query published (s.gth is refreshed
+    // from global memory by thread 0 only, in front of a barrier, so every decision on it is uniform over the CTA).
+    __device__ __forceinline__ float threshold() const {
+        return fmaxf(cand_score(s.theta_key), __uint_as_float(s.gth));
+    }
+    __device__ __forceinline__ void refresh(unsigned int *gq) {
+        if (gq) { const unsigned g = *(volatile unsigned int *)gq; if (g > s.gth) s.gth = g; }
+    }
+
+    __device__ void probe_rounds(int i, unsigned n, int tid, int k, unsigned int *gq) {
         const long long beg = s.beg[i];
         const float m = s.mult[i], rest = s.suf[i + 1];
         const bool has_next = i + 1 < s.U;
@@ -199,7 +218,7 @@ struct Ms {
         const int psh = has_next ? s.pb_sh[i + 1] : 0;
         for (unsigned base = 0; base < n; base += NT * R) {
             const unsigned long long tk = s.theta_key;
-            const float th = cand_score(tk);
+            const float th = threshold();
             if (tid == 0) MS_CNT(6, 1);
             int d[R];
             float v[R];
@@ -218,12 +237,13 @@ struct Ms {
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if (base + r * NT + tid < n && reaches(__fmul_ru(m, v[r]), rest, th)) probe_one(i, d[r], v[r], tk, w[r] == 0u);
+                if (base + r * NT + tid < n && reaches(__fmul_ru(m, v[r]), rest, th)) probe_one(i, d[r], v[r], tk, th, w[r] == 0u);
             }
+            if (tid == 0) refresh(gq);
             __syncthreads();
             if (s.pend_cnt > 0) {
                 if (tid == 0) MS_CNT(7, 1);
-                if (tid < 32) merge_pending(tid, k);
+                if (tid < 32) merge_pending(tid, k, gq);
                 __syncthreads();
             }
         }
@@ -231,21 +251,22 @@ struct Ms {
         __syncthreads();
     }
 
-    __device__ __forceinline__ void check(float v, int pos, int df, float m, float rest, float th) {
+    __device__ __forceinline__ void check(float v, int pos, int df, int lo, float m, float rest, float th) {
         if (__fmul_ru(__fmaf_ru(m, v, rest), 1.00002f) >= th && (unsigned)pos < (unsigned)df)
-        { s.queue[atomicAdd(&s.q_cnt, 1u)] = (unsigned)pos; MS_CNT(1, 1); }
+        { s.queue[atomicAdd(&s.q_cnt, 1u)] = (unsigned)(pos + lo); MS_CNT(1, 1); }
     }
 
-    __device__ bool stream(int i, int tid, int k) {
-        const long long beg = s.beg[i];
-        const int df = s.df[i];
+    __device__ bool stream(int i, int tid, int k, unsigned int *gq) {
+        const int lo = s.lo[i];
+        const long long beg = s.beg[i] + lo;  // positions are pushed relative to the column start
+        const int df = s.hi[i] - lo;
         const float m = s.mult[i], rest = s.suf[i + 1];
         const int head = (int)(beg & 3);
         const int nvec = (df + head + 3) >> 2;
         const float4 *vp = reinterpret_cast<const float4 *>(p.data + (beg - head));
         if (tid == 0) { MS_CNT(0, df); MS_CNT(8, 1); }
         for (int v0 = 0; v0 < nvec; v0 += NT * UNROLL) {
-            const float th = cand_score(s.theta_key);
+            const float th = threshold();
             float4 x[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -257,18 +278,19 @@ struct Ms {
                 const int v = v0 + u * NT + tid;
                 const int pos = 4 * v - head;
                 if (v < nvec) {
-                    check(x[u].x, pos, df, m, rest, th);
-                    check(x[u].y, pos + 1, df, m, rest, th);
-                    check(x[u].z, pos + 2, df, m, rest, th);
-                    check(x[u].w, pos + 3, df, m, rest, th);
+                    check(x[u].x, pos, df, lo, m, rest, th);
+                    check(x[u].y, pos + 1, df, lo, m, rest, th);
+                    check(x[u].z, pos + 2, df, lo, m, rest, th);
+                    check(x[u].w, pos + 3, df, lo, m, rest, th);
                 }
             }
+            if (tid == 0) refresh(gq);
             __syncthreads();
             const unsigned n = s.q_cnt;
             __syncthreads();  // nobody pushes the next chunk's survivors before everybody read the count
             const bool last = v0 + NT * UNROLL >= nvec;
             if (n >= (unsigned)(NT * R) || (last && n > 0)) {
-                probe_rounds(i, n, tid, k);
+                probe_rounds(i, n, tid, k, gq);
                 if (s.work > p.budget) return false;  // too many survivors: the streaming kernel does this query
             }
         }
@@ -276,7 +298,7 @@ struct Ms {
     }
 
     // warp 0: tokens -> distinct lists ordered by upper bound, suffix sums, start threshold
-    __device__ void prologue(int q, int lane) {
+    __device__ void prologue(int q, int part, int P, int lane) {
         const long long qs = p.a.q_ptr[q], qe = p.a.q_ptr[q + 1];
         const long long Tl = qe - qs;
         bool route = p.route_all || Tl > kMaxTok || Tl == 0 || (p.a.mask && p.ctrl->mask_bad);
@@ -339,7 +361,8 @@ struct Ms {
                 for (int j = U - 1; j >= 0; --j) { acc = __fadd_ru(acc, s.ub[j]); s.suf[j] = acc; }
                 // the k-th largest posting of one token is reached by k distinct documents and a document scores at
                 // least each of its postings: the float below it is a safe start value (as in retrieve_fast.cu)
-                s.theta_key = kb > 0u ? ((unsigned long long)(kb - 1u) << 32) : 0ull;
+                s.theta_key = 0ull;
+                s.gth = kb > 0u ? kb - 1u : 0u;
                 s.U = U;
                 s.T = T;
                 s.tot = tot;
@@ -350,50 +373,75 @@ struct Ms {
             s.top[lane] = 0ull;
             __syncwarp();
             if (tot == 0 || (long long)s.df[0] > p.max_first) route = true;
+            // this part's slice of every list: documents [part * n_docs / P, (part + 1) * n_docs / P)
+            if (!route && lane < U) {
+                int lo = 0, hi = s.df[lane];
+                if (P > 1) {
+                    const int d0 = (int)((long long)p.n_docs * part / P), d1 = (int)((long long)p.n_docs * (part + 1) / P);
+                    if (part > 0) lo = lower_bound(lane, d0);
+                    if (part + 1 < P) hi = lower_bound(lane, d1);
+                }
+                s.lo[lane] = lo;
+                s.hi[lane] = hi;
+            }
         }
         if (lane == 0) s.route = route ? 1 : 0;
+    }
+
+    // first position of list j whose document is >= d
+    __device__ int lower_bound(int j, int d) const {
+        int lo = 0, hi = s.df[j];
+        const long long bo = s.bt_off[j];
+        if (bo >= 0) {
+            const unsigned b = (unsigned)d >> s.bt_sh[j];
+            lo = (int)__ldg(p.btab + bo + b);
+            hi = (int)__ldg(p.btab + bo + b + 1);
+        }
+        const int32_t *col = p.indices + s.beg[j];
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(col + mid) < d) lo = mid + 1; else hi = mid;
+        }
+        return lo;
     }
 
     __device__ void run() {
         const int tid = threadIdx.x;
         const int k = p.a.k;
+        const unsigned n_items = p.ctrl->ms_items;
         for (;;) {
             if (tid == 0) s.q_slot = atomicAdd(&p.ctrl->ms_next, 1u);
             __syncthreads();
             const unsigned slot = s.q_slot;
-            if (slot >= (unsigned)p.a.n_queries) break;
-            const int q = p.order ? (int)p.order[slot] : (int)slot;
-            if (tid < 32) prologue(q, tid);
+            if (slot >= n_items) break;
+            const unsigned long long item = p.items[slot];
+            const int q = (int)(unsigned)(item & 0xffffffffull), part = (int)((item >> 32) & 0xffu), P = (int)((item >> 40) & 0xffu);
+            unsigned int *gq = (P > 1) ? p.gtheta + q : nullptr;
+            if (tid < 32) prologue(q, part, P, tid);
             __syncthreads();
             if (!s.route) {
+                if (gq && tid == 0 && s.gth) atomicMax(gq, s.gth);
                 const int U = s.U;
                 for (int i = 0; i < U; ++i) {
-                    const float th = cand_score(s.theta_key);
+                    if (P > 1) {
+                        if (tid == 0) { refresh(gq); s.abort = *(volatile unsigned int *)(p.qstat + q); }
+                        __syncthreads();
+                        if (s.abort) break;  // another part gave the query up
+                    }
+                    const float th = threshold();
                     if (__fmul_ru(s.suf[i], 1.00002f) < th) { if (tid == 0) MS_CNT(9, U - i); break; }  // no unseen document can reach theta
-                    if (!stream(i, tid, k)) break;
+                    if (s.hi[i] > s.lo[i] && !stream(i, tid, k, gq)) break;
                 }
                 if (s.work > p.budget) {
                     if (tid == 0) s.route = 1;
                 } else if (tid < 32) {
-                    const unsigned long long t = s.top[tid];
-                    const unsigned long long kth = shfl64(t, k - 1);
-                    if (kth != 0ull && cand_score(kth) > 0.0f) {
-                        const bool has_shift = p.a.shift != nullptr;
-                        if (tid < k) {
-                            float sc = cand_score(t);
-                            if (has_shift) sc = __fadd_rn(sc, p.a.shift[q]);
-                            p.a.out_ids[(size_t)q * k + tid] = cand_doc(t) + p.doc_base;
-                            p.a.out_scores[(size_t)q * k + tid] = sc;
-                        }
-                        if (tid == 0) atomicAdd(&p.ctrl->posting_count, s.tot);
-                    } else if (tid == 0) {
-                        s.route = 1;  // fewer than k positive matches: padding rules live in retrieve_fast.cu
-                    }
+                    // the part's top list (sorted, zeros = empty); merged, checked and written by ms_merge_kernel
+                    if (tid < k) p.partial[((size_t)p.part_base[q] + part) * k + tid] = s.top[tid];
                 }
                 __syncthreads();
             }
             if (tid == 0) MS_CNT(s.route ? 11 : 10, 1);
-            if (s.route && tid == 0) p.fb_list[atomicAdd(&p.ctrl->fb_count, 1u)] = (unsigned)q;
+            if (s.route && tid == 0) p.qstat[q] = 1u;
             __syncthreads();
         }
 #ifdef BM25CU_PROFILE
@@ -402,6 +450,111 @@ struct Ms {
 #endif
     }
 };
+
+// ---- plan: cut every query into doc-range parts of bounded cost and order the parts longest first ------------------
+// cost of a query = its postings without the longest list (the list that is usually only probed). One CTA.
+constexpr int kMsMaxParts = 16;
+__global__ void __launch_bounds__(1024) ms_plan_kernel(const int32_t *__restrict__ q_tokens, const int64_t *__restrict__ q_ptr,
+                                                       int32_t n_queries, const int64_t *__restrict__ indptr, int32_t n_vocab,
+                                                       long long part_cost, int max_parts, unsigned long long *items,
+                                                       unsigned int *part_base, unsigned long long *qtot, unsigned int *gtheta,
+                                                       unsigned int *qstat, unsigned char *scratch /* 2 bytes per query */,
+                                                       Ctrl *ctrl) {
+    __shared__ unsigned int hist[64], base[64];
+    __shared__ long long ws[33];
+    __shared__ long long carry_s;
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    unsigned char *bucket = scratch, *parts = scratch + n_queries;
+    const int n_round = ((n_queries + blockDim.x - 1) / blockDim.x) * blockDim.x;
+    for (int q = threadIdx.x; q < n_round; q += blockDim.x) {
+        int P = 0;
+        if (q < n_queries) {
+            unsigned long long tot = 0, mx = 0;
+            const long long T = q_ptr[q + 1] - q_ptr[q];
+            for (int64_t i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
+                const int tok = q_tokens[i];
+                if ((unsigned)tok < (unsigned)n_vocab) {
+                    const unsigned long long df = (unsigned long long)(indptr[tok + 1] - indptr[tok]);
+                    tot += df;
+                    mx = df > mx ? df : mx;
+                }
+            }
+            const unsigned long long cost = (T > 1 && tot > mx) ? tot - mx : tot;
+            P = 1;
+            if (T >= 1 && T <= kMaxTok && cost > (unsigned long long)part_cost) {
+                const unsigned long long want = (cost + part_cost - 1) / part_cost;
+                P = want > (unsigned long long)max_parts ? max_parts : (int)want;
+            }
+            const unsigned long long per = cost / P;
+            const int bk = per ? 64 - __clzll((long long)per) : 0;
+            bucket[q] = (unsigned char)bk;
+            parts[q] = (unsigned char)P;
+            qtot[q] = tot;
+            gtheta[q] = 0u;
+            qstat[q] = 0u;
+            atomicAdd(&hist[bk], (unsigned)P);
+        }
+        long long total;
+        const long long ex = block_exclusive_scan((long long)P, ws, &total);
+        if (q < n_queries) part_base[q] = (unsigned int)(carry_s + ex);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int bk = 63; bk >= 0; --bk) { base[bk] = acc; acc += hist[bk]; }
+        ctrl->ms_items = acc;
+        part_base[n_queries] = (unsigned int)carry_s;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < n_queries; q += blockDim.x) {
+        const unsigned P = parts[q];
+        const unsigned at = atomicAdd(&base[bucket[q]], P);
+        for (unsigned j = 0; j < P; ++j)
+            items[at + j] = (unsigned long long)(unsigned)q | ((unsigned long long)j << 32) | ((unsigned long long)P << 40);
+    }
+}
+
+// ---- merge: one warp per query unites the parts' top lists, checks the result and writes the row -------------------
+__global__ void __launch_bounds__(256) ms_merge_kernel(const unsigned long long *__restrict__ items_unused, const unsigned int *__restrict__ part_base,
+                                                       const unsigned long long *__restrict__ partial, const unsigned int *__restrict__ qstat,
+                                                       const unsigned long long *__restrict__ qtot, RetrieveArgs a, int32_t doc_base,
+                                                       Ctrl *ctrl, unsigned int *fb_list) {
+    const int q = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= a.n_queries) return;
+    const int k = a.k;
+    bool route = qstat[q] != 0u;
+    unsigned long long t = 0ull;
+    if (!route) {
+        const unsigned r0 = part_base[q], r1 = part_base[q + 1];
+        for (unsigned r = r0; r < r1; ++r) {
+            const unsigned long long b = (lane < k) ? partial[(size_t)r * k + lane] : 0ull;  // sorted descending
+            t = umax64(t, shfl64(b, 31 - lane));
+#pragma unroll
+            for (int stride = 16; stride > 0; stride >>= 1) {
+                const unsigned long long o = shfl64_xor(t, stride);
+                t = ((lane & stride) == 0) ? umax64(t, o) : umin64(t, o);
+            }
+        }
+        const unsigned long long kth = shfl64(t, k - 1);
+        route = !(kth != 0ull && cand_score(kth) > 0.0f);  // fewer than k positive matches: padding rules live in retrieve_fast.cu
+    }
+    if (route) {
+        if (lane == 0) fb_list[atomicAdd(&ctrl->fb_count, 1u)] = (unsigned)q;
+        return;
+    }
+    if (lane < k) {
+        float sc = cand_score(t);
+        if (a.shift != nullptr) sc = __fadd_rn(sc, a.shift[q]);
+        a.out_ids[(size_t)q * k + lane] = cand_doc(t) + doc_base;
+        a.out_scores[(size_t)q * k + lane] = sc;
+    }
+    if (lane == 0) atomicAdd(&ctrl->posting_count, qtot[q]);
+}
 
 template <int NT, int UNROLL, int R, int MINB>
 __global__ void __launch_bounds__(NT, MINB) retrieve_ms_kernel(const __grid_constant__ MsParams p) {
@@ -427,7 +580,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
         else if (a.k <= 10) p.colkth = ix->d_colkth;
         else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
     }
-    p.order = ix->order_valid ? ix->d_order.as<unsigned int>() : nullptr;
+    p.order = nullptr;
     const bool use_bt = env_int_ms("BM25CU_MS_BTAB", 1) && ix->d_btab != nullptr;
     p.btab = use_bt ? ix->d_btab : nullptr;
     p.btab_off = ix->d_btab_off;
@@ -444,12 +597,40 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.route_all = (!ix->nonneg) || a.k > 32 || (a.mask != nullptr && env_int_ms("BM25CU_MASK_FAST", 1) == 0) ||
                   env_int_ms("BM25CU_FORCE_GENERAL", 0);
     p.max_first = (long long)env_int_ms("BM25CU_MS_MAXFIRST", 0x7fffffff);
-    p.budget = (unsigned int)env_int_ms("BM25CU_MS_BUDGET", 32768);
+    p.budget = (unsigned int)env_int_ms("BM25CU_MS_BUDGET", 1 << 20);
+    // plan: parts of at most `part_cost` postings (BM25CU_MS_PARTCOST), at most BM25CU_MS_MAXPARTS per query
+    int max_parts = env_int_ms("BM25CU_MS_MAXPARTS", kMsMaxParts);
+    if (max_parts < 1) max_parts = 1;
+    if (max_parts > 255) max_parts = 255;
+    const long long part_cost = (long long)env_int_ms("BM25CU_MS_PARTCOST", 32768);
+    const size_t nq = (size_t)a.n_queries;
+    int rc;
+    if ((rc = ix->d_ms_items.reserve(nq * (size_t)max_parts * 8))) return rc;
+    if ((rc = ix->d_ms_rows.reserve((nq + 1) * 4 + nq * 2 + 16))) return rc;
+    if ((rc = ix->d_ms_q.reserve(nq * 16))) return rc;
+    if ((rc = ix->d_ms_partial.reserve(nq * (size_t)max_parts * (size_t)a.k * 8))) return rc;
+    unsigned long long *items = ix->d_ms_items.as<unsigned long long>();
+    unsigned int *part_base = ix->d_ms_rows.as<unsigned int>();
+    unsigned char *scratch = reinterpret_cast<unsigned char *>(part_base + nq + 1);
+    unsigned long long *qtot = ix->d_ms_q.as<unsigned long long>();
+    unsigned int *gtheta = reinterpret_cast<unsigned int *>(qtot + nq);
+    unsigned int *qstat = gtheta + nq;
+    ms_plan_kernel<<<1, 1024, 0, ix->stream>>>(a.q_tokens, a.q_ptr, a.n_queries, ix->d_indptr, ix->n_vocab, part_cost, max_parts,
+                                               items, part_base, qtot, gtheta, qstat, scratch, d_ctrl);
+    BM25CU_CHECK(cudaGetLastError());
+    p.items = items;
+    p.part_base = part_base;
+    p.gtheta = gtheta;
+    p.qstat = qstat;
+    p.partial = ix->d_ms_partial.as<unsigned long long>();
     const int per_sm = env_int_ms("BM25CU_MS_CTAS", 8);
     const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 8);
     retrieve_ms_kernel<128, 4, 4, 8><<<grid, 128, 0, ix->stream>>>(p);
     BM25CU_CHECK(cudaGetLastError());
-    if (launches) ++*launches;
+    ms_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ix->stream>>>(items, part_base, p.partial, qstat, qtot, a, ix->doc_base,
+                                                                              d_ctrl, d_fb_list);
+    BM25CU_CHECK(cudaGetLastError());
+    if (launches) *launches += 3;
     return BM25CU_OK;
 }
 
