@@ -602,7 +602,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     int max_parts = env_int_ms("BM25CU_MS_MAXPARTS", kMsMaxParts);
     if (max_parts < 1) max_parts = 1;
     if (max_parts > 255) max_parts = 255;
-    const long long part_cost = (long long)env_int_ms("BM25CU_MS_PARTCOST", 32768);
+    const long long part_cost = (long long)env_int_ms("BM25CU_MS_PARTCOST", 65536);
     const size_t nq = (size_t)a.n_queries;
     int rc;
     if ((rc = ix->d_ms_items.reserve(nq * (size_t)max_parts * 8))) return rc;

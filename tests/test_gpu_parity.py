@@ -184,9 +184,17 @@ def test_random_corpus_vs_c_oracle(k):
     dense_fn = lambda qi: CO.scores_dense(data, indices, indptr, n_docs, queries[qi], shift=sh[qi])  # noqa: E731
     check_topk_rows(ids, sc, rid, rsc, dense_fn if k <= 100 else None, what=f"random k={k}")
     # small stage / tag settings force many windows and the same answer
-    for env in ({"BM25CU_POOL": "1024", "BM25CU_TAG": "4096"}, {"BM25CU_THREADS": "256", "BM25CU_CTAS_PER_SM": "2"},
-                {"BM25CU_MAXSHIFT": "0"}, {"BM25CU_PRUNE": "0"}, {"BM25CU_MAXSHIFT": "1", "BM25CU_TAG": "8192"},
-                {"BM25CU_THREADS": "128", "BM25CU_PRUNE": "0"}, {"BM25CU_THREADS": "1024"}):
+    # BM25CU_MS=0: the streaming kernel alone (retrieve_fast.cu); the other sets steer the list-at-a-time kernel
+    # (retrieve_ms.cu, k <= 32): one part per query, many small parts, a tiny survivor budget (queries handed on to the
+    # streaming kernel), lookups without bucket tables / presence bitmaps
+    for env in ({"BM25CU_MS": "0"}, {"BM25CU_MS": "0", "BM25CU_POOL": "1024", "BM25CU_TAG": "4096"},
+                {"BM25CU_MS": "0", "BM25CU_THREADS": "256", "BM25CU_CTAS_PER_SM": "2"},
+                {"BM25CU_MS": "0", "BM25CU_MAXSHIFT": "0"}, {"BM25CU_MS": "0", "BM25CU_PRUNE": "0"},
+                {"BM25CU_MS": "0", "BM25CU_MAXSHIFT": "1", "BM25CU_TAG": "8192"},
+                {"BM25CU_MS": "0", "BM25CU_THREADS": "128", "BM25CU_PRUNE": "0"}, {"BM25CU_MS": "0", "BM25CU_THREADS": "1024"},
+                {"BM25CU_MS_MAXPARTS": "1"}, {"BM25CU_MS_PARTCOST": "512"}, {"BM25CU_MS_PARTCOST": "2000", "BM25CU_MS_MAXPARTS": "255"},
+                {"BM25CU_MS_BUDGET": "64"}, {"BM25CU_MS_BUDGET": "600", "BM25CU_MS_PARTCOST": "4096"},
+                {"BM25CU_MS_BTAB": "0"}, {"BM25CU_MS_PBM": "0"}, {"BM25CU_MS_BTAB": "0", "BM25CU_MS_PBM": "0", "BM25CU_SEED_KTH": "0"}):
         old = {kk: os.environ.get(kk) for kk in env}
         os.environ.update(env)
         try:
