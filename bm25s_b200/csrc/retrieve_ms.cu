@@ -166,33 +166,39 @@ struct Ms {
         }
     }
 
-    // Survivor (d, v) of list i: look it up in the other lists, largest upper bound first, until its bound falls below
-    // theta; `first_absent`: the presence bitmap of list i + 1 already said no.
-    __device__ void probe_one(int i, int d, float v, unsigned long long tk, float th, bool first_absent) {
-        MS_CNT(2, 1);
-        if (s.df[i] >= p.n_docs / 64) MS_CNT(12, 1);
-        float acc = __fmul_ru(s.mult[i], v);
-        float vals[16];
-        unsigned found = 1u << i;
-        vals[i] = v;
-        const int U = s.U;
-        for (int j = i + 1; j < U; ++j) {
-            float val;
-            if (!(first_absent && j == i + 1) && lookup(j, d, val)) {
-                vals[j] = val;
-                found |= 1u << j;
-                acc = __fadd_ru(acc, __fmul_ru(s.mult[j], val));
-            }
-            if (!reaches(acc, s.suf[j + 1], th)) return;
+    // position search of document d in list j (after its presence bitmap said "maybe")
+    __device__ __forceinline__ bool search(int j, int d, float &val) {
+        const long long beg = s.beg[j];
+        int lo = 0, hi = s.df[j];
+        const long long bo = s.bt_off[j];
+        if (bo >= 0) {
+            const unsigned b = (unsigned)d >> s.bt_sh[j];
+            lo = (int)__ldg(p.btab + bo + b);
+            hi = (int)__ldg(p.btab + bo + b + 1);
         }
+        const int32_t *col = p.indices + beg;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const int x = __ldg(col + mid);
+            MS_CNT(4, 1);
+            if (x < d) lo = mid + 1;
+            else if (x > d) hi = mid;
+            else { val = __ldg(p.data + beg + mid); MS_CNT(15, 1); return true; }
+        }
+        return false;
+    }
+
+    // A survivor that passed every bound: drop it if an earlier list holds it (scored there), else sum it in the
+    // reference's order - token by token, duplicates again (bm25s/__init__.py:316-318) - and offer it to the top list.
+    __device__ void finish(int i, int d, float v, unsigned found, const float *vals, unsigned long long tk, float th) {
         float dummy;
         for (int j = i - 1; j >= 0; --j)
-            if (lookup(j, d, dummy)) return;  // contains an earlier list's token: scored when that list was streamed
+            if (lookup(j, d, dummy)) return;
         float sc = 0.0f;
         const int T = s.T;
-        for (int t = 0; t < T; ++t) {  // the reference's order: token by token, duplicates again (__init__.py:316-318)
+        for (int t = 0; t < T; ++t) {
             const unsigned u = s.pos2u[t];
-            if (u < 16u && ((found >> u) & 1u)) sc = __fadd_rn(sc, vals[u]);
+            if (u < 16u && ((found >> u) & 1u)) sc = __fadd_rn(sc, (int)u == i ? v : vals[u]);
         }
         if (p.a.mask) sc = (float)((double)sc * p.a.mask[d]);
         const unsigned long long key = pack_cand(sc, d);
@@ -213,16 +219,16 @@ struct Ms {
     __device__ void probe_rounds(int i, unsigned n, int tid, int k, unsigned int *gq) {
         const long long beg = s.beg[i];
         const float m = s.mult[i], rest = s.suf[i + 1];
-        const bool has_next = i + 1 < s.U;
-        const long long po = has_next ? s.pb_off[i + 1] : -1;
-        const int psh = has_next ? s.pb_sh[i + 1] : 0;
+        const int U = s.U;
         for (unsigned base = 0; base < n; base += NT * R) {
             const unsigned long long tk = s.theta_key;
             const float th = threshold();
             if (tid == 0) MS_CNT(6, 1);
             int d[R];
-            float v[R];
-            unsigned w[R];
+            float v[R], acc[R];
+            unsigned found[R];
+            bool alive[R];
+            float vals[R * 16];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const unsigned idx = base + r * NT + tid;
@@ -232,13 +238,57 @@ struct Ms {
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const unsigned x = (unsigned)d[r] >> psh;
-                w[r] = (po >= 0) ? ((__ldg(p.pbm + po + (x >> 5)) >> (x & 31u)) & 1u) : 1u;
+                acc[r] = __fmul_ru(m, v[r]);
+                alive[r] = base + r * NT + tid < n && reaches(acc[r], rest, th);
+                found[r] = 1u << i;
+                if (alive[r]) MS_CNT(2, 1);
+            }
+            // The other lists, largest upper bound first. Per list: the presence tests of the R survivors go out together,
+            // the (few) position searches run with the lanes that need one side by side, then the bounds are re-checked.
+            for (int j = i + 1; j < U; ++j) {
+                const long long po = s.pb_off[j];
+                const int psh = s.pb_sh[j];
+                unsigned w[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const unsigned x = (unsigned)d[r] >> psh;
+                    w[r] = (po >= 0 && alive[r]) ? __ldg(p.pbm + po + (x >> 5)) : 0xffffffffu;
+                }
+                unsigned todo = 0u;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const unsigned x = (unsigned)d[r] >> psh;
+                    if (alive[r]) { MS_CNT(3, 1); if ((w[r] >> (x & 31u)) & 1u) todo |= 1u << r; }
+                }
+                const float mj = s.mult[j];
+                while (todo) {
+                    const int r = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    int dd = d[0];
+#pragma unroll
+                    for (int rr = 1; rr < R; ++rr) dd = (rr == r) ? d[rr] : dd;
+                    float val;
+                    MS_CNT(13, 1);
+                    if (search(j, dd, val)) {
+                        const float add = __fmul_ru(mj, val);
+                        vals[r * 16 + j] = val;
+#pragma unroll
+                        for (int rr = 0; rr < R; ++rr)
+                            if (rr == r) { acc[rr] = __fadd_ru(acc[rr], add); found[rr] |= 1u << j; }
+                    }
+                }
+                const float sufn = s.suf[j + 1];
+                bool any = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    alive[r] = alive[r] && reaches(acc[r], sufn, th);
+                    any |= alive[r];
+                }
+                if (!__any_sync(0xffffffffu, any)) break;
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (base + r * NT + tid < n && reaches(__fmul_ru(m, v[r]), rest, th)) probe_one(i, d[r], v[r], tk, th, w[r] == 0u);
-            }
+            for (int r = 0; r < R; ++r)
+                if (alive[r]) finish(i, d[r], v[r], found[r], vals + r * 16, tk, th);
             if (tid == 0) refresh(gq);
             __syncthreads();
             if (s.pend_cnt > 0) {
