@@ -673,8 +673,8 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.gtheta = gtheta;
     p.qstat = qstat;
     p.partial = ix->d_ms_partial.as<unsigned long long>();
-    const int per_sm = env_int_ms("BM25CU_MS_CTAS", 8);
-    const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 8);
+    const int per_sm = env_int_ms("BM25CU_MS_CTAS", 9);  // 55 registers: nine 128-thread CTAs are resident per SM
+    const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 9);
     retrieve_ms_kernel<128, 4, 4, 8><<<grid, 128, 0, ix->stream>>>(p);
     BM25CU_CHECK(cudaGetLastError());
     ms_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ix->stream>>>(items, part_base, p.partial, qstat, qtot, a, ix->doc_base,
