@@ -144,6 +144,9 @@ struct Ctrl {
     unsigned int ms_next;        // work-queue cursor of the list-at-a-time kernel (retrieve_ms.cu)
     unsigned int fb_count;       // queries that kernel handed on to the streaming kernel
     unsigned int ms_items;       // work items (query parts) of that kernel
+    unsigned int ms_rows;        // rows handed out in its partial-result buffer
+    unsigned int ms_hist[64];    // parts per log2(cost) bucket, and the scatter cursors of the buckets (ms_plan_*_kernel)
+    unsigned int ms_cursor[64];
     unsigned long long prof[48];  // phase cycle counters / event counts of the fused kernel (BM25CU_PROFILE builds)
 };
 

@@ -216,21 +216,21 @@ static int build_bucket_tables(bm25cu_index *ix) {
 // with s the largest shift that keeps at least 8 bits per posting (s = 0, an exact bitmap, for columns denser than
 // n_docs / 8). A document that is not in the column - the usual outcome of a lookup - is recognised by one load with
 // probability >= exp(-1/8). Size: at most 2 bytes per posting. Derived at upload, not part of the saved index.
-__device__ __forceinline__ int pbm_shift_of(long long df, int n_docs) {
+__device__ __forceinline__ int pbm_shift_of(long long df, int n_docs, int bits_per_posting) {
     int s = 0;
-    while (s < 30 && ((8ll * df) << (s + 1)) <= (long long)n_docs) ++s;
+    while (s < 30 && (((long long)bits_per_posting * df) << (s + 1)) <= (long long)n_docs) ++s;
     return s;
 }
 
-__global__ void pbm_size_kernel(const int64_t *__restrict__ indptr, int32_t n_vocab, int32_t n_docs, long long *sizes,
-                                unsigned char *shifts) {
+__global__ void pbm_size_kernel(const int64_t *__restrict__ indptr, int32_t n_vocab, int32_t n_docs, int bits_per_posting,
+                                long long *sizes, unsigned char *shifts) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_vocab) return;
     const long long df = indptr[t + 1] - indptr[t];
     long long sz = 0;
     int sh = 0;
     if (df >= kBtabMinDf) {
-        sh = pbm_shift_of(df, n_docs);
+        sh = pbm_shift_of(df, n_docs, bits_per_posting);
         sz = ((((long long)(n_docs - 1) >> sh) + 32) >> 5) + 1;  // 32-bit words
     }
     sizes[t] = sz;
@@ -266,7 +266,10 @@ static int build_presence_bitmaps(bm25cu_index *ix) {
     BM25CU_CHECK(cudaMalloc(&d_tmp, scan_tmp_elems(V) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_pbm_off, (size_t)(V + 1) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_pbm_sh, (size_t)V));
-    pbm_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, d_sizes, ix->d_pbm_sh);
+    const char *bv = getenv("BM25CU_PBM_BITS");
+    int bits = (bv && *bv) ? atoi(bv) : 8;  // at least this many bits per posting
+    if (bits < 1) bits = 1;
+    pbm_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, bits, d_sizes, ix->d_pbm_sh);
     BM25CU_CHECK(cudaGetLastError());
     BM25CU_CHECK(exclusive_scan<long long>(d_sizes, V, ix->d_pbm_off, d_tmp, ix->stream));
     long long total = 0;

@@ -20,7 +20,6 @@
 // Queries this kernel does not take (empty, > 15 tokens, k > 32, fewer than k positive matches, cost rule) are
 // appended to `fb_list` and served by retrieve_fast_kernel in the same call.
 #include "fast_common.cuh"
-#include "scan.cuh"
 
 namespace bm25cu {
 
@@ -50,6 +49,7 @@ struct MsParams {
     unsigned int *gtheta;             // per query: score bits every part may prune with (max of the parts' k-th best)
     unsigned int *qstat;              // per query: 1 = handed on
     unsigned long long *partial;      // [row][k] sorted keys of a part's top list
+    int kcap;                         // next_pow2(k), at least 32; > 32: the top list lives in shared memory
 };
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -76,14 +76,47 @@ __device__ __forceinline__ bool reaches(float acc, float rest, float th) {
     return __fmul_ru(__fadd_ru(acc, rest), 1.00002f) >= th;
 }
 
-template <int NT, int UNROLL, int R>
+// Block-wide: `add[0..cnt)` (descending, distinct non-zero keys) merged into `cur[0..cap)` (descending, zeros = empty);
+// the cap largest go to `nxt` (rank of an element = its index + how many keys of the other list beat it).
+__device__ __forceinline__ void rank_merge(const unsigned long long *cur, unsigned long long *nxt, int cap,
+                                           const unsigned long long *add, int cnt, int tid, int nt) {
+    for (int a = tid; a < cap; a += nt) {
+        const unsigned long long key = cur[a];
+        int lo = 0, hi = cnt;  // first add[i] <= key
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (add[mid] > key) lo = mid + 1; else hi = mid; }
+        if (a + lo < cap) nxt[a + lo] = key;
+    }
+    for (int b = tid; b < cnt; b += nt) {
+        const unsigned long long key = add[b];
+        int lo = 0, hi = cap;  // first cur[i] < key
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cur[mid] > key) lo = mid + 1; else hi = mid; }
+        if (b + lo < cap) nxt[b + lo] = key;
+    }
+}
+
+// Block-wide bitonic sort, descending, n a power of two, keys in shared memory
+__device__ __forceinline__ void block_sort_desc(unsigned long long *a, int n, int tid, int nt) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (n >> 1); t += nt) {
+                const int lo = ((t / stride) * stride << 1) + (t % stride), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long x = a[lo], y = a[hi];
+                if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int NT, int UNROLL, int R, bool BIG>
 struct Ms {
     static constexpr int CHUNK = NT * 4 * UNROLL;
     static constexpr int QCAP = CHUNK + NT * R;
     struct Sh {
         long long beg[16];
         unsigned long long top[32];
-        unsigned long long pend[NT * R];
+        unsigned long long pend[NT * R + 32];
         unsigned long long theta_key;
         int df[16];
         float ub[16];
@@ -94,7 +127,7 @@ struct Ms {
         long long pb_off[16];
         int pb_sh[16];
         unsigned char pos2u[16];
-        unsigned int pend_cnt, q_cnt, q_slot, work, gth, abort;
+        unsigned int pend_cnt, q_cnt, q_slot, work, gth, abort, top_sel;
         int U, T, route;
         int lo[16], hi[16];   // the part's slice of every list
         unsigned long long tot;
@@ -102,6 +135,8 @@ struct Ms {
     };
     const MsParams &p;
     Sh &s;
+    unsigned long long *big;  // k > 32: two top lists of kcap keys (dynamic shared memory), s.top_sel names the current one
+    int kcap;
 #ifdef BM25CU_PROFILE
     // 0 postings streamed, 1 survivors queued, 2 survivors probed, 3 lookups, 4 lookup steps, 5 candidates accepted,
     // 6 probe rounds, 7 merges, 8 lists streamed, 9 lists skipped, 10 queries served, 11 queries handed on
@@ -110,7 +145,7 @@ struct Ms {
 #else
 #define MS_CNT(i, v)
 #endif
-    __device__ Ms(const MsParams &p_, Sh &s_) : p(p_), s(s_) {}
+    __device__ Ms(const MsParams &p_, Sh &s_, unsigned long long *big_) : p(p_), s(s_), big(big_), kcap(p_.kcap) {}
 
     // is document d in list j? (val = its score)
     __device__ __forceinline__ bool lookup(int j, int d, float &val) {
@@ -140,6 +175,27 @@ struct Ms {
             else { val = __ldg(p.data + beg + mid); MS_CNT(15, 1); return true; }
         }
         return false;
+    }
+
+    // k > 32: all threads. The pending keys are sorted (bitonic, shared memory) and rank-merged into the top list.
+    __device__ void merge_pending_big(int tid, int k, unsigned int *gq) {
+        const int cnt = (int)s.pend_cnt;
+        const int P2 = next_pow2(cnt > 1 ? cnt : 1);
+        for (int i = cnt + tid; i < P2; i += NT) s.pend[i] = 0ull;
+        __syncthreads();
+        block_sort_desc(s.pend, P2, tid, NT);
+        unsigned long long *cur = big + (s.top_sel ? kcap : 0), *nxt = big + (s.top_sel ? 0 : kcap);
+        rank_merge(cur, nxt, kcap, s.pend, cnt, tid, NT);
+        __syncthreads();
+        if (tid == 0) {
+            s.top_sel ^= 1u;
+            const unsigned long long kth = nxt[k - 1];
+            if (kth > s.theta_key) {
+                s.theta_key = kth;
+                if (gq) atomicMax(gq, (unsigned int)(kth >> 32));
+            }
+            s.pend_cnt = 0;
+        }
     }
 
     __device__ void merge_pending(int lane, int k, unsigned int *gq) {
@@ -291,9 +347,15 @@ struct Ms {
                 if (alive[r]) finish(i, d[r], v[r], found[r], vals + r * 16, tk, th);
             if (tid == 0) refresh(gq);
             __syncthreads();
-            if (s.pend_cnt > 0) {
+            if (!BIG) {
+                if (s.pend_cnt > 0) {
+                    if (tid == 0) MS_CNT(7, 1);
+                    if (tid < 32) merge_pending(tid, k, gq);
+                    __syncthreads();
+                }
+            } else if (s.pend_cnt >= 32u || (s.pend_cnt > 0 && base + NT * R >= n)) {  // the shared-memory merge is dearer: batch it
                 if (tid == 0) MS_CNT(7, 1);
-                if (tid < 32) merge_pending(tid, k, gq);
+                merge_pending_big(tid, k, gq);
                 __syncthreads();
             }
         }
@@ -419,8 +481,10 @@ struct Ms {
                 s.pend_cnt = 0;
                 s.q_cnt = 0;
                 s.work = 0;
+                s.top_sel = 0;
             }
             s.top[lane] = 0ull;
+            if (BIG) for (int e = lane; e < kcap; e += 32) big[e] = 0ull;
             __syncwarp();
             if (tot == 0 || (long long)s.df[0] > p.max_first) route = true;
             // this part's slice of every list: documents [part * n_docs / P, (part + 1) * n_docs / P)
@@ -484,6 +548,9 @@ struct Ms {
                 }
                 if (s.work > p.budget) {
                     if (tid == 0) s.route = 1;
+                } else if (BIG) {
+                    const unsigned long long *cur = big + (s.top_sel ? kcap : 0);
+                    for (int t = tid; t < k; t += NT) p.partial[((size_t)p.part_base[q] + part) * k + t] = cur[t];
                 } else if (tid < 32) {
                     // the part's top list (sorted, zeros = empty); merged, checked and written by ms_merge_kernel
                     if (tid < k) p.partial[((size_t)p.part_base[q] + part) * k + tid] = s.top[tid];
@@ -502,74 +569,62 @@ struct Ms {
 };
 
 // ---- plan: cut every query into doc-range parts of bounded cost and order the parts longest first ------------------
-// cost of a query = its postings without the longest list (the list that is usually only probed). One CTA.
+// cost of a query = its postings without the longest list (the list that is usually only probed). Two grid-wide passes:
+// costs + histogram of log2(cost per part), then the scatter into the bucket-ordered item list.
 constexpr int kMsMaxParts = 16;
-__global__ void __launch_bounds__(1024) ms_plan_kernel(const int32_t *__restrict__ q_tokens, const int64_t *__restrict__ q_ptr,
-                                                       int32_t n_queries, const int64_t *__restrict__ indptr, int32_t n_vocab,
-                                                       long long part_cost, int max_parts, unsigned long long *items,
-                                                       unsigned int *part_base, unsigned long long *qtot, unsigned int *gtheta,
-                                                       unsigned int *qstat, unsigned char *scratch /* 2 bytes per query */,
-                                                       Ctrl *ctrl) {
-    __shared__ unsigned int hist[64], base[64];
-    __shared__ long long ws[33];
-    __shared__ long long carry_s;
-    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    unsigned char *bucket = scratch, *parts = scratch + n_queries;
-    const int n_round = ((n_queries + blockDim.x - 1) / blockDim.x) * blockDim.x;
-    for (int q = threadIdx.x; q < n_round; q += blockDim.x) {
-        int P = 0;
-        if (q < n_queries) {
-            unsigned long long tot = 0, mx = 0;
-            const long long T = q_ptr[q + 1] - q_ptr[q];
-            for (int64_t i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
-                const int tok = q_tokens[i];
-                if ((unsigned)tok < (unsigned)n_vocab) {
-                    const unsigned long long df = (unsigned long long)(indptr[tok + 1] - indptr[tok]);
-                    tot += df;
-                    mx = df > mx ? df : mx;
-                }
-            }
-            const unsigned long long cost = (T > 1 && tot > mx) ? tot - mx : tot;
-            P = 1;
-            if (T >= 1 && T <= kMaxTok && cost > (unsigned long long)part_cost) {
-                const unsigned long long want = (cost + part_cost - 1) / part_cost;
-                P = want > (unsigned long long)max_parts ? max_parts : (int)want;
-            }
-            const unsigned long long per = cost / P;
-            const int bk = per ? 64 - __clzll((long long)per) : 0;
-            bucket[q] = (unsigned char)bk;
-            parts[q] = (unsigned char)P;
-            qtot[q] = tot;
-            gtheta[q] = 0u;
-            qstat[q] = 0u;
-            atomicAdd(&hist[bk], (unsigned)P);
+__global__ void __launch_bounds__(256) ms_plan_cost_kernel(const int32_t *__restrict__ q_tokens, const int64_t *__restrict__ q_ptr,
+                                                           int32_t n_queries, const int64_t *__restrict__ indptr, int32_t n_vocab,
+                                                           long long part_cost, int max_parts, unsigned int *part_base,
+                                                           unsigned long long *qtot, unsigned int *gtheta, unsigned int *qstat,
+                                                           unsigned char *scratch /* 2 bytes per query */, Ctrl *ctrl) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    unsigned long long tot = 0, mx = 0;
+    const long long T = q_ptr[q + 1] - q_ptr[q];
+    for (int64_t i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
+        const int tok = q_tokens[i];
+        if ((unsigned)tok < (unsigned)n_vocab) {
+            const unsigned long long df = (unsigned long long)(indptr[tok + 1] - indptr[tok]);
+            tot += df;
+            mx = df > mx ? df : mx;
         }
-        long long total;
-        const long long ex = block_exclusive_scan((long long)P, ws, &total);
-        if (q < n_queries) part_base[q] = (unsigned int)(carry_s + ex);
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += total;
-        __syncthreads();
     }
+    const unsigned long long cost = (T > 1 && tot > mx) ? tot - mx : tot;
+    int P = 1;
+    if (T >= 1 && T <= kMaxTok && cost > (unsigned long long)part_cost) {
+        const unsigned long long want = (cost + part_cost - 1) / part_cost;
+        P = want > (unsigned long long)max_parts ? max_parts : (int)want;
+    }
+    const unsigned long long per = cost / P;
+    const int bk = per ? 64 - __clzll((long long)per) : 0;
+    scratch[q] = (unsigned char)bk;
+    scratch[n_queries + q] = (unsigned char)P;
+    qtot[q] = tot;
+    gtheta[q] = 0u;
+    qstat[q] = 0u;
+    atomicAdd(&ctrl->ms_hist[bk], (unsigned)P);
+    part_base[q] = atomicAdd(&ctrl->ms_rows, (unsigned)P);  // rows of the query's parts in `partial` (any order)
+}
+
+__global__ void __launch_bounds__(256) ms_plan_scatter_kernel(int32_t n_queries, const unsigned char *__restrict__ scratch,
+                                                              unsigned long long *items, Ctrl *ctrl) {
+    __shared__ unsigned int base[64];
     if (threadIdx.x == 0) {
         unsigned int acc = 0;
-        for (int bk = 63; bk >= 0; --bk) { base[bk] = acc; acc += hist[bk]; }
-        ctrl->ms_items = acc;
-        part_base[n_queries] = (unsigned int)carry_s;
+        for (int bk = 63; bk >= 0; --bk) { base[bk] = acc; acc += ctrl->ms_hist[bk]; }
+        if (blockIdx.x == 0) ctrl->ms_items = acc;
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < n_queries; q += blockDim.x) {
-        const unsigned P = parts[q];
-        const unsigned at = atomicAdd(&base[bucket[q]], P);
-        for (unsigned j = 0; j < P; ++j)
-            items[at + j] = (unsigned long long)(unsigned)q | ((unsigned long long)j << 32) | ((unsigned long long)P << 40);
-    }
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    const unsigned bk = scratch[q], P = scratch[n_queries + q];
+    const unsigned at = base[bk] + atomicAdd(&ctrl->ms_cursor[bk], P);
+    for (unsigned j = 0; j < P; ++j)
+        items[at + j] = (unsigned long long)(unsigned)q | ((unsigned long long)j << 32) | ((unsigned long long)P << 40);
 }
 
 // ---- merge: one warp per query unites the parts' top lists, checks the result and writes the row -------------------
-__global__ void __launch_bounds__(256) ms_merge_kernel(const unsigned long long *__restrict__ items_unused, const unsigned int *__restrict__ part_base,
+__global__ void __launch_bounds__(256) ms_merge_kernel(const unsigned char *__restrict__ nparts, const unsigned int *__restrict__ part_base,
                                                        const unsigned long long *__restrict__ partial, const unsigned int *__restrict__ qstat,
                                                        const unsigned long long *__restrict__ qtot, RetrieveArgs a, int32_t doc_base,
                                                        Ctrl *ctrl, unsigned int *fb_list) {
@@ -580,7 +635,7 @@ __global__ void __launch_bounds__(256) ms_merge_kernel(const unsigned long long 
     bool route = qstat[q] != 0u;
     unsigned long long t = 0ull;
     if (!route) {
-        const unsigned r0 = part_base[q], r1 = part_base[q + 1];
+        const unsigned r0 = part_base[q], r1 = r0 + nparts[q];
         for (unsigned r = r0; r < r1; ++r) {
             const unsigned long long b = (lane < k) ? partial[(size_t)r * k + lane] : 0ull;  // sorted descending
             t = umax64(t, shfl64(b, 31 - lane));
@@ -606,11 +661,50 @@ __global__ void __launch_bounds__(256) ms_merge_kernel(const unsigned long long 
     if (lane == 0) atomicAdd(&ctrl->posting_count, qtot[q]);
 }
 
-template <int NT, int UNROLL, int R, int MINB>
+template <int NT, int UNROLL, int R, int MINB, bool BIG>
 __global__ void __launch_bounds__(NT, MINB) retrieve_ms_kernel(const __grid_constant__ MsParams p) {
-    __shared__ typename Ms<NT, UNROLL, R>::Sh sh;
-    Ms<NT, UNROLL, R> m(p, sh);
+    __shared__ typename Ms<NT, UNROLL, R, BIG>::Sh sh;
+    extern __shared__ __align__(16) unsigned long long ms_dyn[];
+    Ms<NT, UNROLL, R, BIG> m(p, sh, ms_dyn);
     m.run();
+}
+
+// k > 32: one CTA per query, the parts' rows are rank-merged one after the other in shared memory
+__global__ void __launch_bounds__(128) ms_merge_big_kernel(const unsigned char *__restrict__ nparts, const unsigned int *__restrict__ part_base, const unsigned long long *__restrict__ partial,
+                                                           const unsigned int *__restrict__ qstat, const unsigned long long *__restrict__ qtot,
+                                                           RetrieveArgs a, int32_t doc_base, int kcap, Ctrl *ctrl, unsigned int *fb_list) {
+    extern __shared__ __align__(16) unsigned long long mg[];  // [2][kcap] top lists + [kcap] one row
+    const int q = blockIdx.x, tid = threadIdx.x, k = a.k;
+    bool route = qstat[q] != 0u;
+    unsigned long long *cur = mg, *nxt = mg + kcap, *row = mg + 2 * kcap;
+    if (!route) {
+        for (int e = tid; e < kcap; e += 128) cur[e] = 0ull;
+        const unsigned r0 = part_base[q], r1 = r0 + nparts[q];
+        for (unsigned r = r0; r < r1; ++r) {
+            __syncthreads();
+            for (int e = tid; e < k; e += 128) row[e] = partial[(size_t)r * k + e];
+            __syncthreads();
+            int cnt = 0;  // rows are sorted, zeros (empty) at the end: first zero by binary search
+            { int lo = 0, hi = k; while (lo < hi) { const int mid = (lo + hi) >> 1; if (row[mid] != 0ull) lo = mid + 1; else hi = mid; } cnt = lo; }
+            rank_merge(cur, nxt, kcap, row, cnt, tid, 128);
+            unsigned long long *t = cur; cur = nxt; nxt = t;
+        }
+        __syncthreads();
+        const unsigned long long kth = cur[k - 1];
+        route = !(kth != 0ull && cand_score(kth) > 0.0f);
+    }
+    if (route) {
+        if (tid == 0) fb_list[atomicAdd(&ctrl->fb_count, 1u)] = (unsigned)q;
+        return;
+    }
+    for (int e = tid; e < k; e += 128) {
+        const unsigned long long t = cur[e];
+        float sc = cand_score(t);
+        if (a.shift != nullptr) sc = __fadd_rn(sc, a.shift[q]);
+        a.out_ids[(size_t)q * k + e] = cand_doc(t) + doc_base;
+        a.out_scores[(size_t)q * k + e] = sc;
+    }
+    if (tid == 0) atomicAdd(&ctrl->posting_count, qtot[q]);
 }
 
 static int env_int_ms(const char *name, int dflt) {
@@ -629,6 +723,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
         if (a.k == 1) p.colkth = ix->d_colmax;
         else if (a.k <= 10) p.colkth = ix->d_colkth;
         else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
+        else if (a.k <= 1000) p.colkth = ix->d_colkth + 2 * (size_t)ix->n_vocab;
     }
     p.order = nullptr;
     const bool use_bt = env_int_ms("BM25CU_MS_BTAB", 1) && ix->d_btab != nullptr;
@@ -644,7 +739,9 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.a = a;
     p.ctrl = d_ctrl;
     p.fb_list = d_fb_list;
-    p.route_all = (!ix->nonneg) || a.k > 32 || (a.mask != nullptr && env_int_ms("BM25CU_MASK_FAST", 1) == 0) ||
+    const int kmax = env_int_ms("BM25CU_MS_KMAX", 1024);  // larger k: the streaming kernel
+    p.kcap = next_pow2(a.k < 32 ? 32 : a.k);
+    p.route_all = (!ix->nonneg) || a.k > kmax || a.k > 1024 || (a.mask != nullptr && env_int_ms("BM25CU_MASK_FAST", 1) == 0) ||
                   env_int_ms("BM25CU_FORCE_GENERAL", 0);
     p.max_first = (long long)env_int_ms("BM25CU_MS_MAXFIRST", 0x7fffffff);
     p.budget = (unsigned int)env_int_ms("BM25CU_MS_BUDGET", 1 << 20);
@@ -652,6 +749,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     int max_parts = env_int_ms("BM25CU_MS_MAXPARTS", kMsMaxParts);
     if (max_parts < 1) max_parts = 1;
     if (max_parts > 255) max_parts = 255;
+    if (max_parts > 8192 / p.kcap && !getenv("BM25CU_MS_MAXPARTS")) max_parts = 8192 / p.kcap > 1 ? 8192 / p.kcap : 1;  // rows of k keys per part
     const long long part_cost = (long long)env_int_ms("BM25CU_MS_PARTCOST", 65536);
     const size_t nq = (size_t)a.n_queries;
     int rc;
@@ -665,8 +763,11 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     unsigned long long *qtot = ix->d_ms_q.as<unsigned long long>();
     unsigned int *gtheta = reinterpret_cast<unsigned int *>(qtot + nq);
     unsigned int *qstat = gtheta + nq;
-    ms_plan_kernel<<<1, 1024, 0, ix->stream>>>(a.q_tokens, a.q_ptr, a.n_queries, ix->d_indptr, ix->n_vocab, part_cost, max_parts,
-                                               items, part_base, qtot, gtheta, qstat, scratch, d_ctrl);
+    const unsigned qblocks = (unsigned)((nq + 255) / 256);
+    ms_plan_cost_kernel<<<qblocks, 256, 0, ix->stream>>>(a.q_tokens, a.q_ptr, a.n_queries, ix->d_indptr, ix->n_vocab, part_cost, max_parts,
+                                                         part_base, qtot, gtheta, qstat, scratch, d_ctrl);
+    BM25CU_CHECK(cudaGetLastError());
+    ms_plan_scatter_kernel<<<qblocks, 256, 0, ix->stream>>>(a.n_queries, scratch, items, d_ctrl);
     BM25CU_CHECK(cudaGetLastError());
     p.items = items;
     p.part_base = part_base;
@@ -675,12 +776,18 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.partial = ix->d_ms_partial.as<unsigned long long>();
     const int per_sm = env_int_ms("BM25CU_MS_CTAS", 9);  // 55 registers: nine 128-thread CTAs are resident per SM
     const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 9);
-    retrieve_ms_kernel<128, 4, 4, 8><<<grid, 128, 0, ix->stream>>>(p);
+    const size_t dyn = p.kcap > 32 ? (size_t)2 * p.kcap * 8 : 0;
+    if (p.kcap <= 32) retrieve_ms_kernel<128, 4, 4, 8, false><<<grid, 128, 0, ix->stream>>>(p);
+    else retrieve_ms_kernel<128, 4, 4, 8, true><<<grid, 128, dyn, ix->stream>>>(p);
     BM25CU_CHECK(cudaGetLastError());
-    ms_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ix->stream>>>(items, part_base, p.partial, qstat, qtot, a, ix->doc_base,
-                                                                              d_ctrl, d_fb_list);
+    if (p.kcap <= 32)
+        ms_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ix->stream>>>(scratch + nq, part_base, p.partial, qstat, qtot, a, ix->doc_base,
+                                                                                  d_ctrl, d_fb_list);
+    else
+        ms_merge_big_kernel<<<(unsigned)nq, 128, (size_t)3 * p.kcap * 8, ix->stream>>>(scratch + nq, part_base, p.partial, qstat, qtot, a, ix->doc_base,
+                                                                                      p.kcap, d_ctrl, d_fb_list);
     BM25CU_CHECK(cudaGetLastError());
-    if (launches) *launches += 3;
+    if (launches) *launches += 4;
     return BM25CU_OK;
 }
 

@@ -22,6 +22,7 @@ import time
 t0 = time.time()
 ix = DeviceIndex.upload_device(data.data_ptr(), indices.data_ptr(), indptr.data_ptr(), data.numel(), n_vocab, n_docs)
 print('upload_device s', round(time.time() - t0, 3))
+t0 = time.time(); ix2 = DeviceIndex.upload_device(data.data_ptr(), indices.data_ptr(), indptr.data_ptr(), data.numel(), n_vocab, n_docs); print('second upload_device s', round(time.time() - t0, 3)); ix2.close(); del ix2
 def run(ms):
     os.environ['BM25CU_MS'] = ms
     oi = torch.empty((n_queries, k), dtype=torch.int32, device=dev); os_ = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
