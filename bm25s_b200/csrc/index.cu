@@ -2,6 +2,7 @@
 // doc-range shard extraction on the device, download, free.
 #include "common.cuh"
 #include "select.cuh"
+#include <chrono>
 #include <cstdlib>
 
 #include "scan.cuh"
@@ -313,9 +314,19 @@ int finalize_index(bm25cu_index *ix) {
         BM25CU_CHECK(cudaGetLastError());
     }
     {
+        const char *tv = getenv("BM25CU_TIME");
+        const bool timing = tv && *tv && atoi(tv) != 0;  // debugging: host time of the lookup-structure builds
+        auto now = [&]() { if (timing) cudaStreamSynchronize(ix->stream); return std::chrono::steady_clock::now(); };
+        auto t0 = now();
         int rc_bt = build_bucket_tables(ix);
         if (rc_bt) return rc_bt;
+        auto t1 = now();
         if ((rc_bt = build_presence_bitmaps(ix))) return rc_bt;
+        auto t2 = now();
+        if (timing)
+            fprintf(stderr, "[bm25cu] bucket tables %.1f ms, presence bitmaps %.1f ms, %.1f MB\n",
+                    std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                    std::chrono::duration<double, std::milli>(t2 - t1).count(), ix->aux_bytes / 1e6);
     }
     unsigned int flag = 0;
     BM25CU_CHECK(cudaMemcpyAsync(&flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost, ix->stream));

@@ -116,7 +116,7 @@ struct Ms {
     struct Sh {
         long long beg[16];
         unsigned long long top[32];
-        unsigned long long pend[NT * R + 32];
+        unsigned long long pend[BIG ? 1024 : NT * R + 32];  // BIG: sorted in place, padded to a power of two
         unsigned long long theta_key;
         int df[16];
         float ub[16];
@@ -346,16 +346,15 @@ struct Ms {
             for (int r = 0; r < R; ++r)
                 if (alive[r]) finish(i, d[r], v[r], found[r], vals + r * 16, tk, th);
             if (tid == 0) refresh(gq);
-            __syncthreads();
-            if (!BIG) {
-                if (s.pend_cnt > 0) {
-                    if (tid == 0) MS_CNT(7, 1);
-                    if (tid < 32) merge_pending(tid, k, gq);
-                    __syncthreads();
-                }
-            } else if (s.pend_cnt >= 32u || (s.pend_cnt > 0 && base + NT * R >= n)) {  // the shared-memory merge is dearer: batch it
+            // the decision to merge is taken by the barrier itself (a thread that pushed sees its own push): a plain read
+            // behind the barrier could race with the reset at the end of the merge
+            const unsigned pc = s.pend_cnt;
+            const bool want = BIG ? (pc >= 32u || (pc > 0u && base + NT * R >= n))  // the shared-memory merge is dearer: batch it
+                                  : pc > 0u;
+            if (__syncthreads_or(want)) {
                 if (tid == 0) MS_CNT(7, 1);
-                merge_pending_big(tid, k, gq);
+                if (BIG) merge_pending_big(tid, k, gq);
+                else if (tid < 32) merge_pending(tid, k, gq);
                 __syncthreads();
             }
         }
@@ -740,7 +739,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.ctrl = d_ctrl;
     p.fb_list = d_fb_list;
     const int kmax = env_int_ms("BM25CU_MS_KMAX", 1024);  // larger k: the streaming kernel
-    p.kcap = next_pow2(a.k < 32 ? 32 : a.k);
+    p.kcap = (a.k > kmax || a.k > 1024) ? 32 : next_pow2(a.k < 32 ? 32 : a.k);  // larger k: every query is handed on, no top list needed
     p.route_all = (!ix->nonneg) || a.k > kmax || a.k > 1024 || (a.mask != nullptr && env_int_ms("BM25CU_MASK_FAST", 1) == 0) ||
                   env_int_ms("BM25CU_FORCE_GENERAL", 0);
     p.max_first = (long long)env_int_ms("BM25CU_MS_MAXFIRST", 0x7fffffff);
@@ -750,7 +749,9 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     if (max_parts < 1) max_parts = 1;
     if (max_parts > 255) max_parts = 255;
     if (max_parts > 8192 / p.kcap && !getenv("BM25CU_MS_MAXPARTS")) max_parts = 8192 / p.kcap > 1 ? 8192 / p.kcap : 1;  // rows of k keys per part
-    const long long part_cost = (long long)env_int_ms("BM25CU_MS_PARTCOST", 65536);
+    // smaller batches are cut finer so that every CTA still gets several parts (NQ shape, 3 452 queries: 1.34 -> 1.20 ms)
+    const int per_sm_cfg = env_int_ms("BM25CU_MS_CTAS", 9);
+    const long long part_cost = (long long)env_int_ms("BM25CU_MS_PARTCOST", a.n_queries >= 3 * ix->sm_count * per_sm_cfg ? 65536 : 32768);
     const size_t nq = (size_t)a.n_queries;
     int rc;
     if ((rc = ix->d_ms_items.reserve(nq * (size_t)max_parts * 8))) return rc;

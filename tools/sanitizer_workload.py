@@ -7,10 +7,16 @@ corp = synth.make_corpus(n_docs, 30, n_vocab, seed=7)
 data, indices, indptr, nonocc = O.build_index(corp.to_lists(), n_vocab, "lucene")
 qs = synth.make_queries(48, n_vocab, seed=8)
 dev = DeviceIndex.upload(data, indices, indptr, n_docs)
+import os
 for k in (10, 300):
-    ids, sc = dev.retrieve(qs.tokens, qs.ptr, k)
-    rid, rsc = CO.retrieve(data, indices, indptr, n_docs, qs.tokens, qs.ptr, k)
-    assert np.array_equal(sc, rsc), k
+    # default (list-at-a-time kernel, parts), many small parts, hand-over to the streaming kernel, streaming kernel alone
+    for env in ({}, {"BM25CU_MS_PARTCOST": "512", "BM25CU_MS_MAXPARTS": "64"}, {"BM25CU_MS_BUDGET": "64"}, {"BM25CU_MS": "0"}):
+        os.environ.update(env)
+        ids, sc = dev.retrieve(qs.tokens, qs.ptr, k)
+        for kk in env:
+            os.environ.pop(kk)
+        rid, rsc = CO.retrieve(data, indices, indptr, n_docs, qs.tokens, qs.ptr, k)
+        assert np.array_equal(sc, rsc), (k, env)
 b = DeviceIndex.build(corp.tokens, corp.ptr, n_vocab, "lucene", "lucene", 1.5, 0.75, 0.5)
 d2 = b.download()
 assert np.array_equal(d2[0], data)
