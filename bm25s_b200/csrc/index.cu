@@ -131,18 +131,18 @@ __global__ void __launch_bounds__(256) column_kth_kernel(const float *__restrict
 
 // ---- bucket tables of the long columns (lookups of retrieve_ms.cu) ------------------------------------------------
 // A column with df >= kBtabMinDf gets a table over buckets of 2^sh consecutive document ids, sh chosen so that a bucket
-// holds 16..32 postings on average: tab[b] = number of postings with doc < b * 2^sh, (n_docs >> sh) + 2 entries.
+// holds 8..16 postings on average: tab[b] = number of postings with doc < b * 2^sh, (n_docs >> sh) + 2 entries.
 // A lookup of document d reads tab[d >> sh], tab[(d >> sh) + 1] and searches that slice of `indices` (one or two
 // sectors) instead of log2(df) scattered ones. Size: at most nnz / 4 bytes. Derived at upload, not part of the index.
 constexpr int kBtabMinDf = 16;
 
-__device__ __forceinline__ int btab_shift_of(long long df, int n_docs) {
+__device__ __forceinline__ int btab_shift_of(long long df, int n_docs, int avg) {
     int sh = 0;
-    while (sh < 31 && ((df << sh) < 16ll * (long long)n_docs)) ++sh;  // smallest sh with df * 2^sh >= 16 * n_docs
+    while (sh < 31 && ((df << sh) < (long long)avg * (long long)n_docs)) ++sh;  // smallest sh with df * 2^sh >= avg * n_docs
     return sh;
 }
 
-__global__ void btab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_vocab, int32_t n_docs, long long *sizes,
+__global__ void btab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_vocab, int32_t n_docs, int avg, long long *sizes,
                                  unsigned char *shifts) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_vocab) return;
@@ -150,7 +150,7 @@ __global__ void btab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_v
     long long sz = 0;
     int sh = 0;
     if (df >= kBtabMinDf) {
-        sh = btab_shift_of(df, n_docs);
+        sh = btab_shift_of(df, n_docs, avg);
         sz = (long long)(n_docs >> sh) + 2;
     }
     sizes[t] = sz;
@@ -195,7 +195,10 @@ static int build_bucket_tables(bm25cu_index *ix) {
     BM25CU_CHECK(cudaMalloc(&d_tmp, scan_tmp_elems(V) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_btab_off, (size_t)(V + 1) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_btab_sh, (size_t)V));
-    btab_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, d_sizes, ix->d_btab_sh);
+    const char *av = getenv("BM25CU_BTAB_AVG");
+    int avg = (av && *av) ? atoi(av) : 8;  // a bucket holds avg .. 2 avg postings on average
+    if (avg < 1) avg = 1;
+    btab_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, avg, d_sizes, ix->d_btab_sh);
     BM25CU_CHECK(cudaGetLastError());
     BM25CU_CHECK(exclusive_scan<long long>(d_sizes, V, ix->d_btab_off, d_tmp, ix->stream));
     long long total = 0;
