@@ -357,3 +357,56 @@ def test_doc_range_shards_merge_to_unsharded():
     np.testing.assert_array_equal(data, g[f"{key(m)}_data"][sel])
     np.testing.assert_array_equal(no, nonocc)
     full.close()
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_full_size_two_algorithms_agree(k):
+    """BASELINE.json's NQ shape at full size (2.68 M documents, 207 M postings, 3 452 queries): the oracle cannot score
+    this in seconds, so the check rests on size-independent properties - the list-at-a-time kernel (retrieve_ms.cu) and
+    the streaming kernel (retrieve_fast.cu), two independent algorithms, return identical ids and identical score bits;
+    rows are sorted by (score desc, id asc) without duplicates; and for sampled queries the dense score vector of the
+    general kernel (get_scores path) confirms every returned score and that nothing outside the row beats its tail."""
+    import torch
+
+    from bm25s_b200 import DeviceIndex, synth
+
+    n_docs, avg_len, n_vocab, n_queries = synth.SHAPES["nq"]
+    dev_t = torch.device("cuda")
+    tokens, ptr = synth.make_corpus_torch(n_docs, avg_len, n_vocab, seed=0, device=dev_t)
+    data, indices, indptr, _ = synth.csc_from_tokens_torch(tokens, ptr, n_vocab)
+    del tokens, ptr
+    qt, qp = synth.make_queries_torch(n_queries, n_vocab, seed=1, device=dev_t)
+    ix = DeviceIndex.upload_device(data.data_ptr(), indices.data_ptr(), indptr.data_ptr(), data.numel(), n_vocab, n_docs)
+
+    def run(ms):
+        old = os.environ.get("BM25CU_MS")
+        os.environ["BM25CU_MS"] = ms
+        try:
+            oi = torch.empty((n_queries, k), dtype=torch.int32, device=dev_t)
+            osc = torch.empty((n_queries, k), dtype=torch.float32, device=dev_t)
+            st = ix.retrieve_device(qt.data_ptr(), qp.data_ptr(), n_queries, int(qp[-1]), k, oi.data_ptr(), osc.data_ptr())
+            return oi.cpu().numpy(), osc.cpu().numpy(), st
+        finally:
+            if old is None:
+                os.environ.pop("BM25CU_MS", None)
+            else:
+                os.environ["BM25CU_MS"] = old
+
+    ids1, sc1, st1 = run("1")
+    ids0, sc0, st0 = run("0")
+    assert st1["n_general"] == 0 and st0["n_general"] == 0
+    assert st1["ms_kernel_ms"] > 0 and st0["ms_kernel_ms"] == 0  # the two runs really took different kernels
+    np.testing.assert_array_equal(sc1.view(np.int32), sc0.view(np.int32))
+    np.testing.assert_array_equal(ids1, ids0)
+    assert np.all(sc1[:, :-1] >= sc1[:, 1:])
+    tie = sc1[:, :-1] == sc1[:, 1:]
+    assert np.all(ids1[:, :-1][tie] < ids1[:, 1:][tie])  # ties by ascending id
+    qt_h, qp_h = qt.cpu().numpy(), qp.cpu().numpy()
+    for q in range(0, n_queries, 431):
+        dense = ix.scores_dense(qt_h[qp_h[q]:qp_h[q + 1]])
+        assert len(set(ids1[q].tolist())) == k
+        np.testing.assert_array_equal(dense[ids1[q]], sc1[q])
+        rest = dense.copy()
+        rest[ids1[q]] = -np.inf
+        assert rest.max() <= sc1[q, -1]
+    ix.close()
