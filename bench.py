@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--n-docs", type=int, default=0, help="override the shape's document count (debugging)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the shards' top-k rows meet - p2p: stores into peer memory over NVLink fused with the merge "
+                         "(bm25cu_exchange_*), nccl: all_gather + merge kernel")
     ap.add_argument("--local-shards", action="store_true",
                     help="N > 1: every rank generates only its own doc range (seed 1000 + rank); implied by --shape 100m")
     return ap.parse_args()
@@ -269,14 +272,45 @@ def main():
     shift_d = None if shift_h is None else torch.from_numpy(shift_h).to(device)
     out_ids = torch.empty((n_queries, k), dtype=torch.int32, device=device)
     out_sc = torch.empty((n_queries, k), dtype=torch.float32, device=device)
+    exch = None
     if world > 1:
-        g_ids = torch.empty((world, n_queries, k), dtype=torch.int32, device=device)
-        g_sc = torch.empty((world, n_queries, k), dtype=torch.float32, device=device)
         m_ids = torch.empty((n_queries, k), dtype=torch.int32, device=device)
         m_sc = torch.empty((n_queries, k), dtype=torch.float32, device=device)
+        if args.exchange == "p2p":
+            def all_gather_bytes(b):
+                mine = torch.tensor(list(b), dtype=torch.uint8, device=device)
+                allh = torch.empty((world, len(b)), dtype=torch.uint8, device=device)
+                dist.all_gather_into_tensor(allh.view(-1), mine)
+                return [bytes(allh[r].cpu().tolist()) for r in range(world)]
+
+            try:
+                exch = _lib.PeerExchange(local_rank, rank, world, n_queries * k, all_gather_bytes)
+                ok = 1
+            except Exception as e:  # CUDA IPC unavailable between these processes: say so and take the NCCL exchange
+                print(f"[bench] peer-memory exchange unavailable ({e}); using all_gather + merge", file=sys.stderr)
+                exch, ok = None, 0
+            okt = torch.tensor([ok], device=device)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)  # every rank takes the same path; also the barrier before the first push
+            torch.cuda.synchronize()
+            if int(okt.item()) == 0:
+                exch = None
+                args.exchange = "nccl"
+        if exch is None:
+            g_ids = torch.empty((world, n_queries, k), dtype=torch.int32, device=device)
+            g_sc = torch.empty((world, n_queries, k), dtype=torch.float32, device=device)
     stats_acc = []
 
-    def step_device(qt, qp):
+    def step_device(qt, qp, collect=True):
+        if world > 1 and exch is not None:
+            # scoring kernels, push into the peers' memory, merge: one chain on the stream, no host round trip in between
+            dev.retrieve_device_enqueue(qt.data_ptr(), qp.data_ptr(), n_queries, n_q_tokens, k, out_ids.data_ptr(), out_sc.data_ptr(),
+                                        shift_ptr=None if shift_d is None else shift_d.data_ptr())
+            exch.merge(out_ids.data_ptr(), out_sc.data_ptr(), n_queries, k, m_ids.data_ptr(), m_sc.data_ptr(), stream.cuda_stream)
+            if not collect:
+                return None
+            st = dev.collect(n_queries, n_q_tokens, k)
+            st["launches"] += 2
+            return st
         st = dev.retrieve_device(qt.data_ptr(), qp.data_ptr(), n_queries, n_q_tokens, k, out_ids.data_ptr(), out_sc.data_ptr(),
                                  shift_ptr=None if shift_d is None else shift_d.data_ptr())
         launches = st["launches"]
@@ -299,15 +333,35 @@ def main():
     # kernel-path arm: queries resident in HBM
     for _ in range(args.warmup):
         step_device(q_tok, q_ptr)
+    exchange_check = None
+    if exch is not None:
+        # untimed self-check: the peer-memory exchange returns exactly what all_gather + bm25cu_topk_merge_device return
+        exch.check(stream.cuda_stream)
+        g_ids = torch.empty((world, n_queries, k), dtype=torch.int32, device=device)
+        g_sc = torch.empty((world, n_queries, k), dtype=torch.float32, device=device)
+        c_ids, c_sc = torch.empty_like(m_ids), torch.empty_like(m_sc)
+        dist.all_gather_into_tensor(g_ids.view(-1), out_ids.view(-1))
+        dist.all_gather_into_tensor(g_sc.view(-1), out_sc.view(-1))
+        _lib.check(_lib.lib().bm25cu_topk_merge_device(
+            _lib.C.c_void_p(g_ids.data_ptr()), _lib.C.c_void_p(g_sc.data_ptr()), world, n_queries, k,
+            _lib.C.c_void_p(c_ids.data_ptr()), _lib.C.c_void_p(c_sc.data_ptr()), local_rank, _lib.C.c_void_p(stream.cuda_stream)))
+        torch.cuda.synchronize()
+        exchange_check = bool(torch.equal(c_ids, m_ids) and torch.equal(c_sc.view(torch.int32), m_sc.view(torch.int32)))
+        del g_ids, g_sc, c_ids, c_sc
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        stats_acc.append(step_device(q_tok, q_ptr))
+    for it in range(args.steps):
+        # p2p exchange: the steps are enqueued back to back, the last one collects the stats (one synchronisation)
+        st_i = step_device(q_tok, q_ptr, collect=(exch is None or it == args.steps - 1))
+        if st_i is not None:
+            stats_acc.append(st_i)
     ev1.record()
     barrier()
+    if exch is not None:
+        exch.check(stream.cuda_stream)  # raises if a peer's rows never arrived
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], device=device, dtype=torch.float64)
@@ -374,10 +428,12 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "bm25cu_retrieve (host numpy arrays in/out)" if world == 1 else "pinned H2D + retrieve_device + all_gather + merge + D2H"},
-            "gpu_launches": int(sum(s["launches"] for s in stats_acc)),
+                    "api": "bm25cu_retrieve (host numpy arrays in/out)" if world == 1 else ("pinned H2D + retrieve_device + peer-memory exchange fused with the merge + D2H" if args.exchange == "p2p" else "pinned H2D + retrieve_device + all_gather + merge + D2H")},
+            "gpu_launches": int(sum(s["launches"] for s in stats_acc)) if exch is None else int(stats_acc[-1]["launches"]) * args.steps,
             "roofline": roofline,
             "n_general": int(stats_acc[-1]["n_general"]), "nnz_local": int(nnz), "index_build_s": round(build_s, 3)}
+    if world > 1:
+        line["exchange"] = {"kind": args.exchange, "same_as_all_gather_merge": exchange_check}
 
     if rank == 0 and world == 1:
         # the user-facing call, Python lists in -> numpy arrays out (BM25.retrieve of the mirror class,

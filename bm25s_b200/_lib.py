@@ -19,8 +19,10 @@ EXPORTED_SYMBOLS = [
     "bm25cu_last_error", "bm25cu_version", "bm25cu_device_count", "bm25cu_index_upload", "bm25cu_index_upload_device", "bm25cu_index_set_stream", "bm25cu_build_begin",
     "bm25cu_build_df_device", "bm25cu_build_df_get", "bm25cu_build_df_set", "bm25cu_build_finish",
     "bm25cu_build_free", "bm25cu_index_build", "bm25cu_index_sizes", "bm25cu_index_download", "bm25cu_retrieve",
-    "bm25cu_retrieve_device", "bm25cu_scores_dense", "bm25cu_topk_dense", "bm25cu_topk_merge",
+    "bm25cu_retrieve_device", "bm25cu_retrieve_device_enqueue", "bm25cu_retrieve_collect", "bm25cu_scores_dense", "bm25cu_topk_dense", "bm25cu_topk_merge",
     "bm25cu_topk_merge_device", "bm25cu_index_free",
+    "bm25cu_exchange_create", "bm25cu_exchange_handle_size", "bm25cu_exchange_handle", "bm25cu_exchange_connect",
+    "bm25cu_exchange_merge", "bm25cu_exchange_check", "bm25cu_exchange_free",
 ]
 
 
@@ -191,6 +193,23 @@ class DeviceIndex:
                                                C.c_void_p(out_scores_ptr), C.byref(st)))
         return st.as_dict()
 
+    def retrieve_device_enqueue(self, q_tokens_ptr, q_ptr_ptr, n_queries, n_query_tokens, k, out_ids_ptr, out_scores_ptr,
+                                shift_ptr=None, mask_ptr=None):
+        """retrieve_device without the synchronisation: the kernels are enqueued on the handle's stream; `collect` later."""
+        with self._lock:
+            check(lib().bm25cu_retrieve_device_enqueue(self._h, C.c_void_p(q_tokens_ptr), C.c_void_p(q_ptr_ptr),
+                                                       C.c_int32(n_queries), C.c_int64(n_query_tokens), C.c_int32(k),
+                                                       C.c_void_p(shift_ptr), C.c_void_p(mask_ptr), C.c_void_p(out_ids_ptr),
+                                                       C.c_void_p(out_scores_ptr)))
+
+    def collect(self, n_queries, n_query_tokens, k):
+        """Synchronise the handle's stream, raise the errors of the enqueued call, return its stats."""
+        st = Stats()
+        with self._lock:
+            check(lib().bm25cu_retrieve_collect(self._h, C.c_int32(n_queries), C.c_int64(n_query_tokens), C.c_int32(k),
+                                                C.byref(st)))
+        return st.as_dict()
+
     def scores_dense(self, q_tokens, shift=None, mask=None):
         q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
         mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.float64)
@@ -284,3 +303,38 @@ def topk_merge(ids: np.ndarray, scores: np.ndarray, device: int = 0):
     check(lib().bm25cu_topk_merge(ptr(ids, C.c_int32), ptr(scores, C.c_float), C.c_int32(n_parts), C.c_int32(nq),
                                   C.c_int32(k), ptr(oi, C.c_int32), ptr(os_, C.c_float), C.c_int32(device)))
     return oi, os_
+
+
+class PeerExchange:
+    """Exchange + merge of the shards' top-k rows over NVLink peer memory (include/bm25cu.h, bm25cu_exchange_*): every
+    rank stores its rows into every peer's buffer and merges its own copy - two kernels on the caller's stream instead of
+    an all_gather and a merge kernel. `all_gather_bytes(b: bytes) -> list[bytes]` exchanges the IPC handles (rank order)."""
+
+    def __init__(self, device: int, rank: int, world: int, max_elems: int, all_gather_bytes, barrier=None):
+        self._h = C.c_void_p()
+        self.rank, self.world, self.device = rank, world, device
+        check(lib().bm25cu_exchange_create(C.c_int32(device), C.c_int32(rank), C.c_int32(world), C.c_int64(max_elems),
+                                           C.byref(self._h)))
+        hs = lib().bm25cu_exchange_handle_size()
+        mine = C.create_string_buffer(hs)
+        check(lib().bm25cu_exchange_handle(self._h, mine))
+        handles = all_gather_bytes(mine.raw)
+        assert len(handles) == world and all(len(h) == hs for h in handles)
+        blob = C.create_string_buffer(b"".join(handles), hs * world)
+        check(lib().bm25cu_exchange_connect(self._h, blob))
+        if barrier is not None:
+            barrier()  # nobody may push before everybody has opened the buffers (the caller's job if no barrier is given)
+
+    def merge(self, ids_ptr, scores_ptr, n_queries, k, out_ids_ptr, out_scores_ptr, stream=0):
+        """All pointers are raw device addresses; enqueues two kernels on `stream` (a raw cudaStream_t), no sync."""
+        check(lib().bm25cu_exchange_merge(self._h, C.c_void_p(ids_ptr), C.c_void_p(scores_ptr), C.c_int32(n_queries),
+                                          C.c_int32(k), C.c_void_p(out_ids_ptr), C.c_void_p(out_scores_ptr),
+                                          C.c_void_p(stream)))
+
+    def check(self, stream=0):
+        check(lib().bm25cu_exchange_check(self._h, C.c_void_p(stream)))
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            lib().bm25cu_exchange_free(self._h)
+            self._h = None

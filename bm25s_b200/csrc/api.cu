@@ -99,6 +99,7 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
     BM25CU_CHECK(cudaEventRecord(ix->ev[2], ix->stream));
     if ((rc = launch_retrieve_general(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches))) return rc;
     BM25CU_CHECK(cudaEventRecord(ix->ev[3], ix->stream));
+    ix->last_launches = launches;
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         stats->launches = launches;
@@ -259,6 +260,41 @@ int bm25cu_retrieve_device(bm25cu_index *ix, const int32_t *q_tokens, const int6
     int rc;
     if ((rc = run_retrieve_on_device(ix, a, stats, n_query_tokens, false))) return rc;
     return finish_stats(ix, a, stats, n_query_tokens, false);
+}
+
+int bm25cu_retrieve_device_enqueue(bm25cu_index *ix, const int32_t *q_tokens, const int64_t *q_ptr, int32_t n_queries,
+                                   int64_t n_query_tokens, int32_t k, const float *shift_per_query,
+                                   const double *weight_mask, int32_t *out_ids, float *out_scores) {
+    BM25CU_REQUIRE(ix != nullptr, "bm25cu_retrieve_device_enqueue: null handle");
+    BM25CU_REQUIRE(n_queries >= 0 && k >= 0, "bm25cu_retrieve_device_enqueue: negative n_queries or k");
+    if (n_queries == 0 || k == 0) return BM25CU_OK;
+    BM25CU_REQUIRE(q_ptr && out_ids && out_scores, "bm25cu_retrieve_device_enqueue: null pointer");
+    BM25CU_CHECK(cudaSetDevice(ix->device));
+    RetrieveArgs a;
+    a.q_tokens = q_tokens;
+    a.q_ptr = q_ptr;
+    a.n_queries = n_queries;
+    a.k = k;
+    a.shift = shift_per_query;
+    a.mask = weight_mask;
+    a.out_ids = out_ids;
+    a.out_scores = out_scores;
+    return run_retrieve_on_device(ix, a, nullptr, n_query_tokens, false);
+}
+
+int bm25cu_retrieve_collect(bm25cu_index *ix, int32_t n_queries, int64_t n_query_tokens, int32_t k, bm25cu_stats *stats) {
+    BM25CU_REQUIRE(ix != nullptr, "bm25cu_retrieve_collect: null handle");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n_queries <= 0 || k <= 0) return BM25CU_OK;
+    BM25CU_REQUIRE(ix->d_ctrl.p != nullptr, "bm25cu_retrieve_collect: no retrieve call has been enqueued");
+    BM25CU_CHECK(cudaSetDevice(ix->device));
+    RetrieveArgs a{};
+    a.n_queries = n_queries;
+    a.k = k;
+    const int launches = ix->last_launches;
+    int rc = finish_stats(ix, a, stats, n_query_tokens, false);
+    if (rc == BM25CU_OK && stats) stats->launches = launches;
+    return rc;
 }
 
 int bm25cu_scores_dense(bm25cu_index *ix, const int32_t *q_tokens, int32_t n_tokens, int32_t has_shift, float shift,

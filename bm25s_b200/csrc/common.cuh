@@ -113,6 +113,7 @@ struct bm25cu_index {
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,
         d_spill, d_order, d_theta, d_fb_list, d_ms_items, d_ms_rows, d_ms_q, d_ms_partial;
+    int last_launches = 0;         // kernels launched by the last retrieve call
     bool ms_ran = false;           // the last call ran retrieve_ms.cu (ev[5] is recorded behind it)
     bool order_valid = false;      // d_order holds the pull order of the current batch
     bm25cu::PinBuf h_in, h_out;

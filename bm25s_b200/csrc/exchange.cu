@@ -1,0 +1,245 @@
+// Exchange of the shards' top-k rows over NVLink peer memory (doc-range sharding), fused with the merge.
+//
+// The reference is single-process: there is nothing to replace; this is the one exchange step the doc-range sharding of
+// DESIGN.md section 5 adds. Instead of an NCCL all_gather followed by a merge kernel, every rank
+//   1. PUSHES its local rows (ids int32[Q][k], scores float32[Q][k]) straight into slot [rank] of a buffer that lives in
+//      the memory of EVERY peer (plain stores through pointers opened with cudaIpcOpenMemHandle: NVLink / NVSwitch peer
+//      writes), fences them system-wide and raises a per-source flag on every peer to the call's epoch;
+//   2. runs the MERGE kernel on its own copy: a CTA per query waits until the world flags reached the epoch, then sorts
+//      the world * k pairs in shared memory (same order as bm25cu_topk_merge: score descending, id ascending).
+// Two kernels on the caller's stream, no host round trip, no collective library call. Buffers are double-buffered by
+// epoch parity: a rank can start pushing call e + 2 only after its merge of call e + 1 ended, which needs every peer's
+// push of e + 1, which every peer enqueues behind its own merge of call e - so nobody overwrites rows still being read.
+#include "common.cuh"
+#include "select.cuh"
+
+namespace {
+
+constexpr int kMaxWorld = 16;
+constexpr size_t kFlagBytes = 512;  // unsigned int flags[2][kMaxWorld], padded
+
+struct ExchangeView {
+    int32_t *ids[2];   // [world][cap]
+    float *scores[2];  // [world][cap]
+    unsigned int *flags;  // [2][kMaxWorld]
+};
+
+__host__ __device__ inline ExchangeView view_of(void *base, int world, long long cap) {
+    ExchangeView v;
+    char *p = static_cast<char *>(base);
+    v.flags = reinterpret_cast<unsigned int *>(p);
+    p += kFlagBytes;
+    for (int b = 0; b < 2; ++b) {
+        v.ids[b] = reinterpret_cast<int32_t *>(p);
+        p += (size_t)world * cap * 4;
+        v.scores[b] = reinterpret_cast<float *>(p);
+        p += (size_t)world * cap * 4;
+    }
+    return v;
+}
+
+struct PeerPtrs {
+    void *p[kMaxWorld];
+};
+
+__global__ void __launch_bounds__(256) exchange_push_kernel(const int32_t *__restrict__ ids, const float *__restrict__ scores,
+                                                            long long n, PeerPtrs peers, int rank, int world, long long cap,
+                                                            int parity, unsigned int epoch, unsigned int *done_counter) {
+    for (int pr = 0; pr < world; ++pr) {
+        const ExchangeView v = view_of(peers.p[pr], world, cap);
+        int32_t *di = v.ids[parity] + (size_t)rank * cap;
+        float *ds = v.scores[parity] + (size_t)rank * cap;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            di[i] = ids[i];
+            ds[i] = scores[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_counter, 1u);
+        if (prev == gridDim.x - 1) {  // last block: every block's rows are fenced - raise the flags
+            *done_counter = 0u;
+            __threadfence_system();
+            for (int pr = 0; pr < world; ++pr) {
+                const ExchangeView v = view_of(peers.p[pr], world, cap);
+                volatile unsigned int *f = v.flags + parity * kMaxWorld + rank;
+                *f = epoch;
+            }
+            __threadfence_system();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) exchange_merge_kernel(void *local, int world, long long cap, int parity, unsigned int epoch,
+                                                             int n_queries, int k, int P, int32_t *out_ids, float *out_scores,
+                                                             unsigned int *err) {
+    extern __shared__ unsigned char smem_raw[];
+    uint32_t *key = reinterpret_cast<uint32_t *>(smem_raw);
+    int32_t *id = reinterpret_cast<int32_t *>(key + P);
+    const ExchangeView v = view_of(local, world, cap);
+    if (threadIdx.x < world) {
+        volatile unsigned int *f = v.flags + parity * kMaxWorld + threadIdx.x;
+        unsigned long long t0 = 0, now = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(*f - epoch) < 0) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 10000000000ull) { atomicOr(err, 1u); break; }  // 10 s: a peer never pushed
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int q = blockIdx.x;
+    const int total = world * k;
+    const int32_t *ids = v.ids[parity];
+    const float *scores = v.scores[parity];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint32_t kk = 0u;
+        int32_t ii = 0x7fffffff;
+        if (i < total) {
+            const int p = i / k, j = i - p * k;
+            const size_t src = (size_t)p * cap + (size_t)q * k + j;
+            const int32_t d = __ldcv(ids + src);  // written by a peer: never from a stale cache line
+            if (d >= 0) { kk = bm25cu::f32_key(__ldcv(scores + src)); ii = d; }
+        }
+        key[i] = kk;
+        id[i] = ii;
+    }
+    bm25cu::block_bitonic_sort_desc<uint32_t, int32_t>(key, id, P);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const uint32_t kk = key[j];
+        int32_t d = id[j];
+        float s;
+        if (d == 0x7fffffff) { d = -1; s = __int_as_float(0xff800000); }
+        else { const uint32_t u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk; s = __uint_as_float(u); }
+        out_ids[(size_t)q * k + j] = d;
+        out_scores[(size_t)q * k + j] = s;
+    }
+}
+
+}  // namespace
+
+struct bm25cu_exchange {
+    int device = 0, rank = 0, world = 1;
+    long long cap = 0;  // elements per rank slot (>= n_queries * k of every call)
+    void *local = nullptr;
+    void *peer[kMaxWorld] = {nullptr};
+    bool connected = false;
+    unsigned int epoch = 0;
+    unsigned int *d_counter = nullptr;  // [0] block counter of the push kernel, [1] error bits of the merge kernel
+    size_t bytes = 0;
+};
+
+using namespace bm25cu;
+
+extern "C" {
+
+int bm25cu_exchange_create(int32_t device, int32_t rank, int32_t world, int64_t max_elems, bm25cu_exchange **out) {
+    BM25CU_REQUIRE(out != nullptr, "bm25cu_exchange_create: null out");
+    BM25CU_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bm25cu_exchange_create: bad rank / world (at most 16 ranks)");
+    BM25CU_REQUIRE(max_elems > 0, "bm25cu_exchange_create: max_elems must be positive");
+    BM25CU_CHECK(cudaSetDevice(device));
+    bm25cu_exchange *x = new bm25cu_exchange();
+    x->device = device;
+    x->rank = rank;
+    x->world = world;
+    x->cap = (max_elems + 3) & ~3ll;
+    x->bytes = kFlagBytes + (size_t)2 * 2 * world * x->cap * 4;
+    cudaError_t e = cudaMalloc(&x->local, x->bytes);
+    if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_counter, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(x->d_counter, 0, 2 * sizeof(unsigned int));
+    if (e != cudaSuccess) {
+        set_error(std::string("bm25cu_exchange_create: ") + cudaGetErrorString(e));
+        cudaFree(x->local);
+        cudaFree(x->d_counter);
+        delete x;
+        return e == cudaErrorMemoryAllocation ? BM25CU_ENOMEM : BM25CU_ECUDA;
+    }
+    x->peer[rank] = x->local;
+    *out = x;
+    return BM25CU_OK;
+}
+
+int bm25cu_exchange_handle_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int bm25cu_exchange_handle(bm25cu_exchange *x, void *handle_out) {
+    BM25CU_REQUIRE(x && handle_out, "bm25cu_exchange_handle: null pointer");
+    BM25CU_CHECK(cudaSetDevice(x->device));
+    cudaIpcMemHandle_t h;
+    BM25CU_CHECK(cudaIpcGetMemHandle(&h, x->local));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return BM25CU_OK;
+}
+
+int bm25cu_exchange_connect(bm25cu_exchange *x, const void *handles) {
+    BM25CU_REQUIRE(x && handles, "bm25cu_exchange_connect: null pointer");
+    BM25CU_CHECK(cudaSetDevice(x->device));
+    const char *hp = static_cast<const char *>(handles);
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, hp + (size_t)r * sizeof(h), sizeof(h));
+        BM25CU_CHECK(cudaIpcOpenMemHandle(&x->peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    x->connected = true;
+    return BM25CU_OK;
+}
+
+int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const float *scores_device, int32_t n_queries,
+                          int32_t k, int32_t *out_ids_device, float *out_scores_device, void *stream) {
+    BM25CU_REQUIRE(x != nullptr, "bm25cu_exchange_merge: null handle");
+    BM25CU_REQUIRE(x->connected || x->world == 1, "bm25cu_exchange_merge: bm25cu_exchange_connect has not been called");
+    BM25CU_REQUIRE(n_queries >= 0 && k >= 0, "bm25cu_exchange_merge: negative size");
+    if (n_queries == 0 || k == 0) return BM25CU_OK;
+    const long long n = (long long)n_queries * k;
+    BM25CU_REQUIRE(n <= x->cap, "bm25cu_exchange_merge: n_queries * k exceeds the capacity given to bm25cu_exchange_create");
+    BM25CU_REQUIRE(ids_device && scores_device && out_ids_device && out_scores_device, "bm25cu_exchange_merge: null pointer");
+    BM25CU_CHECK(cudaSetDevice(x->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned int epoch = ++x->epoch;
+    const int parity = (int)(epoch & 1u);
+    PeerPtrs pp;
+    for (int r = 0; r < kMaxWorld; ++r) pp.p[r] = r < x->world ? x->peer[r] : nullptr;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 592) grid = 592;
+    exchange_push_kernel<<<grid, 256, 0, st>>>(ids_device, scores_device, n, pp, x->rank, x->world, x->cap, parity, epoch, x->d_counter);
+    BM25CU_CHECK(cudaGetLastError());
+    const int P = next_pow2(x->world * k);
+    const size_t smem = (size_t)P * 8;
+    BM25CU_REQUIRE(smem <= 200 * 1024, "bm25cu_exchange_merge: world * k too large for one CTA (max 25600 pairs)");
+    BM25CU_CHECK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    exchange_merge_kernel<<<n_queries, 256, smem, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k, P, out_ids_device,
+                                                       out_scores_device, x->d_counter + 1);
+    BM25CU_CHECK(cudaGetLastError());
+    return BM25CU_OK;
+}
+
+/* error bits of the merge kernels so far (1: a peer's rows did not arrive within 10 s); synchronises the stream */
+int bm25cu_exchange_check(bm25cu_exchange *x, void *stream) {
+    BM25CU_REQUIRE(x != nullptr, "bm25cu_exchange_check: null handle");
+    BM25CU_CHECK(cudaSetDevice(x->device));
+    unsigned int err = 0;
+    BM25CU_CHECK(cudaMemcpyAsync(&err, x->d_counter + 1, sizeof(err), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    BM25CU_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (err) {
+        set_error("bm25cu_exchange: a peer's rows did not arrive within 10 s");
+        return BM25CU_ECUDA;
+    }
+    return BM25CU_OK;
+}
+
+int bm25cu_exchange_free(bm25cu_exchange *x) {
+    if (!x) return BM25CU_OK;
+    cudaSetDevice(x->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < x->world; ++r)
+        if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    cudaFree(x->local);
+    cudaFree(x->d_counter);
+    delete x;
+    return BM25CU_OK;
+}
+
+}  // extern "C"

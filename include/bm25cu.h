@@ -127,6 +127,15 @@ int bm25cu_retrieve_device(bm25cu_index *ix, const int32_t *q_tokens, const int6
                            int64_t n_query_tokens, int32_t k, const float *shift_per_query,
                            const double *weight_mask, int32_t *out_ids, float *out_scores, bm25cu_stats *stats);
 
+/* bm25cu_retrieve_device in two halves, for callers that chain more device work behind the scoring kernels (the
+ * exchange below): _enqueue launches the kernels on the handle's stream and returns at once, nothing is synchronised;
+ * _collect synchronises the stream, reports the errors of the enqueued call (token id out of range, internal) and
+ * fills `stats` (may be NULL) - call it before the outputs are read on the host. */
+int bm25cu_retrieve_device_enqueue(bm25cu_index *ix, const int32_t *q_tokens, const int64_t *q_ptr, int32_t n_queries,
+                                   int64_t n_query_tokens, int32_t k, const float *shift_per_query,
+                                   const double *weight_mask, int32_t *out_ids, float *out_scores);
+int bm25cu_retrieve_collect(bm25cu_index *ix, int32_t n_queries, int64_t n_query_tokens, int32_t k, bm25cu_stats *stats);
+
 /* Dense scores of one query: replaces BM25.get_scores_from_ids (bm25s/__init__.py:581-620). out: float32[n_docs_local] */
 int bm25cu_scores_dense(bm25cu_index *ix, const int32_t *q_tokens, int32_t n_tokens, int32_t has_shift, float shift,
                         const double *weight_mask, float *out);
@@ -143,6 +152,27 @@ int bm25cu_topk_merge(const int32_t *ids, const float *scores, int32_t n_parts, 
                       int32_t *out_ids, float *out_scores, int32_t device);
 int bm25cu_topk_merge_device(const int32_t *ids, const float *scores, int32_t n_parts, int32_t n_queries, int32_t k,
                              int32_t *out_ids, float *out_scores, int32_t device, void *stream);
+
+/*
+ * Exchange of the shards' top-k rows over NVLink peer memory, fused with the merge (doc-range sharding over the GPUs of
+ * one box, one process per GPU). No reference equivalent (the reference is single-process); it stands where an
+ * all_gather + bm25cu_topk_merge_device would. Protocol: every rank creates an exchange for at most max_elems =
+ * n_queries * k result elements, publishes its bm25cu_exchange_handle (bm25cu_exchange_handle_size() opaque bytes,
+ * a CUDA IPC handle) to the others by any means (torch.distributed, MPI, a file), connects with the world handles
+ * (rank-major, its own slot is ignored) and, after a barrier, calls bm25cu_exchange_merge once per batch on every rank:
+ * the local rows (device pointers, as written by bm25cu_retrieve_device) are stored into every peer's buffer, and the
+ * merged rows [n_queries][k] (score descending, id ascending) appear in out_* on every rank. Two kernels on `stream`,
+ * nothing is synchronised; bm25cu_exchange_check synchronises and reports a peer that never delivered.
+ */
+typedef struct bm25cu_exchange bm25cu_exchange;
+int bm25cu_exchange_create(int32_t device, int32_t rank, int32_t world, int64_t max_elems, bm25cu_exchange **out);
+int bm25cu_exchange_handle_size(void);
+int bm25cu_exchange_handle(bm25cu_exchange *x, void *handle_out);
+int bm25cu_exchange_connect(bm25cu_exchange *x, const void *handles);
+int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const float *scores_device, int32_t n_queries,
+                          int32_t k, int32_t *out_ids_device, float *out_scores_device, void *stream);
+int bm25cu_exchange_check(bm25cu_exchange *x, void *stream);
+int bm25cu_exchange_free(bm25cu_exchange *x);
 
 int bm25cu_index_free(bm25cu_index *ix);
 
