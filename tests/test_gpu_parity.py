@@ -410,3 +410,30 @@ def test_full_size_two_algorithms_agree(k):
         rest[ids1[q]] = -np.inf
         assert rest.max() <= sc1[q, -1]
     ix.close()
+
+
+def test_peer_exchange_single_rank_epochs():
+    """bm25cu_exchange_* with world = 1 (all a one-GPU box can run; bench.py checks N > 1 against all_gather + merge): the
+    push + merge kernels return the rows in (score desc, id asc) order, call after call (both buffer parities), and
+    rows with fewer than k valid entries keep their -1 / -inf tail."""
+    import torch
+
+    from bm25s_b200 import _lib
+
+    dev_t = torch.device("cuda")
+    Q, k = 37, 10
+    g = torch.Generator(device="cpu").manual_seed(5)
+    ex = _lib.PeerExchange(0, 0, 1, Q * k, lambda b: [b])
+    for call in range(5):
+        sc = torch.rand((Q, k), generator=g).round(decimals=1)  # ties on purpose
+        ids = torch.stack([torch.randperm(1000, generator=g)[:k] for _ in range(Q)]).to(torch.int32)
+        ids[3, 6:] = -1
+        sc[3, 6:] = float("-inf")
+        d_ids, d_sc = ids.to(dev_t), sc.to(dev_t)
+        o_ids, o_sc = torch.empty_like(d_ids), torch.empty_like(d_sc)
+        ex.merge(d_ids.data_ptr(), d_sc.data_ptr(), Q, k, o_ids.data_ptr(), o_sc.data_ptr(), 0)
+        ex.check(0)
+        ref_i, ref_s = _lib.topk_merge(ids.numpy()[None], sc.numpy()[None], device=0)
+        np.testing.assert_array_equal(o_ids.cpu().numpy(), ref_i, err_msg=f"call {call}")
+        np.testing.assert_array_equal(o_sc.cpu().numpy(), ref_s, err_msg=f"call {call}")
+    ex.close()
