@@ -8,17 +8,21 @@
 //     (rare tokens first). List i is STREAMED - only its float32 scores, 16 bytes per load - and a posting (d, v) is a
 //     survivor when  mult*v + sum of ub over the lists after i  can still reach theta, the k-th best key so far.
 //     Documents that contain a token of an earlier list were scored when that list was streamed.
-//   * a survivor is looked up in the other lists (binary search, or the per-column bucket table of index.cu), the
-//     bound is re-checked after every lookup, and a document that passes is summed in QUERY-TOKEN ORDER, duplicates
+//   * a survivor is looked up in the other lists (one load of the column's presence bitmap; a "maybe" is searched in the
+//     slice its bucket table names - both built by index.cu at upload), the bound is re-checked after every lookup, and a document that passes is summed in QUERY-TOKEN ORDER, duplicates
 //     added again at their position - the reference's float32 order, so scores are bit-identical to numpy's.
 //   * when the upper bounds of the lists not yet streamed sum below theta, no unseen document can enter the top-k and
 //     the query ends: the long lists of frequent tokens are usually never streamed, only probed.
 //   * candidates are 64-bit keys (score bits, ~doc): order = score descending, doc ascending, as in retrieve_fast.cu;
 //     pruning keeps everything whose bound is >= theta's score, acceptance is key > theta, so the result does not
-//     depend on the order in which documents are met. For k <= 32 the top list lives in one warp's registers.
+//     depend on the order in which documents are met. For k <= 32 the top list lives in one warp's registers, for
+//     k <= 1024 in shared memory.
+//   * a query is cut into doc-range PARTS of bounded cost (ms_plan_*_kernel); CTAs pull parts longest first, the parts of
+//     a query publish their k-th best score to each other, ms_merge_kernel unites their top lists and writes the row.
 //
-// Queries this kernel does not take (empty, > 15 tokens, k > 32, fewer than k positive matches, cost rule) are
-// appended to `fb_list` and served by retrieve_fast_kernel in the same call.
+// Queries this kernel does not take (empty, > 15 tokens, k > 1024, fewer than k documents with a positive score, masks
+// outside [0, 1], a part over its survivor budget) are appended to `fb_list` and served by retrieve_fast_kernel in the
+// same call.
 #include "fast_common.cuh"
 
 namespace bm25cu {
@@ -29,7 +33,6 @@ struct MsParams {
     const int64_t *indptr;
     const float *colmax;
     const float *colkth;        // start value table valid for this k (nullptr: none)
-    const unsigned int *order;  // pull order (longest first) or nullptr
     const unsigned int *btab;   // bucket tables (index.cu) or nullptr: binary search
     const long long *btab_off;  // per column: offset into btab, -1 = no table
     const unsigned char *btab_sh;
@@ -41,7 +44,6 @@ struct MsParams {
     Ctrl *ctrl;
     unsigned int *fb_list;
     int route_all;
-    long long max_first;  // cost rule: hand the query on when its first (rarest) list is longer than this
     unsigned int budget;  // survivors a work item may look up before its query is handed on (safety valve)
     // work items: a query is cut into P doc-range parts served by different CTAs (MsPlan below)
     const unsigned long long *items;  // q | part << 32 | P << 40, longest first
@@ -485,7 +487,7 @@ struct Ms {
             s.top[lane] = 0ull;
             if (BIG) for (int e = lane; e < kcap; e += 32) big[e] = 0ull;
             __syncwarp();
-            if (tot == 0 || (long long)s.df[0] > p.max_first) route = true;
+            if (tot == 0) route = true;
             // this part's slice of every list: documents [part * n_docs / P, (part + 1) * n_docs / P)
             if (!route && lane < U) {
                 int lo = 0, hi = s.df[lane];
@@ -724,7 +726,6 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
         else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
         else if (a.k <= 1000) p.colkth = ix->d_colkth + 2 * (size_t)ix->n_vocab;
     }
-    p.order = nullptr;
     const bool use_bt = env_int_ms("BM25CU_MS_BTAB", 1) && ix->d_btab != nullptr;
     p.btab = use_bt ? ix->d_btab : nullptr;
     p.btab_off = ix->d_btab_off;
@@ -742,7 +743,6 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.kcap = (a.k > kmax || a.k > 1024) ? 32 : next_pow2(a.k < 32 ? 32 : a.k);  // larger k: every query is handed on, no top list needed
     p.route_all = (!ix->nonneg) || a.k > kmax || a.k > 1024 || (a.mask != nullptr && env_int_ms("BM25CU_MASK_FAST", 1) == 0) ||
                   env_int_ms("BM25CU_FORCE_GENERAL", 0);
-    p.max_first = (long long)env_int_ms("BM25CU_MS_MAXFIRST", 0x7fffffff);
     p.budget = (unsigned int)env_int_ms("BM25CU_MS_BUDGET", 1 << 20);
     // plan: parts of at most `part_cost` postings (BM25CU_MS_PARTCOST), at most BM25CU_MS_MAXPARTS per query
     int max_parts = env_int_ms("BM25CU_MS_MAXPARTS", kMsMaxParts);

@@ -437,3 +437,37 @@ def test_peer_exchange_single_rank_epochs():
         np.testing.assert_array_equal(o_ids.cpu().numpy(), ref_i, err_msg=f"call {call}")
         np.testing.assert_array_equal(o_sc.cpu().numpy(), ref_s, err_msg=f"call {call}")
     ex.close()
+
+
+def test_list_at_a_time_kernel_edge_cases():
+    """retrieve_ms.cu against the C oracle on the shapes that steer its control flow: tokens whose column is empty, a
+    query of one repeated token, 15 tokens (the most it takes), 16 (handed on to the general kernel), k on both sides of
+    the register / shared-memory top list (32 | 33) and of its limit (1024 | 1025), k larger than the number of documents
+    with a positive score (padding rule: handed on), every BM25 variant with its shift."""
+    from bm25s_b200 import DeviceIndex, synth
+
+    n_docs, n_vocab = 30_000, 3_000
+    corp = synth.make_corpus(n_docs, 25, n_vocab, seed=31)
+    docs = corp.to_lists()
+    empty = sorted(set(range(n_vocab)) - set(t for d in docs for t in d))[:2]  # tokens without a posting, if any
+    rare = [n_vocab - 1 - i for i in range(20)]
+    queries = [[0], [5, 5, 5], [0, 1], [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14], list(range(16)),
+               rare[:4], rare[:2] + [0, 1], [2, 700, 2, 1500, 2], [n_vocab - 1], [10, 20, 30, 40]]
+    if empty:
+        queries += [[empty[0]], [empty[0], 3], empty + [7, 7]]
+    queries += synth.make_queries(40, n_vocab, seed=32).to_lists()
+    ptr = np.zeros(len(queries) + 1, np.int64)
+    np.cumsum([len(q) for q in queries], out=ptr[1:])
+    flat = np.array([t for q in queries for t in q], np.int32)
+    for method in ("lucene", "bm25l", "robertson"):
+        data, indices, indptr, nonocc = O.build_index(docs, n_vocab, method)
+        sh = None if nonocc is None else np.array([O.query_shift(nonocc, q) for q in queries], np.float32)
+        dev = DeviceIndex.upload(data, indices, indptr, n_docs, nonocc=nonocc)
+        for k in (1, 2, 31, 32, 33, 64, 1000, 1024, 1025, 5000):
+            ids, sc, st = dev.retrieve(flat, ptr, k, shift=sh, with_stats=True)
+            if k <= 2048 and data.min() >= 0:
+                assert st["n_general"] == 1, (method, k)  # the 16-token query; larger k or negative scores: every query
+            rid, rsc = CO.retrieve(data, indices, indptr, n_docs, flat, ptr, k, shift=sh)
+            dense_fn = lambda qi: CO.scores_dense(data, indices, indptr, n_docs, queries[qi], shift=None if sh is None else sh[qi])  # noqa: E731
+            check_topk_rows(ids, sc, rid, rsc, dense_fn if k <= 64 else None, what=f"{method} k={k}")
+        dev.close()
