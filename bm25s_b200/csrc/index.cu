@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "select.cuh"
 #include <chrono>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 
 #include "scan.cuh"
@@ -395,6 +397,79 @@ int bm25cu_device_count(int32_t *n) {
     return BM25CU_OK;
 }
 
+// ---- host -> device copies through a pinned staging ring -----------------------------------------
+// cudaMemcpy from pageable memory (numpy arrays, .npy memmaps) is staged by the driver on one thread at 8-10 GB/s.
+// Here kStageThreads host threads each own two pinned buffers and a stream: a thread copies its chunks into pinned
+// memory (page faults of a memmap are taken in parallel, too) while the DMA engine drains the other buffer.
+// The ring (kStageThreads * 2 * kStageChunk bytes of pinned memory) is allocated once per process and device.
+constexpr int kStageThreads = 4;
+constexpr size_t kStageChunk = (size_t)8 << 20;
+
+struct StageRing {
+    int device = -1;
+    char *buf[kStageThreads][2] = {};
+    cudaStream_t st[kStageThreads] = {};
+    cudaEvent_t ev[kStageThreads][2] = {};
+    bool ok = false;
+};
+static std::mutex g_stage_mu;
+static StageRing g_stage;
+
+static bool stage_ring_ready(int device) {
+    if (g_stage.ok && g_stage.device == device) return true;
+    if (g_stage.ok) return false;  // one ring per process: uploads to another device take the plain path
+    for (int t = 0; t < kStageThreads; ++t) {
+        if (cudaStreamCreateWithFlags(&g_stage.st[t], cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (int b = 0; b < 2; ++b) {
+            if (cudaHostAlloc((void **)&g_stage.buf[t][b], kStageChunk, cudaHostAllocDefault) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&g_stage.ev[t][b], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+    }
+    g_stage.device = device;
+    g_stage.ok = true;
+    return true;
+}
+
+// Synchronous: returns when `bytes` bytes of host memory at `src` are in device memory at `dst`.
+static cudaError_t staged_h2d(void *dst, const void *src, size_t bytes, int device) {
+    const char *ev = getenv("BM25CU_STAGED_UPLOAD");
+    const bool want = !(ev && *ev && atoi(ev) == 0) && bytes >= 4 * kStageChunk;
+    std::unique_lock<std::mutex> lock(g_stage_mu);
+    if (!want || !stage_ring_ready(device)) {
+        lock.unlock();
+        cudaGetLastError();
+        return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    }
+    const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+    cudaError_t errs[kStageThreads];
+    std::thread th[kStageThreads];
+    for (int t = 0; t < kStageThreads; ++t) {
+        errs[t] = cudaSuccess;
+        th[t] = std::thread([&, t]() {
+            cudaError_t e = cudaSetDevice(device);
+            int used[2] = {0, 0};
+            for (size_t c = t, i = 0; c < n_chunks && e == cudaSuccess; c += kStageThreads, ++i) {
+                const int b = (int)(i & 1);
+                const size_t off = c * kStageChunk, n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+                if (used[b]) e = cudaEventSynchronize(g_stage.ev[t][b]);  // the DMA out of this buffer has finished
+                if (e != cudaSuccess) break;
+                std::memcpy(g_stage.buf[t][b], static_cast<const char *>(src) + off, n);
+                e = cudaMemcpyAsync(static_cast<char *>(dst) + off, g_stage.buf[t][b], n, cudaMemcpyHostToDevice, g_stage.st[t]);
+                if (e == cudaSuccess) e = cudaEventRecord(g_stage.ev[t][b], g_stage.st[t]);
+                used[b] = 1;
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g_stage.st[t]);
+            errs[t] = e;
+        });
+    }
+    cudaError_t res = cudaSuccess;
+    for (int t = 0; t < kStageThreads; ++t) {
+        th[t].join();
+        if (errs[t] != cudaSuccess) res = errs[t];
+    }
+    return res;
+}
+
 static int upload_impl(const float *data, const int32_t *indices, const int64_t *indptr, int64_t nnz,
                        int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
                        int32_t doc_hi, bool src_on_device, bm25cu_index **out) {
@@ -433,9 +508,12 @@ static int upload_impl(const float *data, const int32_t *indices, const int64_t 
         ix->nnz = nnz;
         if ((rc = alloc_postings(ix, nnz))) return fail(rc);
         TRY(cudaMemcpyAsync(ix->d_indptr, indptr, (size_t)(n_vocab + 1) * sizeof(int64_t), cudaMemcpyDefault, ix->stream));
-        if (nnz) {
+        if (nnz && src_on_device) {
             TRY(cudaMemcpyAsync(ix->d_data, data, (size_t)nnz * sizeof(float), cudaMemcpyDefault, ix->stream));
             TRY(cudaMemcpyAsync(ix->d_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault, ix->stream));
+        } else if (nnz) {
+            TRY(staged_h2d(ix->d_data, data, (size_t)nnz * sizeof(float), device));
+            TRY(staged_h2d(ix->d_indices, indices, (size_t)nnz * sizeof(int32_t), device));
         }
     } else {
         // stage the full matrix on the device, cut out the doc range there
@@ -460,8 +538,13 @@ static int upload_impl(const float *data, const int32_t *indices, const int64_t 
         TRY2(cudaMalloc(&d_tmp, scan_tmp_elems(n_vocab) * sizeof(long long)));
         TRY2(cudaMemcpyAsync(f_indptr, indptr, (size_t)(n_vocab + 1) * sizeof(int64_t), cudaMemcpyDefault, ix->stream));
         if (nnz) {
-            TRY2(cudaMemcpyAsync(f_data, data, (size_t)nnz * sizeof(float), cudaMemcpyDefault, ix->stream));
-            TRY2(cudaMemcpyAsync(f_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault, ix->stream));
+            if (src_on_device) {
+                TRY2(cudaMemcpyAsync(f_data, data, (size_t)nnz * sizeof(float), cudaMemcpyDefault, ix->stream));
+                TRY2(cudaMemcpyAsync(f_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault, ix->stream));
+            } else {
+                TRY2(staged_h2d(f_data, data, (size_t)nnz * sizeof(float), device));
+                TRY2(staged_h2d(f_indices, indices, (size_t)nnz * sizeof(int32_t), device));
+            }
         }
         if (n_vocab > 0) {
             shard_bounds_kernel<<<(n_vocab + 255) / 256, 256, 0, ix->stream>>>(f_indices, f_indptr, n_vocab, doc_lo, doc_hi, d_start, d_count);
