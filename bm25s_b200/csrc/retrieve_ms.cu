@@ -52,6 +52,7 @@ struct MsParams {
     unsigned int *qstat;              // per query: 1 = handed on
     unsigned long long *partial;      // [row][k] sorted keys of a part's top list
     int kcap;                         // next_pow2(k), at least 32; > 32: the top list lives in shared memory
+    unsigned int big_merge_at;        // k > 32: pending keys that start a merge in the middle of a probe call (<= 512)
 };
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -351,7 +352,7 @@ struct Ms {
             // the decision to merge is taken by the barrier itself (a thread that pushed sees its own push): a plain read
             // behind the barrier could race with the reset at the end of the merge
             const unsigned pc = s.pend_cnt;
-            const bool want = BIG ? (pc >= 32u || (pc > 0u && base + NT * R >= n))  // the shared-memory merge is dearer: batch it
+            const bool want = BIG ? (pc >= p.big_merge_at || (pc > 0u && base + NT * R >= n))  // the shared-memory merge is dearer: batch it
                                   : pc > 0u;
             if (__syncthreads_or(want)) {
                 if (tid == 0) MS_CNT(7, 1);
@@ -744,6 +745,9 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.route_all = (!ix->nonneg) || a.k > kmax || a.k > 1024 || (a.mask != nullptr && env_int_ms("BM25CU_MASK_FAST", 1) == 0) ||
                   env_int_ms("BM25CU_FORCE_GENERAL", 0);
     p.budget = (unsigned int)env_int_ms("BM25CU_MS_BUDGET", 1 << 20);
+    p.big_merge_at = (unsigned int)env_int_ms("BM25CU_MS_BIGMERGE", 128);
+    if (p.big_merge_at > 512u) p.big_merge_at = 512u;
+    if (p.big_merge_at < 1u) p.big_merge_at = 1u;
     // plan: parts of at most `part_cost` postings (BM25CU_MS_PARTCOST), at most BM25CU_MS_MAXPARTS per query
     int max_parts = env_int_ms("BM25CU_MS_MAXPARTS", kMsMaxParts);
     if (max_parts < 1) max_parts = 1;
