@@ -98,3 +98,58 @@ class ShardedIndex:
         from ._lib import topk_merge
 
         return topk_merge(gi.cpu().numpy(), gs.cpu().numpy(), device=self.device)
+
+    # ---- device-resident path: queries and results stay in HBM, the exchange runs over NVLink peer memory -------------
+    def enable_peer_exchange(self, max_queries: int, k: int):
+        """Set up the peer-memory exchange (bm25cu_exchange_*, csrc/exchange.cu) for batches of up to `max_queries`
+        queries and `k` results. NCCL process group required (the IPC handles travel through one all_gather)."""
+        import torch
+        import torch.distributed as dist
+
+        from ._lib import PeerExchange
+
+        dev_t = torch.device("cuda", self.device)
+        if getattr(self, "_exchange", None) is not None:  # a new size: every rank lets go of the old buffers first
+            torch.cuda.synchronize(dev_t)
+            dist.barrier(group=self.group)
+            self._exchange.close()
+            self._exchange = None
+
+        def all_gather_bytes(b):
+            mine = torch.tensor(list(b), dtype=torch.uint8, device=dev_t)
+            allh = torch.empty((self.world, len(b)), dtype=torch.uint8, device=dev_t)
+            dist.all_gather_into_tensor(allh.view(-1), mine, group=self.group)
+            return [bytes(allh[r].cpu().tolist()) for r in range(self.world)]
+
+        self._exchange = PeerExchange(self.device, self.rank, self.world, max_queries * k, all_gather_bytes)
+        dist.barrier(group=self.group)  # nobody pushes before everybody has opened the buffers
+        torch.cuda.synchronize(dev_t)
+        return self._exchange
+
+    def retrieve_device(self, q_tokens, q_ptr, k, shift=None, stream=None):
+        """torch CUDA tensors in (flat int32 token ids, int64 pointers, optional float32 shifts), merged
+        (ids int32[Q,k], scores float32[Q,k]) CUDA tensors out on every rank. One chain on `stream` (default: torch's
+        current stream): scoring kernels of this shard, stores into the peers' memory, merge. Returns after the
+        chain has been synchronised and the call's errors have been raised."""
+        import torch
+
+        if getattr(self, "_exchange", None) is None and self.world > 1:
+            raise RuntimeError("call enable_peer_exchange(max_queries, k) on every rank first")
+        st = torch.cuda.current_stream() if stream is None else stream
+        if getattr(self, "_stream_handle", None) != st.cuda_stream:
+            self.dev.set_stream(st.cuda_stream)
+            self._stream_handle = st.cuda_stream
+        nq = int(q_ptr.numel()) - 1
+        n_tok = int(q_tokens.numel())
+        ids = torch.empty((nq, k), dtype=torch.int32, device=q_ptr.device)
+        sc = torch.empty((nq, k), dtype=torch.float32, device=q_ptr.device)
+        self.dev.retrieve_device_enqueue(q_tokens.data_ptr(), q_ptr.data_ptr(), nq, n_tok, k, ids.data_ptr(), sc.data_ptr(),
+                                         shift_ptr=None if shift is None else shift.data_ptr())
+        if self.world == 1:
+            self.dev.collect(nq, n_tok, k)
+            return ids, sc
+        m_ids, m_sc = torch.empty_like(ids), torch.empty_like(sc)
+        self._exchange.merge(ids.data_ptr(), sc.data_ptr(), nq, k, m_ids.data_ptr(), m_sc.data_ptr(), st.cuda_stream)
+        self.dev.collect(nq, n_tok, k)
+        self._exchange.check(st.cuda_stream)
+        return m_ids, m_sc
