@@ -471,3 +471,56 @@ def test_list_at_a_time_kernel_edge_cases():
             dense_fn = lambda qi: CO.scores_dense(data, indices, indptr, n_docs, queries[qi], shift=None if sh is None else sh[qi])  # noqa: E731
             check_topk_rows(ids, sc, rid, rsc, dense_fn if k <= 64 else None, what=f"{method} k={k}")
         dev.close()
+
+
+@pytest.mark.parametrize("k", [1, 10, 50, 200])
+def test_tie_heavy_corpus(k):
+    """Every document has the same length and holds a token at most once, so a column carries ONE score value and whole
+    runs of documents tie exactly - at the k-th place, too. The pruning rules keep bounds >= theta and accept keys > theta,
+    so the rows must be the unique (score desc, id asc) top-k whatever the part layout; checked against the C oracle
+    (scores bit-exact, ids as sets above the k-th score, every id verified against the dense scores) and for identical
+    ids across kernels and part layouts."""
+    from bm25s_b200 import DeviceIndex
+
+    rng = np.random.default_rng(51)
+    n_docs, n_vocab, L = 40_000, 600, 12
+    # token t is drawn with probability ~ 1 / (t + 3): a few dense columns, many sparse ones
+    p = 1.0 / (np.arange(n_vocab) + 3.0)
+    p /= p.sum()
+    docs = [rng.choice(n_vocab, size=L, replace=False, p=p).tolist() for _ in range(n_docs)]
+    data, indices, indptr, nonocc = O.build_index(docs, n_vocab, "lucene")
+    assert len(np.unique(data[indptr[0]:indptr[1]])) == 1  # one score per column: ties everywhere
+    queries = [[0], [1, 2], [0, 1, 2], [5, 40, 300], [599], [2, 2, 7], [10, 11, 12, 13, 14, 15], [0, 599], [3, 250]]
+    queries += [rng.choice(n_vocab, size=int(rng.integers(1, 6)), p=p).tolist() for _ in range(40)]
+    ptr = np.zeros(len(queries) + 1, np.int64)
+    np.cumsum([len(q) for q in queries], out=ptr[1:])
+    flat = np.array([t for q in queries for t in q], np.int32)
+    dev = DeviceIndex.upload(data, indices, indptr, n_docs)
+    ids, sc = dev.retrieve(flat, ptr, k)
+    rid, rsc = CO.retrieve(data, indices, indptr, n_docs, flat, ptr, k)
+    dense_fn = lambda qi: CO.scores_dense(data, indices, indptr, n_docs, queries[qi])  # noqa: E731
+    check_topk_rows(ids, sc, rid, rsc, dense_fn, what=f"ties k={k}")
+    # the deterministic tie rule: within a run of equal scores the ids ascend, and nothing with a smaller id and the same
+    # score as the row's tail was left out
+    for q in range(len(queries)):
+        tie = sc[q][:-1] == sc[q][1:]
+        assert np.all(ids[q][:-1][tie] < ids[q][1:][tie]), q
+        dense = dense_fn(q)
+        tail = np.flatnonzero(dense == sc[q][-1])
+        n_tail = int((sc[q] == sc[q][-1]).sum())
+        assert set(ids[q][sc[q] == sc[q][-1]].tolist()) == set(tail[:n_tail].tolist()), q
+    for env in ({"BM25CU_MS": "0"}, {"BM25CU_MS_MAXPARTS": "1"}, {"BM25CU_MS_PARTCOST": "256", "BM25CU_MS_MAXPARTS": "64"},
+                {"BM25CU_SEED_KTH": "0"}, {"BM25CU_MS_PBM": "0", "BM25CU_MS_BTAB": "0"}):
+        old = {kk: os.environ.get(kk) for kk in env}
+        os.environ.update(env)
+        try:
+            ids2, sc2 = dev.retrieve(flat, ptr, k)
+        finally:
+            for kk, v in old.items():
+                if v is None:
+                    os.environ.pop(kk, None)
+                else:
+                    os.environ[kk] = v
+        np.testing.assert_array_equal(sc2, sc, err_msg=str(env))
+        np.testing.assert_array_equal(ids2, ids, err_msg=str(env))
+    dev.close()
