@@ -524,3 +524,21 @@ def test_tie_heavy_corpus(k):
         np.testing.assert_array_equal(sc2, sc, err_msg=str(env))
         np.testing.assert_array_equal(ids2, ids, err_msg=str(env))
     dev.close()
+
+
+def test_sharded_retrieve_with_peer_exchange_two_gpus():
+    """Needs two GPUs (skipped on a one-GPU box): tools/sharded_check.py under torchrun - sharded GPU build, scoring,
+    peer-memory exchange fused with the merge, and the NCCL variant, against the C oracle on the unsharded corpus."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29547", os.path.join(root, "tools", "sharded_check.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "sharded check ok: bm25+ world 2" in res.stdout
