@@ -53,6 +53,8 @@ struct MsParams {
     unsigned long long *partial;      // [row][k] sorted keys of a part's top list
     int kcap;                         // next_pow2(k), at least 32; > 32: the top list lives in shared memory
     unsigned int big_merge_at;        // k > 32: pending keys that start a merge in the middle of a probe call (<= 512)
+    float *theta_io;                  // experiment (BM25CU_DEBUG_THETA): 1 = the merge kernel records every query's final
+    int theta_mode;                   // threshold, 2 = every part starts from the recorded value (what a perfect start buys)
 };
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -477,6 +479,7 @@ struct Ms {
                 // least each of its postings: the float below it is a safe start value (as in retrieve_fast.cu)
                 s.theta_key = 0ull;
                 s.gth = kb > 0u ? kb - 1u : 0u;
+                if (p.theta_mode == 2) { const unsigned tb = __float_as_uint(p.theta_io[q]); if (tb > s.gth) s.gth = tb; }
                 s.U = U;
                 s.T = T;
                 s.tot = tot;
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(256) ms_plan_scatter_kernel(int32_t n_queries,
 __global__ void __launch_bounds__(256) ms_merge_kernel(const unsigned char *__restrict__ nparts, const unsigned int *__restrict__ part_base,
                                                        const unsigned long long *__restrict__ partial, const unsigned int *__restrict__ qstat,
                                                        const unsigned long long *__restrict__ qtot, RetrieveArgs a, int32_t doc_base,
-                                                       Ctrl *ctrl, unsigned int *fb_list) {
+                                                       Ctrl *ctrl, unsigned int *fb_list, float *theta_out) {
     const int q = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= a.n_queries) return;
@@ -649,6 +652,7 @@ __global__ void __launch_bounds__(256) ms_merge_kernel(const unsigned char *__re
         }
         const unsigned long long kth = shfl64(t, k - 1);
         route = !(kth != 0ull && cand_score(kth) > 0.0f);  // fewer than k positive matches: padding rules live in retrieve_fast.cu
+        if (theta_out && lane == 0) { const unsigned kb = (unsigned)(kth >> 32); theta_out[q] = (!route && kb > 0u) ? __uint_as_float(kb - 1u) : 0.0f; }
     }
     if (route) {
         if (lane == 0) fb_list[atomicAdd(&ctrl->fb_count, 1u)] = (unsigned)q;
@@ -745,6 +749,13 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.route_all = (!ix->nonneg) || a.k > kmax || a.k > 1024 || (a.mask != nullptr && env_int_ms("BM25CU_MASK_FAST", 1) == 0) ||
                   env_int_ms("BM25CU_FORCE_GENERAL", 0);
     p.budget = (unsigned int)env_int_ms("BM25CU_MS_BUDGET", 1 << 20);
+    p.theta_mode = env_int_ms("BM25CU_DEBUG_THETA", 0);
+    p.theta_io = nullptr;
+    if (p.theta_mode) {
+        int rc0 = ix->d_theta.reserve((size_t)(a.n_queries > 0 ? a.n_queries : 1) * sizeof(float));
+        if (rc0) return rc0;
+        p.theta_io = ix->d_theta.as<float>();
+    }
     p.big_merge_at = (unsigned int)env_int_ms("BM25CU_MS_BIGMERGE", 128);
     if (p.big_merge_at > 512u) p.big_merge_at = 512u;
     if (p.big_merge_at < 1u) p.big_merge_at = 1u;
@@ -789,7 +800,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     BM25CU_CHECK(cudaGetLastError());
     if (p.kcap <= 32)
         ms_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ix->stream>>>(scratch + nq, part_base, p.partial, qstat, qtot, a, ix->doc_base,
-                                                                                  d_ctrl, d_fb_list);
+                                                                                  d_ctrl, d_fb_list, p.theta_mode == 1 ? p.theta_io : nullptr);
     else
         ms_merge_big_kernel<<<(unsigned)nq, 128, (size_t)3 * p.kcap * 8, ix->stream>>>(scratch + nq, part_base, p.partial, qstat, qtot, a, ix->doc_base,
                                                                                       p.kcap, d_ctrl, d_fb_list);
