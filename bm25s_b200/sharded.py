@@ -1,6 +1,7 @@
 """Doc-range sharding over the GPUs of one box: one process per GPU (torch.distributed), every rank
 holds the CSC rows of a contiguous document range, scores the whole query batch on its shard with the fused kernel,
-local top-k lists are exchanged with ONE all_gather and merged on the device (bm25cu_topk_merge). The index build
+local top-k lists are exchanged and merged on the device - `retrieve_device`: stores into the peers' memory over NVLink
+fused with the merge (bm25cu_exchange_*); `retrieve`: host arrays, all_gather + bm25cu_topk_merge. The index build
 shards the same way: shard-local counting, one all_reduce of the document frequencies (+ doc count, total length),
 then shard-local scoring - no posting crosses the fabric. torch is plumbing only (process group, device buffers).
 
