@@ -445,7 +445,7 @@ def main():
         api.scores, api.vocab_dict, api.unique_token_ids_set = ph, {}, set(range(n_vocab))
         api.nonoccurrence_array = no_h if shift_h is not None else None
         api._dev = dev
-        api._dev_key = (id(ph["data"]), id(ph["indices"]), id(ph["indptr"]), n_docs, 1, api.device)
+        api._dev_key = api._residency_key()
         q_lists = [q_tok_h[q_ptr_h[i]:q_ptr_h[i + 1]].tolist() for i in range(n_queries)]
         api.retrieve(q_lists, k=k, return_as="tuple")
         n_api = max(1, min(args.steps, 3))

@@ -2,6 +2,7 @@
 missing, or a call fails, this module raises."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import subprocess
@@ -20,7 +21,8 @@ EXPORTED_SYMBOLS = [
     "bm25cu_build_df_device", "bm25cu_build_df_get", "bm25cu_build_df_set", "bm25cu_build_finish",
     "bm25cu_build_free", "bm25cu_index_build", "bm25cu_index_sizes", "bm25cu_index_download", "bm25cu_retrieve",
     "bm25cu_retrieve_device", "bm25cu_retrieve_device_enqueue", "bm25cu_retrieve_collect", "bm25cu_scores_dense", "bm25cu_topk_dense", "bm25cu_topk_merge",
-    "bm25cu_topk_merge_device", "bm25cu_index_free",
+    "bm25cu_topk_merge_device", "bm25cu_index_free", "bm25cu_index_set_option", "bm25cu_index_unset_option",
+    "bm25cu_debug_colkth", "bm25cu_debug_prof",
     "bm25cu_exchange_create", "bm25cu_exchange_handle_size", "bm25cu_exchange_handle", "bm25cu_exchange_connect",
     "bm25cu_exchange_merge", "bm25cu_exchange_check", "bm25cu_exchange_free",
 ]
@@ -104,6 +106,7 @@ class DeviceIndex:
     def __init__(self, handle):
         self._h = handle
         self._lock = threading.Lock()  # a handle is not thread-safe (include/bm25cu.h)
+        self._opts = {}                # knobs set through set_option (the library keeps the authoritative table)
         nnz, nv, nd, lo, hn = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         check(lib().bm25cu_index_sizes(self._h, C.byref(nnz), C.byref(nv), C.byref(nd), C.byref(lo), C.byref(hn)))
         self.nnz, self.n_vocab, self.n_docs, self.doc_lo, self.has_nonocc = nnz.value, nv.value, nd.value, lo.value, bool(hn.value)
@@ -133,6 +136,34 @@ class DeviceIndex:
                                                C.c_void_p(nonocc_ptr), C.c_int32(device), C.c_int32(doc_lo),
                                                C.c_int32(doc_hi), C.byref(h)))
         return cls(h)
+
+    def set_option(self, name: str, value: int):
+        """Change a tuning / debugging knob of this handle (include/bm25cu.h: bm25cu_index_set_option). The BM25CU_*
+        environment is only read when a handle is created."""
+        with self._lock:
+            check(lib().bm25cu_index_set_option(self._h, name.encode(), C.c_int32(int(value))))
+        self._opts[name] = int(value)
+
+    def unset_option(self, name: str):
+        with self._lock:
+            check(lib().bm25cu_index_unset_option(self._h, name.encode()))
+        self._opts.pop(name, None)
+
+    @contextlib.contextmanager
+    def options(self, **kv):
+        """`with dev.options(MS=0, POOL=1024): ...` - knobs set for the block, previous settings restored after it."""
+        kv = {(k[7:] if k.startswith("BM25CU_") else k): int(v) for k, v in kv.items()}
+        old = {k: self._opts.get(k) for k in kv}
+        try:
+            for k, v in kv.items():
+                self.set_option(k, v)
+            yield self
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    self.unset_option(k)
+                else:
+                    self.set_option(k, v)
 
     def set_stream(self, stream_handle: int):
         check(lib().bm25cu_index_set_stream(self._h, C.c_void_p(stream_handle)))
@@ -239,6 +270,7 @@ class Builder:
     def __init__(self, tokens, doc_ptr, n_vocab, device=0, on_device=False, n_docs=None):
         self._b = C.c_void_p()
         self.n_vocab = int(n_vocab)
+        self.device = int(device)
         if on_device:
             self.n_docs = int(n_docs)
             check(lib().bm25cu_build_begin(C.c_void_p(tokens), C.c_void_p(doc_ptr), C.c_int32(self.n_docs),
@@ -254,6 +286,23 @@ class Builder:
         out = np.empty(self.n_vocab, np.int32)
         check(lib().bm25cu_build_df_get(self._b, ptr(out, C.c_int32)))
         return out
+
+    def df_device_tensor(self):
+        """The builder's shard-local document frequencies as a torch int32[n_vocab] CUDA tensor that ALIASES the
+        library's device array (bm25cu_build_df_device): an in-place all_reduce on it is all a sharded build needs."""
+        import torch
+
+        p = C.c_void_p()
+        check(lib().bm25cu_build_df_device(self._b, C.byref(p)))
+
+        class _Arr:  # __cuda_array_interface__ view of the raw pointer
+            pass
+
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (self.n_vocab,), "typestr": "<i4", "data": (int(p.value), False), "version": 3,
+                                      "strides": None}
+        self._df_keepalive = a
+        return torch.as_tensor(a, device=torch.device("cuda", self.device))
 
     def set_df(self, df: np.ndarray):
         df = np.ascontiguousarray(df, dtype=np.int32)

@@ -10,6 +10,7 @@ import itertools
 import json
 import logging
 import os
+import threading
 from pathlib import Path
 from typing import Any, Dict, Iterable, List, NamedTuple, Tuple, Union
 
@@ -104,28 +105,54 @@ class BM25:
         self.nonoccurrence_array = None
         self._dev = None
         self._dev_key = None
+        self._dev_lock = threading.Lock()
         _lib.lib()  # fail loudly, now, if the CUDA library is missing
 
     # ------------------------------------------------------------------ device residency
-    def _device_index(self) -> _lib.DeviceIndex:
-        """Upload `self.scores` on first use; re-upload if the arrays were swapped (load_scores, direct assignment)."""
+    def _residency_key(self):
+        """What the HBM copy was made from: the array OBJECTS themselves (kept alive by the key, so an id cannot be
+        reused by another array) plus the sizes. In-place edits of the arrays are not seen: call `invalidate()`."""
         sc = self.scores
-        key = (id(sc["data"]), id(sc["indices"]), id(sc["indptr"]), sc["num_docs"], len(sc["data"]), self.device)
-        if self._dev is None or self._dev_key != key:
+        return (sc["data"], sc["indices"], sc["indptr"], sc["num_docs"], len(sc["data"]), self.nonoccurrence_array, self.device)
+
+    @staticmethod
+    def _same_key(a, b):
+        return a is not None and b is not None and len(a) == len(b) and all(
+            (x is y) if isinstance(x, np.ndarray) or x is None or y is None else (x == y) for x, y in zip(a, b))
+
+    def invalidate(self):
+        """Drop the HBM copy of `self.scores`; the next retrieve / get_scores uploads again. Call it after editing
+        `self.scores[...]` or `nonoccurrence_array` in place (swapping the arrays is detected without it)."""
+        with self._dev_lock:
             if self._dev is not None:
                 self._dev.close()
-            self._dev = _lib.DeviceIndex.upload(sc["data"], sc["indices"], sc["indptr"], int(sc["num_docs"]),
-                                                nonocc=self.nonoccurrence_array, device=self.device)
-            self._dev_key = key
-        return self._dev
+            self._dev = None
+            self._dev_key = None
+
+    def _device_index(self) -> _lib.DeviceIndex:
+        """Upload `self.scores` on first use; re-upload if the arrays were swapped (load_scores, direct assignment)."""
+        with self._dev_lock:  # concurrent retrieve() calls: one upload
+            key = self._residency_key()
+            if self._dev is None or not self._same_key(self._dev_key, key):
+                if self._dev is not None:
+                    self._dev.close()
+                    self._dev = None
+                sc = self.scores
+                self._dev = _lib.DeviceIndex.upload(sc["data"], sc["indices"], sc["indptr"], int(sc["num_docs"]),
+                                                    nonocc=self.nonoccurrence_array, device=self.device)
+                self._dev_key = key
+            return self._dev
 
     def _adopt_device_index(self, dev: _lib.DeviceIndex, num_docs: int):
         """After a GPU build: mirror the arrays to host so `self.scores` / save() are reference-identical."""
         data, indices, indptr, nonocc = dev.download()
-        self.scores = {"data": data, "indices": indices, "indptr": indptr, "num_docs": num_docs}
-        self.nonoccurrence_array = nonocc
-        self._dev = dev
-        self._dev_key = (id(data), id(indices), id(indptr), num_docs, len(data), self.device)
+        with self._dev_lock:
+            if self._dev is not None and self._dev is not dev:
+                self._dev.close()
+            self.scores = {"data": data, "indices": indices, "indptr": indptr, "num_docs": num_docs}
+            self.nonoccurrence_array = nonocc
+            self._dev = dev
+            self._dev_key = self._residency_key()
 
     # ------------------------------------------------------------------ index build
     @staticmethod
@@ -292,8 +319,20 @@ class BM25:
         shift = None
         if self.nonoccurrence_array is not None:
             shift = self.nonoccurrence_array[ids].sum()  # numpy's own float32 reduction (bit-exact by construction)
-        mask = None if weight_mask is None else np.asarray(weight_mask, dtype=np.float64)
+        mask = self._mask_f64(weight_mask)
         return self._device_index().scores_dense(ids, shift=shift, mask=mask)
+
+    def _mask_f64(self, weight_mask):
+        """The weight mask as the float64 vector the C ABI takes (exact for bool / int32 / float32 / float64 masks); its
+        length is checked here because the library reads num_docs values from it."""
+        if weight_mask is None:
+            return None
+        mask = np.asarray(weight_mask)
+        if mask.ndim != 1:
+            raise ValueError("weight_mask must be a 1D array.")
+        if len(mask) != self.scores["num_docs"]:
+            raise ValueError("The length of the weight_mask must be the same as the length of the corpus.")
+        return np.ascontiguousarray(mask, dtype=np.float64)
 
     def get_scores(self, query_tokens_single: List[str], weight_mask=None) -> np.ndarray:
         """bm25s/__init__.py:622-638"""
@@ -432,7 +471,7 @@ class BM25:
             out = (np.zeros((nq, k), np.float32), np.zeros((nq, k), np.int64))
             return out + ({},) if with_stats else out
         shift = self._query_shifts(flat, ptr)
-        mask = None if weight_mask is None else np.asarray(weight_mask, dtype=np.float64)
+        mask = self._mask_f64(weight_mask)
         res = self._device_index().retrieve(flat, ptr, k, shift=shift, mask=mask, with_stats=with_stats)
         ids, scores = res[0], res[1]
         out = (scores, ids.astype(np.int64))
@@ -491,6 +530,7 @@ class BM25:
             "num_docs": num_docs,
         }
         self.scores = scores
+        self.invalidate()
 
     @classmethod
     def load(cls, save_dir, data_name="data.csc.index.npy", indices_name="indices.csc.index.npy",

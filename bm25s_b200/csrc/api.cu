@@ -1,8 +1,6 @@
 // extern "C" entry points of the query path (declared in include/bm25cu.h).
 #include <vector>
 
-#include <cstdlib>
-
 #include "common.cuh"
 
 using namespace bm25cu;
@@ -63,14 +61,10 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
         BM25CU_CHECK(cudaGetLastError());
         ++launches;
     }
-    // BM25CU_KERNEL selects the structure of K1: 5 (default) = per-warp document sub-ranges (retrieve_fast.cu),
-    // 7 = bit tags + posting-index splits with barriers between the phases (retrieve_v7.cu, experimental).
-    // BM25CU_MS (default 1): queries go to the list-at-a-time kernel first (retrieve_ms.cu: plan, parts, merge); what it
-    // hands on is served by the streaming kernel from a device-side list.
-    const char *kv = getenv("BM25CU_KERNEL");
-    const int kernel = (kv && *kv) ? atoi(kv) : 5;
-    const char *mv = getenv("BM25CU_MS");
-    const bool ms = kernel == 5 && !(mv && *mv && atoi(mv) == 0);
+    // Knob MS (default 1): queries go to the list-at-a-time kernel first (retrieve_ms.cu: plan, parts, merge); what it
+    // hands on is served by the streaming kernel from a device-side list. A batch that kernel cannot take at all (k over
+    // its top-list capacity, an index with negative scores, FORCE_GENERAL) skips it: no plan, no partial-result buffer.
+    const bool ms = ix->knobs.get("MS", 1) != 0 && retrieve_ms_takes(ix, a);
     ix->ms_ran = false;
     ix->order_valid = false;
     if (ms) {
@@ -82,8 +76,7 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
                                        ix->d_fb_list.as<unsigned int>(), &d_ctrl->fb_count)))
             return rc;
     } else {
-        const char *ov = getenv("BM25CU_ORDER");
-        if (a.n_queries >= 4 * ix->sm_count && !(ov && *ov && atoi(ov) == 0)) {  // small batches: every CTA gets at most a few queries
+        if (a.n_queries >= 4 * ix->sm_count && ix->knobs.get("ORDER", 1) != 0) {  // small batches: every CTA gets at most a few queries
             if ((rc = ix->d_order.reserve((size_t)a.n_queries * 5))) return rc;
             order_queries_kernel<<<1, 1024, 0, ix->stream>>>(a.q_tokens, a.q_ptr, a.n_queries, ix->d_indptr, ix->n_vocab,
                                                              ix->d_order.as<unsigned int>(),
@@ -92,9 +85,7 @@ int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats
             ix->order_valid = true;
             ++launches;
         }
-        rc = (kernel == 7) ? launch_retrieve_v7(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches)
-                           : launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches);
-        if (rc) return rc;
+        if ((rc = launch_retrieve_fast(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches))) return rc;
     }
     BM25CU_CHECK(cudaEventRecord(ix->ev[2], ix->stream));
     if ((rc = launch_retrieve_general(ix, a, d_ctrl, ix->d_general_list.as<unsigned int>(), &launches))) return rc;
@@ -151,8 +142,19 @@ int finish_stats(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, i
 
 extern "C" {
 
-// debug: copy the phase counters of the last retrieve call (48 x uint64); zeros unless built with -DBM25CU_PROFILE
-// debugging / tests only (not part of include/bm25cu.h): the per-column 10th / 100th / 1000th largest scores, f32[3][n_vocab]
+int bm25cu_index_set_option(bm25cu_index *ix, const char *name, int32_t value) {
+    BM25CU_REQUIRE(ix != nullptr && name != nullptr && *name, "bm25cu_index_set_option: null handle or name");
+    ix->knobs.set(name, value);
+    return BM25CU_OK;
+}
+
+int bm25cu_index_unset_option(bm25cu_index *ix, const char *name) {
+    BM25CU_REQUIRE(ix != nullptr && name != nullptr && *name, "bm25cu_index_unset_option: null handle or name");
+    ix->knobs.unset(name);
+    return BM25CU_OK;
+}
+
+// diagnostics (declared in include/bm25cu.h): the per-column 10th / 100th / 1000th largest scores, f32[3][n_vocab]
 int bm25cu_debug_colkth(bm25cu_index *ix, float *out) {
     BM25CU_REQUIRE(ix && out && ix->d_colkth, "bm25cu_debug_colkth: no table");
     BM25CU_CHECK(cudaSetDevice(ix->device));
@@ -160,6 +162,7 @@ int bm25cu_debug_colkth(bm25cu_index *ix, float *out) {
     return BM25CU_OK;
 }
 
+// diagnostics: the phase counters of the last retrieve call (48 x uint64); zeros unless built with -DBM25CU_PROFILE
 int bm25cu_debug_prof(bm25cu_index *ix, unsigned long long *out) {
     BM25CU_REQUIRE(ix && out && ix->d_ctrl.p, "bm25cu_debug_prof: no retrieve call yet");
     BM25CU_CHECK(cudaSetDevice(ix->device));

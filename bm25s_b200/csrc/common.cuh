@@ -5,8 +5,11 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/bm25cu.h"
 
@@ -79,6 +82,24 @@ struct PinBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Tuning / debugging knobs of a handle. Filled ONCE, when the handle is created, from the BM25CU_* environment
+// variables; changed afterwards only through bm25cu_index_set_option. Names are stored without the BM25CU_ prefix.
+struct Knobs {
+    std::vector<std::pair<std::string, int>> kv;
+    static const char *strip(const char *name) { return std::strncmp(name, "BM25CU_", 7) == 0 ? name + 7 : name; }
+    void load_env();
+    int find(const char *name) const {
+        name = strip(name);
+        for (size_t i = 0; i < kv.size(); ++i)
+            if (kv[i].first == name) return (int)i;
+        return -1;
+    }
+    bool has(const char *name) const { return find(name) >= 0; }
+    int get(const char *name, int dflt) const { const int i = find(name); return i >= 0 ? kv[i].second : dflt; }
+    void set(const char *name, int v) { const int i = find(name); if (i >= 0) kv[i].second = v; else kv.emplace_back(strip(name), v); }
+    void unset(const char *name) { const int i = find(name); if (i >= 0) kv.erase(kv.begin() + i); }
+};
+
 constexpr int kPadElems = 64;  // every posting array is over-allocated by this many elements (bulk-copy tails)
 
 }  // namespace bm25cu
@@ -118,6 +139,7 @@ struct bm25cu_index {
     bool order_valid = false;      // d_order holds the pull order of the current batch
     bm25cu::PinBuf h_in, h_out;
     int general_rows = 0;
+    bm25cu::Knobs knobs;           // BM25CU_* environment at creation + bm25cu_index_set_option
 };
 
 namespace bm25cu {
@@ -154,9 +176,8 @@ struct Ctrl {
 // qlist/qcount non-null: serve only the *qcount queries listed in qlist (what retrieve_ms.cu handed on)
 int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_general_list,
                          int *launches, const unsigned int *qlist = nullptr, const unsigned int *qcount = nullptr);
+bool retrieve_ms_takes(const bm25cu_index *ix, const RetrieveArgs &a);  // false: the batch skips retrieve_ms.cu altogether
 int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_fb_list, int *launches);
-int launch_retrieve_v7(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_general_list,
-                         int *launches);
 int launch_retrieve_general(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl,
                             const unsigned int *d_general_list, int *launches);
 int launch_scores_dense(bm25cu_index *ix, const int32_t *d_q, int32_t n_tokens, int has_shift, float shift,

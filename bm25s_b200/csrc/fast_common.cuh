@@ -52,7 +52,6 @@ struct FastParams {
     int theta_mode;
     int trigger;   // candidate count at a window end that starts a cut of the buffer
     int stages;    // stage buffers of the posting pool (2: the next window loads while this one is processed)
-    int hash_max;  // v6: inserts into the per-window contribution hash before falling back to global searches
 };
 
 // ---------------------------------------------------------------- PTX wrappers (mbarrier + bulk async copy)

@@ -2,7 +2,7 @@
 // exact order (token by token, scoring.py:358-366), applies the weight mask (bm25s/__init__.py:610-612), selects
 // the k largest by radix select (selection.py:14-37) and adds the non-occurrence shift (__init__.py:616-618).
 // It serves the inputs the fused streaming kernel (retrieve_fast.cu) declines: weight masks, queries with more
-// than 64 tokens, negative scores in the matrix, very large k; and it backs get_scores / selection.topk.
+// than 15 tokens (kMaxTok), negative scores in the matrix, very large k; and it backs get_scores / selection.topk.
 #include "common.cuh"
 #include "select.cuh"
 
@@ -12,11 +12,17 @@ constexpr int kGeneralThreads = 1024;
 
 // scores[d] = sum over tokens (in order) of M[d, t]; the row must be zero on entry. Column rows are unique,
 // so one token's adds never collide; __syncthreads between tokens keeps the reference's summation order.
+// A token id outside [0, n_vocab) is skipped and reported through `err` bit 0 (the host checks ids too; device entry
+// points get theirs from the caller).
 __device__ void dense_score_row(const float *__restrict__ data, const int32_t *__restrict__ indices,
-                                const int64_t *__restrict__ indptr, const int32_t *__restrict__ q, int nq,
-                                float *row) {
+                                const int64_t *__restrict__ indptr, int32_t n_vocab, const int32_t *__restrict__ q, int nq,
+                                float *row, unsigned int *err) {
     for (int t = 0; t < nq; ++t) {
         const int tok = q[t];
+        if ((unsigned)tok >= (unsigned)n_vocab) {  // uniform over the CTA
+            if (threadIdx.x == 0 && err) atomicOr(err, 1u);
+            continue;
+        }
         const int64_t s = indptr[tok], e = indptr[tok + 1];
         for (int64_t j = s + threadIdx.x; j < e; j += blockDim.x) row[indices[j]] += data[j];
         __syncthreads();
@@ -30,10 +36,10 @@ __device__ void zero_row(float *row, int64_t n) {
 
 __global__ void __launch_bounds__(kGeneralThreads)
 scores_dense_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices,
-                    const int64_t *__restrict__ indptr, const int32_t *__restrict__ q, int nq, int64_t n_docs,
+                    const int64_t *__restrict__ indptr, int32_t n_vocab, const int32_t *__restrict__ q, int nq, int64_t n_docs,
                     const double *__restrict__ mask, int has_shift, float shift, float *out) {
     zero_row(out, n_docs);
-    dense_score_row(data, indices, indptr, q, nq, out);
+    dense_score_row(data, indices, indptr, n_vocab, q, nq, out, nullptr);
     for (int64_t d = threadIdx.x; d < n_docs; d += blockDim.x) {
         float s = out[d];
         if (mask) s = (float)__dmul_rn((double)s, mask[d]);
@@ -45,7 +51,7 @@ scores_dense_kernel(const float *__restrict__ data, const int32_t *__restrict__ 
 // One CTA drains the general queue: query list[c], list[c + gridDim.x], ...
 __global__ void __launch_bounds__(kGeneralThreads)
 retrieve_general_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices,
-                        const int64_t *__restrict__ indptr, int64_t n_docs, int32_t doc_base, RetrieveArgs a,
+                        const int64_t *__restrict__ indptr, int32_t n_vocab, int64_t n_docs, int32_t doc_base, RetrieveArgs a,
                         Ctrl *ctrl, const unsigned int *__restrict__ list, float *scratch, uint32_t *tmp_key,
                         int32_t *tmp_id, int P) {
     __shared__ unsigned int hist[256];
@@ -63,11 +69,14 @@ retrieve_general_kernel(const float *__restrict__ data, const int32_t *__restric
         const int nq = (int)(qe - qs);
         if (threadIdx.x == 0) {
             unsigned long long postings = 0;
-            for (int t = 0; t < nq; ++t) { int tok = a.q_tokens[qs + t]; postings += (unsigned long long)(indptr[tok + 1] - indptr[tok]); }
+            for (int t = 0; t < nq; ++t) {
+                const int tok = a.q_tokens[qs + t];
+                if ((unsigned)tok < (unsigned)n_vocab) postings += (unsigned long long)(indptr[tok + 1] - indptr[tok]);
+            }
             atomicAdd(&ctrl->posting_count, postings);
         }
         zero_row(row, n_docs);
-        dense_score_row(data, indices, indptr, a.q_tokens + qs, nq, row);
+        dense_score_row(data, indices, indptr, n_vocab, a.q_tokens + qs, nq, row, &ctrl->error);
         if (a.mask && nq > 0) {
             for (int64_t d = threadIdx.x; d < n_docs; d += blockDim.x)
                 row[d] = (float)__dmul_rn((double)row[d], a.mask[d]);
@@ -105,7 +114,7 @@ retrieve_general_kernel(const float *__restrict__ data, const int32_t *__restric
 
 int launch_scores_dense(bm25cu_index *ix, const int32_t *d_q, int32_t n_tokens, int has_shift, float shift,
                         const double *d_mask, float *d_out) {
-    scores_dense_kernel<<<1, kGeneralThreads, 0, ix->stream>>>(ix->d_data, ix->d_indices, ix->d_indptr, d_q, n_tokens,
+    scores_dense_kernel<<<1, kGeneralThreads, 0, ix->stream>>>(ix->d_data, ix->d_indices, ix->d_indptr, ix->n_vocab, d_q, n_tokens,
                                                                ix->n_docs, d_mask, has_shift, shift, d_out);
     BM25CU_CHECK(cudaGetLastError());
     return BM25CU_OK;
@@ -125,7 +134,7 @@ int launch_retrieve_general(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctr
     float *scratch = ix->d_scratch.as<float>();
     uint32_t *tmp_key = reinterpret_cast<uint32_t *>(scratch + (size_t)rows * n);
     int32_t *tmp_id = reinterpret_cast<int32_t *>(tmp_key + (size_t)rows * P);
-    retrieve_general_kernel<<<rows, kGeneralThreads, 0, ix->stream>>>(ix->d_data, ix->d_indices, ix->d_indptr,
+    retrieve_general_kernel<<<rows, kGeneralThreads, 0, ix->stream>>>(ix->d_data, ix->d_indices, ix->d_indptr, ix->n_vocab,
                                                                       ix->n_docs, ix->doc_base, a, d_ctrl,
                                                                       d_general_list, scratch, tmp_key, tmp_id, P);
     BM25CU_CHECK(cudaGetLastError());

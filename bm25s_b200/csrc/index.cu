@@ -14,6 +14,16 @@ namespace bm25cu {
 static thread_local std::string g_last_error;
 void set_error(const std::string &msg) { g_last_error = msg; }
 
+extern "C" char **environ;
+void Knobs::load_env() {
+    for (char **e = environ; e && *e; ++e) {
+        if (std::strncmp(*e, "BM25CU_", 7) != 0) continue;
+        const char *eq = std::strchr(*e, '=');
+        if (!eq || !eq[1]) continue;
+        set(std::string(*e + 7, (size_t)(eq - (*e + 7))).c_str(), atoi(eq + 1));
+    }
+}
+
 // per column: [first posting with doc >= doc_lo, first posting with doc >= doc_hi)
 __global__ void shard_bounds_kernel(const int32_t *__restrict__ indices, const int64_t *__restrict__ indptr,
                                     int32_t n_vocab, int32_t doc_lo, int32_t doc_hi, int64_t *start, int64_t *count) {
@@ -47,6 +57,50 @@ __global__ void shard_copy_kernel(const float *__restrict__ data, const int32_t 
         out_data[dst + i] = data[src + i];
         out_indices[dst + i] = indices[src + i] - doc_lo;
     }
+}
+
+// Structural validation of an uploaded CSC (one warp per column): flags[0] |= 1 indptr not non-decreasing inside
+// [0, nnz], |= 2 a document id outside [0, n_docs), |= 4 rows of a column not strictly ascending. The kernels rely on
+// all three (lower bounds, bucket tables, presence bitmaps, scatter into row[indices[j]]); the reference would raise
+// IndexError or return garbage for such a matrix, here the upload is refused.
+__global__ void validate_csc_kernel(const int32_t *__restrict__ indices, const int64_t *__restrict__ indptr, int32_t n_vocab,
+                                    int64_t nnz, int32_t n_docs, unsigned int *flags) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_vocab) return;
+    const int64_t s = indptr[warp], e = indptr[warp + 1];
+    if (s < 0 || e < s || e > nnz) {
+        if (lane == 0) atomicOr(flags, 1u);
+        return;
+    }
+    unsigned int bad = 0u;
+    for (int64_t i = s + lane; i < e; i += 32) {
+        const int32_t d = indices[i];
+        if ((unsigned)d >= (unsigned)n_docs) bad |= 2u;
+        if (i + 1 < e && indices[i + 1] <= d) bad |= 4u;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
+static int validate_csc(const int32_t *d_indices, const int64_t *d_indptr, int32_t n_vocab, int64_t nnz, int32_t n_docs,
+                        cudaStream_t stream) {
+    if (n_vocab <= 0) return BM25CU_OK;
+    unsigned int *d_flag = nullptr, flag = 0;
+    BM25CU_CHECK(cudaMalloc(&d_flag, sizeof(unsigned int)));
+    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(unsigned int), stream);
+    if (e == cudaSuccess) {
+        const int64_t threads = (int64_t)n_vocab * 32;
+        validate_csc_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_indices, d_indptr, n_vocab, nnz, n_docs, d_flag);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d_flag);
+    BM25CU_CHECK(e);
+    if (flag & 1u) { set_error("bm25cu_index_upload: indptr is not non-decreasing within [0, nnz]"); return BM25CU_EINVAL; }
+    if (flag & 2u) { set_error("bm25cu_index_upload: indices holds a document id outside [0, n_docs)"); return BM25CU_EINVAL; }
+    if (flag & 4u) { set_error("bm25cu_index_upload: the rows of a column are not strictly ascending"); return BM25CU_EINVAL; }
+    return BM25CU_OK;
 }
 
 // flags[0] |= 1 if any score is negative, NaN or infinite
@@ -189,16 +243,14 @@ __global__ void btab_fill_kernel(const int32_t *__restrict__ indices, const int6
 
 static int build_bucket_tables(bm25cu_index *ix) {
     if (ix->n_vocab <= 0 || ix->nnz <= 0 || ix->n_docs <= 0) return BM25CU_OK;
-    const char *ev = getenv("BM25CU_BTAB");
-    if (ev && *ev && atoi(ev) == 0) return BM25CU_OK;
+    if (ix->knobs.get("BTAB", 1) == 0) return BM25CU_OK;
     long long *d_sizes = nullptr, *d_tmp = nullptr;
     const int V = ix->n_vocab;
     BM25CU_CHECK(cudaMalloc(&d_sizes, (size_t)V * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&d_tmp, scan_tmp_elems(V) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_btab_off, (size_t)(V + 1) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_btab_sh, (size_t)V));
-    const char *av = getenv("BM25CU_BTAB_AVG");
-    int avg = (av && *av) ? atoi(av) : 8;  // a bucket holds avg .. 2 avg postings on average
+    int avg = ix->knobs.get("BTAB_AVG", 8);  // a bucket holds avg .. 2 avg postings on average
     if (avg < 1) avg = 1;
     btab_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, avg, d_sizes, ix->d_btab_sh);
     BM25CU_CHECK(cudaGetLastError());
@@ -264,16 +316,14 @@ __global__ void pbm_fill_kernel(const int32_t *__restrict__ indices, const int64
 
 static int build_presence_bitmaps(bm25cu_index *ix) {
     if (ix->n_vocab <= 0 || ix->nnz <= 0 || ix->n_docs <= 0) return BM25CU_OK;
-    const char *ev = getenv("BM25CU_PBM");
-    if (ev && *ev && atoi(ev) == 0) return BM25CU_OK;
+    if (ix->knobs.get("PBM", 1) == 0) return BM25CU_OK;
     long long *d_sizes = nullptr, *d_tmp = nullptr;
     const int V = ix->n_vocab;
     BM25CU_CHECK(cudaMalloc(&d_sizes, (size_t)V * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&d_tmp, scan_tmp_elems(V) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_pbm_off, (size_t)(V + 1) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_pbm_sh, (size_t)V));
-    const char *bv = getenv("BM25CU_PBM_BITS");
-    int bits = (bv && *bv) ? atoi(bv) : 8;  // at least this many bits per posting
+    int bits = ix->knobs.get("PBM_BITS", 8);  // at least this many bits per posting
     if (bits < 1) bits = 1;
     pbm_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, bits, d_sizes, ix->d_pbm_sh);
     BM25CU_CHECK(cudaGetLastError());
@@ -294,6 +344,7 @@ static int build_presence_bitmaps(bm25cu_index *ix) {
 }
 
 int finalize_index(bm25cu_index *ix) {
+    ix->knobs.load_env();  // the one place the BM25CU_* environment is read for this handle
     cudaDeviceProp prop;
     BM25CU_CHECK(cudaGetDeviceProperties(&prop, ix->device));
     ix->sm_count = prop.multiProcessorCount;
@@ -319,8 +370,7 @@ int finalize_index(bm25cu_index *ix) {
         BM25CU_CHECK(cudaGetLastError());
     }
     {
-        const char *tv = getenv("BM25CU_TIME");
-        const bool timing = tv && *tv && atoi(tv) != 0;  // debugging: host time of the lookup-structure builds
+        const bool timing = ix->knobs.get("TIME", 0) != 0;  // debugging: host time of the lookup-structure builds
         auto now = [&]() { if (timing) cudaStreamSynchronize(ix->stream); return std::chrono::steady_clock::now(); };
         auto t0 = now();
         int rc_bt = build_bucket_tables(ix);
@@ -431,9 +481,8 @@ static bool stage_ring_ready(int device) {
 }
 
 // Synchronous: returns when `bytes` bytes of host memory at `src` are in device memory at `dst`.
-static cudaError_t staged_h2d(void *dst, const void *src, size_t bytes, int device) {
-    const char *ev = getenv("BM25CU_STAGED_UPLOAD");
-    const bool want = !(ev && *ev && atoi(ev) == 0) && bytes >= 4 * kStageChunk;
+static cudaError_t staged_h2d(void *dst, const void *src, size_t bytes, int device, bool staged) {
+    const bool want = staged && bytes >= 4 * kStageChunk;
     std::unique_lock<std::mutex> lock(g_stage_mu);
     if (!want || !stage_ring_ready(device)) {
         lock.unlock();
@@ -487,6 +536,8 @@ static int upload_impl(const float *data, const int32_t *indices, const int64_t 
     ix->n_vocab = n_vocab;
     ix->n_docs = doc_hi - doc_lo;
     ix->doc_base = doc_lo;
+    const char *sv = getenv("BM25CU_STAGED_UPLOAD");  // read once per upload (the handle's knob table is filled in finalize_index)
+    const bool staged = !(sv && *sv && atoi(sv) == 0);
     int rc = BM25CU_OK;
     auto fail = [&](int code) { destroy(ix); return code; };
 #define TRY(expr)                                                       \
@@ -512,9 +563,10 @@ static int upload_impl(const float *data, const int32_t *indices, const int64_t 
             TRY(cudaMemcpyAsync(ix->d_data, data, (size_t)nnz * sizeof(float), cudaMemcpyDefault, ix->stream));
             TRY(cudaMemcpyAsync(ix->d_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault, ix->stream));
         } else if (nnz) {
-            TRY(staged_h2d(ix->d_data, data, (size_t)nnz * sizeof(float), device));
-            TRY(staged_h2d(ix->d_indices, indices, (size_t)nnz * sizeof(int32_t), device));
+            TRY(staged_h2d(ix->d_data, data, (size_t)nnz * sizeof(float), device, staged));
+            TRY(staged_h2d(ix->d_indices, indices, (size_t)nnz * sizeof(int32_t), device, staged));
         }
+        if ((rc = validate_csc(ix->d_indices, ix->d_indptr, n_vocab, nnz, n_docs, ix->stream))) return fail(rc);
     } else {
         // stage the full matrix on the device, cut out the doc range there
         float *f_data = nullptr;
@@ -542,10 +594,11 @@ static int upload_impl(const float *data, const int32_t *indices, const int64_t 
                 TRY2(cudaMemcpyAsync(f_data, data, (size_t)nnz * sizeof(float), cudaMemcpyDefault, ix->stream));
                 TRY2(cudaMemcpyAsync(f_indices, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault, ix->stream));
             } else {
-                TRY2(staged_h2d(f_data, data, (size_t)nnz * sizeof(float), device));
-                TRY2(staged_h2d(f_indices, indices, (size_t)nnz * sizeof(int32_t), device));
+                TRY2(staged_h2d(f_data, data, (size_t)nnz * sizeof(float), device, staged));
+                TRY2(staged_h2d(f_indices, indices, (size_t)nnz * sizeof(int32_t), device, staged));
             }
         }
+        if ((rc = validate_csc(f_indices, f_indptr, n_vocab, nnz, n_docs, ix->stream))) { cleanup(); return fail(rc); }
         if (n_vocab > 0) {
             shard_bounds_kernel<<<(n_vocab + 255) / 256, 256, 0, ix->stream>>>(f_indices, f_indptr, n_vocab, doc_lo, doc_hi, d_start, d_count);
             TRY2(cudaGetLastError());

@@ -1289,11 +1289,6 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) retrieve_fast_kernel(
     f.run();
 }
 
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_general_list,
                          int *launches, const unsigned int *qlist, const unsigned int *qcount) {
     FastParams p;
@@ -1305,14 +1300,14 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.qcount = qlist ? qcount : nullptr;
     // the k-th-largest table holds ranks 10 / 100 / 1000: rank r bounds every k <= r (k = 1 uses the column maxima)
     p.colkth = nullptr;
-    if (env_int("BM25CU_SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {  // a mask may remove the documents behind the bound
+    if (ix->knobs.get("SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {  // a mask may remove the documents behind the bound
         if (a.k == 1) p.colkth = ix->d_colmax;
         else if (a.k <= 10) p.colkth = ix->d_colkth;
         else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
         else if (a.k <= 1000) p.colkth = ix->d_colkth + 2 * (size_t)ix->n_vocab;
     }
-    p.prune = env_int("BM25CU_PRUNE", 1);
-    p.max_shift = env_int("BM25CU_MAXSHIFT", 2);
+    p.prune = ix->knobs.get("PRUNE", 1);
+    p.max_shift = ix->knobs.get("MAXSHIFT", 2);
     if (p.max_shift < 0) p.max_shift = 0;
     if (p.max_shift > 2) p.max_shift = 2;
     p.n_docs = ix->n_docs;
@@ -1321,23 +1316,22 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.a = a;
     p.ctrl = d_ctrl;
     p.general_list = d_general_list;
-    int threads = env_int("BM25CU_THREADS", 512);
+    int threads = ix->knobs.get("THREADS", 512);
     if (threads != 128 && threads != 256 && threads != 1024) threads = 512;
-    const int ctas_per_sm = env_int("BM25CU_CTAS_PER_SM", 1);
+    const int ctas_per_sm = ix->knobs.get("CTAS_PER_SM", 1);
     const int kcap = next_pow2(a.k < 1 ? 1 : a.k);
-    const int cb_min = env_int("BM25CU_CBMIN", 32);  // candidate buffer: 2 * next_pow2(k) entries unless raised (small buffers compact often and keep theta fresh)
+    const int cb_min = ix->knobs.get("CBMIN", 32);  // candidate buffer: 2 * next_pow2(k) entries unless raised (small buffers compact often and keep theta fresh)
     // 2 * next_pow2(k) keys for small k; four times for larger k (fewer cuts), never more than 4096 unless k needs it
     int cb_auto = kcap <= 64 ? 2 * kcap : 4 * kcap;
     if (cb_auto > 4096) cb_auto = 2 * kcap > 4096 ? 2 * kcap : 4096;
     p.cbcap = cb_auto < cb_min ? next_pow2(cb_min) : cb_auto;
-    p.route_all_general = (!ix->nonneg) || (a.k > 2048) || env_int("BM25CU_FORCE_GENERAL", 0) ||
-                          (a.mask != nullptr && env_int("BM25CU_MASK_FAST", 1) == 0);
+    p.route_all_general = (!ix->nonneg) || (a.k > 2048) || ix->knobs.get("FORCE_GENERAL", 0) ||
+                          (a.mask != nullptr && ix->knobs.get("MASK_FAST", 1) == 0);
     const int budget = ix->max_smem_optin / (ctas_per_sm > 0 ? ctas_per_sm : 1) - (ctas_per_sm > 1 ? 1024 : 0);
     const int nw = threads / 32 - 1;
     p.nwarps = nw;
-    p.debug = env_int("BM25CU_DEBUG_SKIP", 0);
-    p.hash_max = 0;
-    p.theta_mode = env_int("BM25CU_DEBUG_THETA", 0);
+    p.debug = ix->knobs.get("DEBUG_SKIP", 0);
+    p.theta_mode = ix->knobs.get("DEBUG_THETA", 0);
     p.theta_io = nullptr;
     if (p.theta_mode) {
         int rc0 = ix->d_theta.reserve((size_t)(a.n_queries > 0 ? a.n_queries : 1) * sizeof(float));
@@ -1345,9 +1339,9 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
         p.theta_io = ix->d_theta.as<float>();
     }
     // pool: 4-byte slots per stage
-    p.stages = env_int("BM25CU_STAGES", 2) == 1 ? 1 : 2;
+    p.stages = ix->knobs.get("STAGES", 2) == 1 ? 1 : 2;
     p.trigger = 0;
-    int pool = env_int("BM25CU_POOL", ctas_per_sm > 1 ? 6144 : (p.stages == 1 ? 24576 : 14336));
+    int pool = ix->knobs.get("POOL", ctas_per_sm > 1 ? 6144 : (p.stages == 1 ? 24576 : 14336));
     pool = (pool + 3) & ~3;
     const int min_pool = kMaxTok * 2 * kMinCap + 256;
     if (pool < min_pool) pool = min_pool;
@@ -1362,10 +1356,10 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
         fixed = Fast<512>::fixed_smem(p);
         tagcap = (long long)budget - (long long)fixed - 64;
     }
-    const int tag_env = env_int("BM25CU_TAG", 0);
+    const int tag_env = ix->knobs.get("TAG", 0);
     if (tag_env > 0 && tag_env < tagcap) tagcap = tag_env;
     p.tagcap = (int)(tagcap & ~15ll);
-    p.trigger = env_int("BM25CU_TRIGGER", p.cbcap / 2);  // candidates that start a cut of the buffer at a window end
+    p.trigger = ix->knobs.get("TRIGGER", p.cbcap / 2);  // candidates that start a cut of the buffer at a window end
     if (p.trigger <= a.k) p.trigger = a.k + 1;
     if (p.trigger > p.cbcap) p.trigger = p.cbcap;
     p.spillcap = (p.stages == 1 ? 1 : 2) * p.poolcap;

@@ -592,6 +592,8 @@ __global__ void __launch_bounds__(256) ms_plan_cost_kernel(const int32_t *__rest
             const unsigned long long df = (unsigned long long)(indptr[tok + 1] - indptr[tok]);
             tot += df;
             mx = df > mx ? df : mx;
+        } else {
+            atomicOr(&ctrl->error, 1u);  // every token of the batch is range-checked here, whatever route its query takes
         }
     }
     const unsigned long long cost = (T > 1 && tot > mx) ? tot - mx : tot;
@@ -713,9 +715,11 @@ __global__ void __launch_bounds__(128) ms_merge_big_kernel(const unsigned char *
     if (tid == 0) atomicAdd(&ctrl->posting_count, qtot[q]);
 }
 
-static int env_int_ms(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
+// The batch-wide conditions under which every query would be handed on: the caller skips this file altogether then.
+bool retrieve_ms_takes(const bm25cu_index *ix, const RetrieveArgs &a) {
+    const int kmax = ix->knobs.get("MS_KMAX", 1024);  // larger k: the streaming kernel
+    return ix->nonneg && a.k <= kmax && a.k <= 1024 && !(a.mask != nullptr && ix->knobs.get("MASK_FAST", 1) == 0) &&
+           !ix->knobs.get("FORCE_GENERAL", 0);
 }
 
 int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, unsigned int *d_fb_list, int *launches) {
@@ -725,17 +729,17 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.indptr = ix->d_indptr;
     p.colmax = ix->d_colmax;
     p.colkth = nullptr;
-    if (env_int_ms("BM25CU_SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {
+    if (ix->knobs.get("SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {
         if (a.k == 1) p.colkth = ix->d_colmax;
         else if (a.k <= 10) p.colkth = ix->d_colkth;
         else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
         else if (a.k <= 1000) p.colkth = ix->d_colkth + 2 * (size_t)ix->n_vocab;
     }
-    const bool use_bt = env_int_ms("BM25CU_MS_BTAB", 1) && ix->d_btab != nullptr;
+    const bool use_bt = ix->knobs.get("MS_BTAB", 1) && ix->d_btab != nullptr;
     p.btab = use_bt ? ix->d_btab : nullptr;
     p.btab_off = ix->d_btab_off;
     p.btab_sh = ix->d_btab_sh;
-    p.pbm = (env_int_ms("BM25CU_MS_PBM", 1) && ix->d_pbm) ? ix->d_pbm : nullptr;
+    p.pbm = (ix->knobs.get("MS_PBM", 1) && ix->d_pbm) ? ix->d_pbm : nullptr;
     p.pbm_off = ix->d_pbm_off;
     p.pbm_sh = ix->d_pbm_sh;
     p.n_docs = ix->n_docs;
@@ -744,31 +748,34 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.a = a;
     p.ctrl = d_ctrl;
     p.fb_list = d_fb_list;
-    const int kmax = env_int_ms("BM25CU_MS_KMAX", 1024);  // larger k: the streaming kernel
-    p.kcap = (a.k > kmax || a.k > 1024) ? 32 : next_pow2(a.k < 32 ? 32 : a.k);  // larger k: every query is handed on, no top list needed
-    p.route_all = (!ix->nonneg) || a.k > kmax || a.k > 1024 || (a.mask != nullptr && env_int_ms("BM25CU_MASK_FAST", 1) == 0) ||
-                  env_int_ms("BM25CU_FORCE_GENERAL", 0);
-    p.budget = (unsigned int)env_int_ms("BM25CU_MS_BUDGET", 1 << 20);
-    p.theta_mode = env_int_ms("BM25CU_DEBUG_THETA", 0);
+    p.kcap = next_pow2(a.k < 32 ? 32 : a.k);
+    p.route_all = retrieve_ms_takes(ix, a) ? 0 : 1;  // (the caller does not come here then; kept as a safe default)
+    p.budget = (unsigned int)ix->knobs.get("MS_BUDGET", 1 << 20);
+    p.theta_mode = ix->knobs.get("DEBUG_THETA", 0);
     p.theta_io = nullptr;
     if (p.theta_mode) {
         int rc0 = ix->d_theta.reserve((size_t)(a.n_queries > 0 ? a.n_queries : 1) * sizeof(float));
         if (rc0) return rc0;
         p.theta_io = ix->d_theta.as<float>();
     }
-    p.big_merge_at = (unsigned int)env_int_ms("BM25CU_MS_BIGMERGE", 128);
+    p.big_merge_at = (unsigned int)ix->knobs.get("MS_BIGMERGE", 128);
     if (p.big_merge_at > 512u) p.big_merge_at = 512u;
     if (p.big_merge_at < 1u) p.big_merge_at = 1u;
     // plan: parts of at most `part_cost` postings (BM25CU_MS_PARTCOST), at most BM25CU_MS_MAXPARTS per query
-    int max_parts = env_int_ms("BM25CU_MS_MAXPARTS", kMsMaxParts);
+    int max_parts = ix->knobs.get("MS_MAXPARTS", kMsMaxParts);
     if (max_parts < 1) max_parts = 1;
     if (max_parts > 255) max_parts = 255;
-    if (max_parts > 8192 / p.kcap && !getenv("BM25CU_MS_MAXPARTS")) max_parts = 8192 / p.kcap > 1 ? 8192 / p.kcap : 1;  // rows of k keys per part
+    if (max_parts > 8192 / p.kcap && !ix->knobs.has("MS_MAXPARTS")) max_parts = 8192 / p.kcap > 1 ? 8192 / p.kcap : 1;  // rows of k keys per part
+    {   // the partial-result buffer (n_queries * max_parts rows of k keys) stays under 1 GiB: large k * large batches get fewer parts
+        const size_t row_bytes = (size_t)(a.n_queries > 0 ? a.n_queries : 1) * (size_t)a.k * 8;
+        const size_t fit = ((size_t)1 << 30) / row_bytes;
+        if ((size_t)max_parts > fit) max_parts = fit > 1 ? (int)fit : 1;
+    }
     // smaller batches and smaller shards are cut finer so that every CTA still gets several parts (NQ shape, 3 452 queries:
     // 1.34 -> 1.20 ms; a 1/8 shard of the MS-MARCO shape: 0.81 -> 0.68 ms)
-    const int per_sm_cfg = env_int_ms("BM25CU_MS_CTAS", 9);
+    const int per_sm_cfg = ix->knobs.get("MS_CTAS", 9);
     const bool small = a.n_queries < 3 * ix->sm_count * per_sm_cfg || ix->nnz < 300000000ll;
-    const long long part_cost = (long long)env_int_ms("BM25CU_MS_PARTCOST", small ? 32768 : 65536);
+    const long long part_cost = (long long)ix->knobs.get("MS_PARTCOST", small ? 32768 : 65536);
     const size_t nq = (size_t)a.n_queries;
     int rc;
     if ((rc = ix->d_ms_items.reserve(nq * (size_t)max_parts * 8))) return rc;
@@ -792,7 +799,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.gtheta = gtheta;
     p.qstat = qstat;
     p.partial = ix->d_ms_partial.as<unsigned long long>();
-    const int per_sm = env_int_ms("BM25CU_MS_CTAS", 9);  // 55 registers: nine 128-thread CTAs are resident per SM
+    const int per_sm = ix->knobs.get("MS_CTAS", 9);  // 55 registers: nine 128-thread CTAs are resident per SM
     const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 9);
     const size_t dyn = p.kcap > 32 ? (size_t)2 * p.kcap * 8 : 0;
     if (p.kcap <= 32) retrieve_ms_kernel<128, 4, 4, 8, false><<<grid, 128, 0, ix->stream>>>(p);

@@ -53,11 +53,12 @@ class ShardedIndex:
 
     @classmethod
     def build(cls, tokens_local, doc_ptr_local, n_vocab, method="lucene", idf_method=None, k1=1.5, b=0.75, delta=0.5,
-              rank=0, world=1, device=0, group=None, doc_lo=0, on_device=False, n_docs_local=None,
+              rank=0, world=1, device=0, group=None, doc_lo=None, on_device=False, n_docs_local=None,
               total_len_local=None):
         """GPU build of this rank's shard (bm25cu_build_begin / _finish); the document frequencies, the document count
         and the total length are all-reduced across the group in between. With `on_device`, `tokens_local` /
-        `doc_ptr_local` are raw device addresses and `n_docs_local` / `total_len_local` must be given."""
+        `doc_ptr_local` are raw device addresses and `n_docs_local` / `total_len_local` must be given. `doc_lo` (global id
+        of this shard's first document) defaults to the sum of the document counts of the lower ranks."""
         import torch
         import torch.distributed as dist
 
@@ -69,14 +70,28 @@ class ShardedIndex:
         if world > 1:
             nccl = dist.get_backend(group) == "nccl"
             dev_t = torch.device("cuda", device) if nccl else torch.device("cpu")
-            tdf = torch.from_numpy(bld.df().astype(np.int64)).to(dev_t)
-            meta = torch.tensor([nd_local, total_len], dtype=torch.int64, device=dev_t)
-            dist.all_reduce(tdf, group=group)
+            meta = torch.zeros(2 + world, dtype=torch.int64, device=dev_t)  # doc count, total length, per-rank doc counts
+            meta[0], meta[1], meta[2 + rank] = nd_local, total_len, nd_local
             dist.all_reduce(meta, group=group)
-            bld.set_df(tdf.cpu().numpy().astype(np.int32))
-            n_docs_global, total_global = int(meta[0].item()), int(meta[1].item())
+            if nccl:
+                # the shard-local document frequencies are summed where they lie: NCCL reduces the builder's own int32[V]
+                # device array in place (bm25cu_build_df_device), no host round trip
+                tdf = bld.df_device_tensor()
+                torch.cuda.current_stream(dev_t).synchronize()
+                dist.all_reduce(tdf, group=group)
+                torch.cuda.current_stream(dev_t).synchronize()
+            else:
+                tdf = torch.from_numpy(bld.df().astype(np.int64))
+                dist.all_reduce(tdf, group=group)
+                bld.set_df(tdf.numpy().astype(np.int32))
+            meta_h = meta.cpu().tolist()
+            n_docs_global, total_global = int(meta_h[0]), int(meta_h[1])
+            if doc_lo is None:  # contiguous ranges in rank order: exclusive scan of the shards' document counts
+                doc_lo = int(sum(meta_h[2:2 + rank]))
         else:
             n_docs_global, total_global = nd_local, total_len
+            if doc_lo is None:
+                doc_lo = 0
         dev = bld.finish(n_docs_global, total_global, method, idf_method or method, k1, b, delta, doc_lo=doc_lo)
         bld.close()
         return cls(dev, n_docs_global, rank, world, device, group)

@@ -97,6 +97,18 @@ int bm25cu_index_build(const int32_t *tokens, const int64_t *doc_ptr, int32_t n_
                        int32_t tfc_method, int32_t idf_method, double k1, double bparam, double delta,
                        int32_t device, int32_t tokens_on_device, bm25cu_index **out);
 
+/* Tuning / debugging knobs of a handle (DESIGN.md lists them). The BM25CU_<NAME> environment variables are read ONCE,
+ * when a handle is created; afterwards a knob changes only through these calls. `name` with or without the BM25CU_
+ * prefix, e.g. bm25cu_index_set_option(ix, "MS", 0) serves every query with the streaming kernel alone. */
+int bm25cu_index_set_option(bm25cu_index *ix, const char *name, int32_t value);
+int bm25cu_index_unset_option(bm25cu_index *ix, const char *name);
+
+/* Diagnostics. _colkth: the upload-time table of the 10th / 100th / 1000th largest score of every column,
+ * float32[3][n_vocab] (start values of the pruning threshold). _prof: 48 uint64 phase counters of the last retrieve call
+ * (all zero unless the library was built with -DBM25CU_PROFILE: `make prof`). */
+int bm25cu_debug_colkth(bm25cu_index *ix, float *out);
+int bm25cu_debug_prof(bm25cu_index *ix, unsigned long long *out);
+
 /* Sizes of a shard, then a copy of it back into caller-allocated numpy arrays (so that `self.scores`
  * and BM25.save, bm25s/__init__.py:1010-1017, stay reference-identical). indices are shard-local ids. */
 int bm25cu_index_sizes(const bm25cu_index *ix, int64_t *nnz, int32_t *n_vocab, int32_t *n_docs_local,

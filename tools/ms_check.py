@@ -1,5 +1,5 @@
 """K1m (retrieve_ms.cu) against the streaming kernel at full size: identical ids and scores, timing, work counters.
-usage: python tools/ms_check.py [shape] [k] [n_docs]   (env BM25CU_* knobs apply to the K1m run)"""
+usage: python tools/ms_check.py [shape] [k] [n_docs]   (MS_SWEEP='MS_CTAS=8,MS_PARTCOST=4096;...' runs knob sets)"""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bm25s_b200._lib as L
@@ -24,7 +24,7 @@ ix = DeviceIndex.upload_device(data.data_ptr(), indices.data_ptr(), indptr.data_
 print('upload_device s', round(time.time() - t0, 3))
 t0 = time.time(); ix2 = DeviceIndex.upload_device(data.data_ptr(), indices.data_ptr(), indptr.data_ptr(), data.numel(), n_vocab, n_docs); print('second upload_device s', round(time.time() - t0, 3)); ix2.close(); del ix2
 def run(ms):
-    os.environ['BM25CU_MS'] = ms
+    ix.set_option('MS', int(ms))
     oi = torch.empty((n_queries, k), dtype=torch.int32, device=dev); os_ = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
     best = None
     for it in range(4):
@@ -39,7 +39,9 @@ for cfg in os.environ.get('MS_SWEEP', '').split(';'):
     if not cfg:
         continue
     kv = dict(x.split('=') for x in cfg.split(','))
-    os.environ.update(kv)
+    kv = {kk.replace('BM25CU_', ''): int(v) for kk, v in kv.items()}
+    for kk, v in kv.items():
+        ix.set_option(kk, v)
     oi1, os1, st1 = run('1')
     prof = (C.c_ulonglong * 48)()
     L.check(L.lib().bm25cu_debug_prof(ix._h, prof))
@@ -47,7 +49,7 @@ for cfg in os.environ.get('MS_SWEEP', '').split(';'):
     ok = bool((oi1 == oi0).all()) and bool((os1.view(torch.int32) == os0.view(torch.int32)).all())
     print('SWEEP', cfg, 'ms', round(st1['fast_kernel_ms'], 3), 'K1m', round(st1['ms_kernel_ms'], 3), 'identical', ok, ' '.join(f'{n.split()[0][:5]}{n.split()[-1][:6]}={v}' for n, v in zip(names, p)))
     for key in kv:
-        os.environ.pop(key, None)
+        ix.unset_option(key)
 oi1, os1, st1 = run('1')
 prof = (C.c_ulonglong * 48)()
 L.check(L.lib().bm25cu_debug_prof(ix._h, prof))

@@ -10,11 +10,9 @@ dev = DeviceIndex.upload(data, indices, indptr, n_docs)
 import os
 for k in (10, 300):
     # default (list-at-a-time kernel, parts), many small parts, hand-over to the streaming kernel, streaming kernel alone
-    for env in ({}, {"BM25CU_MS_PARTCOST": "512", "BM25CU_MS_MAXPARTS": "64"}, {"BM25CU_MS_BUDGET": "64"}, {"BM25CU_MS": "0"}):
-        os.environ.update(env)
-        ids, sc = dev.retrieve(qs.tokens, qs.ptr, k)
-        for kk in env:
-            os.environ.pop(kk)
+    for env in ({}, {"MS_PARTCOST": 512, "MS_MAXPARTS": 64}, {"MS_BUDGET": 64}, {"MS": 0}):
+        with dev.options(**env):
+            ids, sc = dev.retrieve(qs.tokens, qs.ptr, k)
         rid, rsc = CO.retrieve(data, indices, indptr, n_docs, qs.tokens, qs.ptr, k)
         assert np.array_equal(sc, rsc), (k, env)
 b = DeviceIndex.build(corp.tokens, corp.ptr, n_vocab, "lucene", "lucene", 1.5, 0.75, 0.5)

@@ -13,7 +13,7 @@ ix = DeviceIndex.upload_device(data.data_ptr(), indices.data_ptr(), indptr.data_
 k = 10
 oi = torch.empty((n_queries, k), dtype=torch.int32, device=dev); os_ = torch.empty((n_queries, k), dtype=torch.float32, device=dev)
 def run(mode, reps=3):
-    os.environ['BM25CU_DEBUG_THETA'] = str(mode)
+    ix.set_option('DEBUG_THETA', mode)
     ms = []
     for _ in range(reps):
         st = ix.retrieve_device(qt.data_ptr(), qp.data_ptr(), n_queries, int(qp[-1]), k, oi.data_ptr(), os_.data_ptr())
