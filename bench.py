@@ -1,14 +1,20 @@
 """Benchmark of the bm25s query-time hot path on B200: QPS at k=10 on the MS-MARCO-shaped synthetic corpus
 (8.8 M docs, 6 980 queries) - BASELINE.json's metric - with the roofline of the fused scoring + top-k kernel and the
-CPU baseline (the C port of the reference algorithm, oracle/bm25_oracle.c) timed on the box's host cores.
+CPU baselines timed on the box's host cores: the C port of the reference algorithm (oracle/bm25_oracle.c) and, when
+`baseline/_ref` holds the reference package (copied there by __graft_entry__.build()), the UNMODIFIED reference itself
+(bm25s numpy and numba backends) on the same CSC.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape msmarco|nq|scifact] [--k 10]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape msmarco|nq|scifact|100m] [--k 10]
 
 One "step" = one pass of the hot path over the whole query batch. N > 1 (torchrun, one rank per GPU): documents are
-sharded by contiguous doc-id range, every rank scores the whole batch on its shard, local top-k lists are exchanged
-with one NCCL all_gather and merged on the device (strong scaling: the corpus and the batch are fixed).
+sharded by contiguous doc-id range, every rank scores the whole batch on its shard, the local top-k rows are exchanged
+(stores into the peers' memory over NVLink fused with the merge, or NCCL all_gather + merge with --exchange nccl) and
+merged on the device (strong scaling: the corpus and the batch are fixed). Every line carries `result_digest`, a hash of
+the merged ids and score bits of the whole batch: the tie rule is deterministic (score desc, id asc), so the digest is
+the same at N = 1, 2, 4, 8, and a sample of rows is checked against the C oracle on the unsharded matrix at every N.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,9 +40,12 @@ def parse():
     ap.add_argument("--shape", default="msmarco")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--method", default="lucene")
+    ap.add_argument("--queries", type=int, default=0, help="override the shape's batch size (BASELINE configs[3]: 10000)")
     ap.add_argument("--n-docs", type=int, default=0, help="override the shape's document count (debugging)")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baselines AND the oracle spot check")
+    ap.add_argument("--no-reference-backends", action="store_true", help="cpu_baseline: the C port only")
+    ap.add_argument("--parity-queries", type=int, default=300, help="rows checked against the C oracle (0: none)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the shards' top-k rows meet - p2p: stores into peer memory over NVLink fused with the merge "
                          "(bm25cu_exchange_*), nccl: all_gather + merge kernel")
@@ -46,7 +55,8 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe), sampled every 50 ms from before the warm-up to
+    the end of the end-to-end arm, so that the short timed region is always covered by samples under load."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -59,7 +69,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -74,24 +84,28 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        # "under load": samples whose power draw is in the upper half of the observed range
+        load = [s for s, p in zip(sm, pw) if pw and p >= (min(pw) + max(pw)) / 2]
+        return {"sm_mhz": float(np.median(load if load else sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(load),
+                "window": "warm-up + timed region + end-to-end arm, 50 ms period"}
 
 
 def shape_of(args):
@@ -100,6 +114,8 @@ def shape_of(args):
     n_docs, avg_len, n_vocab, n_queries = synth.SHAPES[args.shape]
     if args.n_docs:
         n_docs = args.n_docs
+    if args.queries:
+        n_queries = args.queries
     return n_docs, avg_len, n_vocab, n_queries
 
 
@@ -124,33 +140,26 @@ def build_corpus(args, device, rank=0, world=1):
 
 def build_index(args, tokens, ptr, rank, world, local_rank):
     """The library's own GPU index build (bm25cu_build_begin/_finish) of this rank's doc-range shard; timed, reported
-    as `index_build_s` (not part of the metric)."""
+    as `index_build_s` (not part of the metric). Returns a ShardedIndex (world 1: a single whole shard)."""
     import torch
 
-    from bm25s_b200 import DeviceIndex
     from bm25s_b200.sharded import ShardedIndex, shard_bounds
 
     n_docs, avg_len, n_vocab, n_queries = shape_of(args)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    if world == 1:
-        dev = DeviceIndex.build_device(tokens.data_ptr(), ptr.data_ptr(), n_docs, n_vocab, args.method, args.method,
-                                       1.5, 0.75, 0.5, device=local_rank)
+    lo, hi = shard_bounds(n_docs, world, rank)
+    if world == 1 or local_shards(args, world):
+        t_lo, t_hi = 0, int(ptr[-1].item())
+        tok_l, ptr_l = tokens, ptr
     else:
-        lo, hi = shard_bounds(n_docs, world, rank)
-        if local_shards(args, world):
-            t_lo, t_hi = 0, int(ptr[-1].item())
-            tok_l, ptr_l = tokens, ptr
-        else:
-            t_lo, t_hi = int(ptr[lo].item()), int(ptr[hi].item())
-            tok_l = tokens[t_lo:t_hi].contiguous()
-            ptr_l = (ptr[lo:hi + 1] - t_lo).contiguous()
-        sh = ShardedIndex.build(tok_l.data_ptr(), ptr_l.data_ptr(), n_vocab, method=args.method, rank=rank, world=world,
-                                device=local_rank, doc_lo=lo, on_device=True, n_docs_local=hi - lo,
-                                total_len_local=t_hi - t_lo)
-        dev = sh.dev
+        t_lo, t_hi = int(ptr[lo].item()), int(ptr[hi].item())
+        tok_l = tokens[t_lo:t_hi].contiguous()
+        ptr_l = (ptr[lo:hi + 1] - t_lo).contiguous()
+    sh = ShardedIndex.build(tok_l.data_ptr(), ptr_l.data_ptr(), n_vocab, method=args.method, rank=rank, world=world,
+                            device=local_rank, doc_lo=lo, on_device=True, n_docs_local=hi - lo, total_len_local=t_hi - t_lo)
     torch.cuda.synchronize()
-    return dev, time.perf_counter() - t0
+    return sh, time.perf_counter() - t0
 
 
 def peaks():
@@ -163,7 +172,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(csc_host, q_tok, q_ptr, n_docs, k, shift, target_seconds, n_threads=0):
+def query_shifts(nonocc, q_tok, q_ptr):
+    """nonoccurrence_array[ids].sum() per query by numpy itself (bm25s/__init__.py:616-617)."""
+    if nonocc is None:
+        return None
+    return np.array([nonocc[q_tok[q_ptr[i]:q_ptr[i + 1]]].sum() for i in range(len(q_ptr) - 1)], np.float32)
+
+
+def sub_batch(q_tok, q_ptr, rows):
+    """The queries `rows` of a flat batch as a flat batch of their own."""
+    ptr = np.zeros(len(rows) + 1, np.int64)
+    np.cumsum([q_ptr[q + 1] - q_ptr[q] for q in rows], out=ptr[1:])
+    tok = np.concatenate([q_tok[q_ptr[q]:q_ptr[q + 1]] for q in rows]).astype(np.int32) if len(rows) else np.zeros(0, np.int32)
+    return tok, ptr
+
+
+def port_baseline(csc_host, q_tok, q_ptr, n_docs, k, shift, target_seconds, n_threads=0):
     """The reference algorithm (C port, oracle/bm25_oracle.c) on the host cores over a bounded query sample."""
     from oracle import c_oracle as CO
 
@@ -176,16 +200,142 @@ def cpu_baseline(csc_host, q_tok, q_ptr, n_docs, k, shift, target_seconds, n_thr
         sub_ptr = q_ptr[: n + 1]
         sub_tok = q_tok[: int(sub_ptr[-1])]
         t0 = time.perf_counter()
-        ids, sc = CO.retrieve(data, indices, indptr, n_docs, sub_tok, sub_ptr, k, shift=None if shift is None else shift[:n],
-                              n_threads=cores)
-        return time.perf_counter() - t0, ids, sc
+        CO.retrieve(data, indices, indptr, n_docs, sub_tok, sub_ptr, k, shift=None if shift is None else shift[:n], n_threads=cores)
+        return time.perf_counter() - t0
 
-    t_probe, _, _ = run(probe)
-    per_q = t_probe / probe
+    per_q = run(probe) / probe
     n = int(min(nq, max(probe, target_seconds / max(per_q, 1e-9))))
-    t, ids, sc = run(n)
+    t = run(n)
     return {"value": n / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n} of {nq} queries, one pass, {t:.2f} s, threads pull queries from a shared counter"}, (n, ids, sc)
+            "sample": f"first {n} of {nq} queries, one pass, {t:.2f} s, threads pull queries from a shared counter"}
+
+
+def oracle_parity(csc_host, q_tok, q_ptr, n_docs, k, shift, ids, scores, n_rows):
+    """Strided sample of the batch scored by the C oracle on the whole (unsharded) matrix: scores bit-equal, ids equal
+    as sets above the k-th score, every returned id carries its oracle dense score (a few rows)."""
+    from oracle import c_oracle as CO
+
+    data, indices, indptr = csc_host
+    nq = len(q_ptr) - 1
+    rows = np.unique(np.linspace(0, nq - 1, num=min(n_rows, nq)).astype(np.int64))
+    s_tok, s_ptr = sub_batch(q_tok, q_ptr, rows)
+    rid, rsc = CO.retrieve(data, indices, indptr, n_docs, s_tok, s_ptr, k, shift=None if shift is None else shift[rows])
+    ok = bool(np.array_equal(scores[rows].view(np.int32), rsc.view(np.int32)))
+    for j, q in enumerate(rows):
+        kth = rsc[j, -1]
+        ok &= set(ids[q][scores[q] > kth].tolist()) == set(rid[j][rsc[j] > kth].tolist())
+    dense_rows = rows[:: max(1, len(rows) // 8)]
+    for q in dense_rows:
+        dense = CO.scores_dense(data, indices, indptr, n_docs, q_tok[q_ptr[q]:q_ptr[q + 1]], shift=None if shift is None else shift[q])
+        ok &= bool(np.array_equal(dense[ids[q]], scores[q]))
+        rest = dense.copy()
+        rest[ids[q]] = -np.inf
+        ok &= bool(rest.max() <= scores[q, -1])
+    return {"queries": int(len(rows)), "dense_rows": int(len(dense_rows)), "ok": bool(ok),
+            "what": "scores bit-equal, id sets equal above the k-th score, dense-vector check of returned ids and of the tail"}
+
+
+def reference_module():
+    """The unmodified reference package from baseline/_ref (installed there by __graft_entry__.build()), or None."""
+    p = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(p, "bm25s", "__init__.py")):
+        return None
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    os.environ.setdefault("DISABLE_TQDM", "1")
+    try:
+        import bm25s  # noqa: PLC0415
+
+        return bm25s
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] baseline/_ref/bm25s does not import: {e}", file=sys.stderr)
+        return None
+
+
+def reference_backends(bm25s, csc_host, nonocc, n_docs, n_vocab, method, q_lists, k, seconds, ours=None):
+    """The reference's own retrieve() (bm25s/__init__.py:676-939) on the same CSC, injected the way load_scores does
+    (:1121-1127): numpy backend on one core, numba backend on one thread and on os.cpu_count() threads. Bounded samples.
+    `ours` = (ids, scores) of the same batch for a tie-aware parity check against the numpy backend."""
+    import platform
+
+    data, indices, indptr = csc_host
+    out = {"cpu_count": os.cpu_count(), "cpu": platform.processor() or platform.machine(), "numpy": np.__version__}
+
+    def make(backend):
+        r = bm25s.BM25(method=method, backend=backend)
+        r.scores = {"data": data, "indices": indices, "indptr": indptr, "num_docs": n_docs}
+        r.nonoccurrence_array = nonocc
+        r.vocab_dict = {}
+        r.unique_token_ids_set = set(range(n_vocab))
+        return r
+
+    def timed(r, qs, **kw):
+        t0 = time.perf_counter()
+        res = r.retrieve(qs, k=k, show_progress=False, **kw)
+        return time.perf_counter() - t0, res
+
+    # numpy backend, one core (n_threads=0): probe 2 queries, then a sample sized for `seconds`
+    try:
+        r = make("numpy")
+        t, _ = timed(r, q_lists[:2], n_threads=0)
+        n = int(max(2, min(len(q_lists), 200, seconds / max(t / 2, 1e-9))))
+        t, res = timed(r, q_lists[:n], n_threads=0)
+        out["numpy"] = {"value": n / t, "unit": UNIT, "cores": 1, "sample": f"first {n} queries, n_threads=0, {t:.2f} s"}
+        if ours is not None:
+            ids, sc = ours
+            rs, ri = np.asarray(res.scores), np.asarray(res.documents)
+            ok = True
+            for q in range(n):
+                ok &= bool(np.allclose(sc[q], rs[q], rtol=1e-5, atol=0))
+                kth = rs[q, -1]
+                ok &= set(ids[q][sc[q] > kth].tolist()) == set(ri[q][rs[q] > kth].tolist())
+            out["numpy"]["parity_with_ours"] = {"queries": n, "ok": bool(ok), "bit_equal_scores": bool(np.array_equal(sc[:n], rs))}
+    except Exception as e:  # noqa: BLE001
+        out["numpy"] = {"error": repr(e)[:200]}
+    try:
+        import numba
+
+        out["numba_version"] = numba.__version__
+        r = make("numba")
+        timed(r, q_lists[:4], n_threads=1)  # JIT compilation
+        best = None
+        for label, nt in (("numba_1_thread", 1), ("numba_all_threads", -1)):
+            cores = 1 if nt == 1 else os.cpu_count()
+            probe = max(4, cores)
+            t, _ = timed(r, q_lists[:probe], n_threads=nt)
+            n = int(max(probe, min(len(q_lists), seconds / max(t / probe, 1e-9))))
+            t, _ = timed(r, q_lists[:n], n_threads=nt)
+            out[label] = {"value": n / t, "unit": UNIT, "cores": cores, "sample": f"first {n} queries, n_threads={nt}, {t:.2f} s"}
+            if best is None or out[label]["value"] > out[best]["value"]:
+                best = label
+        out["numba_best"] = best
+    except Exception as e:  # noqa: BLE001
+        out["numba_error"] = repr(e)[:200]
+    return out
+
+
+def digest_of(ids, scores):
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(ids, dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(scores, dtype=np.float32).view(np.int32).tobytes())
+    return h.hexdigest()[:16]
+
+
+def unsharded_csc(args, device, local_rank):
+    """Rank 0, untimed: the whole (unsharded) matrix built by the library and downloaded, for the oracle check at N > 1."""
+    import torch
+
+    from bm25s_b200 import DeviceIndex, synth
+
+    n_docs, avg_len, n_vocab, _ = shape_of(args)
+    tokens, ptr = synth.make_corpus_torch(n_docs, avg_len, n_vocab, seed=0, device=device)
+    full = DeviceIndex.build_device(tokens.data_ptr(), ptr.data_ptr(), n_docs, n_vocab, args.method, args.method, 1.5, 0.75, 0.5,
+                                    device=local_rank)
+    del tokens, ptr
+    data_h, indices_h, indptr_h, no_h = full.download()
+    full.close()
+    torch.cuda.empty_cache()
+    return (data_h, indices_h, indptr_h), no_h
 
 
 def main():
@@ -193,8 +343,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
-        return 0
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        world = 1  # the reference arm is one process on the host cores
     import torch
 
     if not torch.cuda.is_available():
@@ -211,36 +363,42 @@ def main():
 
     import torch.distributed as dist
 
-    if world > 1 and args.impl == "ours":
+    if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    (tokens, ptr), (q_tok, q_ptr) = build_corpus(args, device, rank if args.impl == "ours" else 0, world if args.impl == "ours" else 1)
-    dev, build_s = build_index(args, tokens, ptr, rank if args.impl == "ours" else 0, world if args.impl == "ours" else 1,
-                               local_rank)
+    (tokens, ptr), (q_tok, q_ptr) = build_corpus(args, device, rank, world)
+    sh, build_s = build_index(args, tokens, ptr, rank, world, local_rank)
+    dev = sh.dev
     del tokens, ptr
     torch.cuda.empty_cache()
     nnz = dev.nnz
     q_tok_h = q_tok.cpu().numpy()
     q_ptr_h = q_ptr.cpu().numpy()
     n_q_tokens = int(q_ptr_h[-1])
-    shift_h = None
-    csc_host = None
-    if (args.impl == "reference") or (rank == 0 and world == 1 and not args.no_cpu_baseline) or dev.has_nonocc:
+    want_cpu = rank == 0 and not args.no_cpu_baseline
+    csc_host, no_h = None, None
+    if world == 1 and (args.impl == "reference" or want_cpu):
         data_h, indices_h, indptr_h, no_h = dev.download()
         csc_host = (data_h, indices_h, indptr_h)
-        if no_h is not None:
-            shift_h = np.array([no_h[q_tok_h[q_ptr_h[i]:q_ptr_h[i + 1]]].sum() for i in range(n_queries)], np.float32)
+    elif dev.has_nonocc:
+        no_h = dev.download_nonocc()
+    shift_h = query_shifts(no_h, q_tok_h, q_ptr_h)
 
-    # ------------------------------------------------------------------ reference arm: CPU port on host cores
+    # ------------------------------------------------------------------ reference arm: CPU implementations on host cores
     if args.impl == "reference":
         dev.close()
         torch.cuda.empty_cache()
         from oracle import c_oracle as CO
 
         cores = CO.max_threads()
-        # bounded sample per step: sized from a probe so that (warmup + steps) passes end within a few minutes
-        base, _ = cpu_baseline(csc_host, q_tok_h, q_ptr_h, n_docs, k, shift_h, target_seconds=2.0)
-        budget = 150.0 / max(1, args.steps + args.warmup)
-        n = int(max(cores, min(n_queries, base["value"] * budget)))
+        n_pass = max(1, args.steps + args.warmup)
+        ref = reference_module()
+        backends = None
+        if ref is not None and not args.no_reference_backends:
+            q_lists = [q_tok_h[q_ptr_h[i]:q_ptr_h[i + 1]].tolist() for i in range(n_queries)]
+            backends = reference_backends(ref, csc_host, no_h, n_docs, n_vocab, args.method, q_lists, k, seconds=8.0)
+        # C port: bounded sample per step, sized from a probe so that (warmup + steps) passes end within ~2 minutes
+        base = port_baseline(csc_host, q_tok_h, q_ptr_h, n_docs, k, shift_h, target_seconds=2.0)
+        n = int(max(cores, min(n_queries, base["value"] * (110.0 / n_pass))))
         sub_ptr = q_ptr_h[: n + 1]
         sub_tok = q_tok_h[: int(sub_ptr[-1])]
         times = []
@@ -252,78 +410,56 @@ def main():
                 times.append(dt)
         total = sum(times)
         qps = n * len(times) / total
-        line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1000 * total / len(times), "higher_is_better": True,
+        cb = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"first {n} of {n_queries} queries per step",
+              "port": {"value": qps, "cores": cores, "what": "oracle/bm25_oracle.c, pthreads over queries"}}
+        value, ms_step = qps, 1000 * total / len(times)
+        if backends is not None:
+            cb["reference_backends"] = backends
+            best = backends.get("numba_best")
+            cands = [(backends[x]["value"], x) for x in ("numpy", best) if x and isinstance(backends.get(x), dict) and "value" in backends[x]]
+            if cands and max(cands)[0] > qps:
+                # the unmodified reference beats the port on this box: it is the arm's value
+                v, name = max(cands)
+                cb.update({"value": v, "kind": "reference", "cores": backends[name]["cores"], "sample": f"bm25s {name}: " + backends[name]["sample"]})
+                value, ms_step = v, 1000.0 * n_queries / v
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"first {n} of {n_queries} queries per step"},
-                "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "cpu_baseline": cb,
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "value = the fastest CPU arm on this box: the C port of the reference algorithm on all host threads, or the "
+                        "unmodified reference (baseline/_ref) if one of its backends is faster; the CSC comes from the library's GPU "
+                        "build (bit-identical to the reference's, tests/test_gpu_build.py), the timed region is CPU-only"}
         print(json.dumps(line))
         return 0
 
     # ------------------------------------------------------------------ our arm
-    from bm25s_b200 import _lib
-
-    if not (rank == 0 and world == 1 and not args.no_cpu_baseline):
-        csc_host = None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     stream = torch.cuda.current_stream()
-    dev.set_stream(stream.cuda_stream)
-
     shift_d = None if shift_h is None else torch.from_numpy(shift_h).to(device)
-    out_ids = torch.empty((n_queries, k), dtype=torch.int32, device=device)
-    out_sc = torch.empty((n_queries, k), dtype=torch.float32, device=device)
-    exch = None
+    work = (torch.empty((n_queries, k), dtype=torch.int32, device=device), torch.empty((n_queries, k), dtype=torch.float32, device=device))
+    merged = work
     if world > 1:
-        m_ids = torch.empty((n_queries, k), dtype=torch.int32, device=device)
-        m_sc = torch.empty((n_queries, k), dtype=torch.float32, device=device)
+        merged = (torch.empty((n_queries, k), dtype=torch.int32, device=device), torch.empty((n_queries, k), dtype=torch.float32, device=device))
         if args.exchange == "p2p":
-            def all_gather_bytes(b):
-                mine = torch.tensor(list(b), dtype=torch.uint8, device=device)
-                allh = torch.empty((world, len(b)), dtype=torch.uint8, device=device)
-                dist.all_gather_into_tensor(allh.view(-1), mine)
-                return [bytes(allh[r].cpu().tolist()) for r in range(world)]
-
             try:
-                exch = _lib.PeerExchange(local_rank, rank, world, n_queries * k, all_gather_bytes)
+                sh.enable_peer_exchange(n_queries, k)
                 ok = 1
             except Exception as e:  # CUDA IPC unavailable between these processes: say so and take the NCCL exchange
                 print(f"[bench] peer-memory exchange unavailable ({e}); using all_gather + merge", file=sys.stderr)
-                exch, ok = None, 0
+                ok = 0
             okt = torch.tensor([ok], device=device)
-            dist.all_reduce(okt, op=dist.ReduceOp.MIN)  # every rank takes the same path; also the barrier before the first push
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)  # every rank takes the same path
             torch.cuda.synchronize()
             if int(okt.item()) == 0:
-                exch = None
                 args.exchange = "nccl"
-        if exch is None:
-            g_ids = torch.empty((world, n_queries, k), dtype=torch.int32, device=device)
-            g_sc = torch.empty((world, n_queries, k), dtype=torch.float32, device=device)
-    stats_acc = []
+        if args.exchange == "nccl":
+            sh.enable_nccl_exchange()
 
-    def step_device(qt, qp, collect=True):
-        if world > 1 and exch is not None:
-            # scoring kernels, push into the peers' memory, merge: one chain on the stream, no host round trip in between
-            dev.retrieve_device_enqueue(qt.data_ptr(), qp.data_ptr(), n_queries, n_q_tokens, k, out_ids.data_ptr(), out_sc.data_ptr(),
-                                        shift_ptr=None if shift_d is None else shift_d.data_ptr())
-            exch.merge(out_ids.data_ptr(), out_sc.data_ptr(), n_queries, k, m_ids.data_ptr(), m_sc.data_ptr(), stream.cuda_stream)
-            if not collect:
-                return None
-            st = dev.collect(n_queries, n_q_tokens, k)
-            st["launches"] += 2
-            return st
-        st = dev.retrieve_device(qt.data_ptr(), qp.data_ptr(), n_queries, n_q_tokens, k, out_ids.data_ptr(), out_sc.data_ptr(),
-                                 shift_ptr=None if shift_d is None else shift_d.data_ptr())
-        launches = st["launches"]
-        if world > 1:
-            dist.all_gather_into_tensor(g_ids.view(-1), out_ids.view(-1))
-            dist.all_gather_into_tensor(g_sc.view(-1), out_sc.view(-1))
-            _lib.check(_lib.lib().bm25cu_topk_merge_device(
-                _lib.C.c_void_p(g_ids.data_ptr()), _lib.C.c_void_p(g_sc.data_ptr()), world, n_queries, k,
-                _lib.C.c_void_p(m_ids.data_ptr()), _lib.C.c_void_p(m_sc.data_ptr()), local_rank,
-                _lib.C.c_void_p(stream.cuda_stream)))
-            launches += 1
-        st["launches"] = launches
-        return st
+    def step_device(qt, qp):
+        """The library's chain (ShardedIndex.retrieve_device_enqueue): scoring kernels, exchange, merge; no synchronisation."""
+        return sh.retrieve_device_enqueue(qt, qp, k, shift=shift_d, stream=stream, out=merged if world > 1 else None, work=work)
 
     def barrier():
         if world > 1:
@@ -333,36 +469,35 @@ def main():
     # kernel-path arm: queries resident in HBM
     for _ in range(args.warmup):
         step_device(q_tok, q_ptr)
+        sh.collect()
     exchange_check = None
-    if exch is not None:
+    if world > 1 and args.exchange == "p2p":
         # untimed self-check: the peer-memory exchange returns exactly what all_gather + bm25cu_topk_merge_device return
-        exch.check(stream.cuda_stream)
+        from bm25s_b200 import _lib
+
         g_ids = torch.empty((world, n_queries, k), dtype=torch.int32, device=device)
         g_sc = torch.empty((world, n_queries, k), dtype=torch.float32, device=device)
-        c_ids, c_sc = torch.empty_like(m_ids), torch.empty_like(m_sc)
-        dist.all_gather_into_tensor(g_ids.view(-1), out_ids.view(-1))
-        dist.all_gather_into_tensor(g_sc.view(-1), out_sc.view(-1))
+        c_ids, c_sc = torch.empty_like(merged[0]), torch.empty_like(merged[1])
+        dist.all_gather_into_tensor(g_ids.view(-1), work[0].view(-1))
+        dist.all_gather_into_tensor(g_sc.view(-1), work[1].view(-1))
         _lib.check(_lib.lib().bm25cu_topk_merge_device(
             _lib.C.c_void_p(g_ids.data_ptr()), _lib.C.c_void_p(g_sc.data_ptr()), world, n_queries, k,
             _lib.C.c_void_p(c_ids.data_ptr()), _lib.C.c_void_p(c_sc.data_ptr()), local_rank, _lib.C.c_void_p(stream.cuda_stream)))
         torch.cuda.synchronize()
-        exchange_check = bool(torch.equal(c_ids, m_ids) and torch.equal(c_sc.view(torch.int32), m_sc.view(torch.int32)))
+        exchange_check = bool(torch.equal(c_ids, merged[0]) and torch.equal(c_sc.view(torch.int32), merged[1].view(torch.int32)))
         del g_ids, g_sc, c_ids, c_sc
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for it in range(args.steps):
-        # p2p exchange: the steps are enqueued back to back, the last one collects the stats (one synchronisation)
-        st_i = step_device(q_tok, q_ptr, collect=(exch is None or it == args.steps - 1))
-        if st_i is not None:
-            stats_acc.append(st_i)
+        # the steps are enqueued back to back; per-step events split scoring from exchange + merge (+ waiting for peers)
+        ev[it][0].record()
+        step_device(q_tok, q_ptr)
+        ev[it][1].record()
     ev1.record()
     barrier()
-    if exch is not None:
-        exch.check(stream.cuda_stream)  # raises if a peer's rows never arrived
-    clocks = sampler.stop()
+    stats = sh.collect()  # one synchronisation; errors of the last call, stats of its scoring kernels
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], device=device, dtype=torch.float64)
     if world > 1:
@@ -370,20 +505,29 @@ def main():
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = n_queries / (ms_per_step / 1000.0)
+    step_ms_local = float(np.mean([ev[i][0].elapsed_time(ev[i][1]) for i in range(args.steps)]))
+    digest_device = digest_of(merged[0].cpu().numpy(), merged[1].cpu().numpy())
 
-    # end-to-end arm: HOST buffers in, host results out, through the C ABI call a binding makes
+    # a few separately collected steps: the library's own CUDA events around the scoring kernels (roofline), per rank
+    stats_acc = []
+    for _ in range(min(5, args.steps)):
+        barrier()
+        step_device(q_tok, q_ptr)
+        stats_acc.append(sh.collect())
+
+    # end-to-end arm: HOST buffers in, host results out
     q_tok_pin = torch.from_numpy(q_tok_h).pin_memory()
     q_ptr_pin = torch.from_numpy(q_ptr_h).pin_memory()
     res_pin_i = torch.empty((n_queries, k), dtype=torch.int32).pin_memory()
     res_pin_s = torch.empty((n_queries, k), dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        if world == 1:
-            ids, sc = dev.retrieve(q_tok_h, q_ptr_h, k, shift=shift_h)
-            return ids, sc
+        if world == 1:  # the C ABI call a binding makes: bm25cu_retrieve with host numpy arrays
+            return dev.retrieve(q_tok_h, q_ptr_h, k, shift=shift_h)
+        # N > 1: pinned host -> device copies, the library's sharded chain, device -> pinned host copies
         qt = q_tok_pin.to(device, non_blocking=True)
         qp = q_ptr_pin.to(device, non_blocking=True)
-        step_device(qt, qp)
+        m_ids, m_sc = sh.retrieve_device(qt, qp, k, shift=shift_d, stream=stream)
         res_pin_i.copy_(m_ids, non_blocking=True)
         res_pin_s.copy_(m_sc, non_blocking=True)
         torch.cuda.synchronize()
@@ -401,8 +545,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_qps = n_queries * args.steps / float(t.item())
-    h2d = n_q_tokens * 4 + (n_queries + 1) * 8 + (n_queries * 4 if shift_h is not None else 0)
+    clocks = sampler.stop()
+    h2d = n_q_tokens * 4 + (n_queries + 1) * 8 + (n_queries * 4 if shift_h is not None and world == 1 else 0)
     d2h = n_queries * k * 8
+    e2e_ids, e2e_sc = np.array(e2e_ids), np.array(e2e_sc)
+    digest = digest_of(e2e_ids, e2e_sc)
 
     # roofline of the dominant kernel (fused scoring + top-k), CUDA events inside the library on the launch stream
     fast_ms = float(np.mean([s["fast_kernel_ms"] for s in stats_acc]))
@@ -410,30 +557,45 @@ def main():
     alg_bytes = int(stats_acc[-1]["algorithmic_bytes"])
     peak, peak_src = peaks()
     achieved = alg_bytes / (fast_ms / 1000.0) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if world == 1 and args.shape == "msmarco" and k == 10 and os.path.exists(tpath):
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-            traffic = float(json.load(open(tpath))["dram_bytes_per_launch"])
+        try:
+            tj = json.load(open(tpath))
+            traffic = float(tj["dram_bytes_per_launch"])
+            traffic_src = ("stored constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the "
+                           "committed `ncu --set full` capture of this command (" + str(tj.get("source", "profiles/")) + ")")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel": ("retrieve_ms_kernel (+ ms_plan_kernel, ms_merge_kernel; retrieve_fast_kernel serves what it hands on)"
                            if ms_ms > 0 else "retrieve_fast_kernel"),
                 "kernel_ms": fast_ms, "ms_kernel_ms": ms_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
+    launches_per_step = int(stats_acc[-1]["launches"])
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "bm25cu_retrieve (host numpy arrays in/out)" if world == 1 else ("pinned H2D + retrieve_device + peer-memory exchange fused with the merge + D2H" if args.exchange == "p2p" else "pinned H2D + retrieve_device + all_gather + merge + D2H")},
-            "gpu_launches": int(sum(s["launches"] for s in stats_acc)) if exch is None else int(stats_acc[-1]["launches"]) * args.steps,
-            "roofline": roofline,
+                    "api": "bm25cu_retrieve (host numpy arrays in/out)" if world == 1 else
+                           "pinned H2D + ShardedIndex.retrieve_device (scoring kernels + " +
+                           ("peer-memory exchange fused with the merge" if args.exchange == "p2p" else "all_gather + merge") + ") + D2H"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "result_digest": digest, "result_digest_device_path": digest_device,
             "n_general": int(stats_acc[-1]["n_general"]), "nnz_local": int(nnz), "index_build_s": round(build_s, 3)}
     if world > 1:
         line["exchange"] = {"kind": args.exchange, "same_as_all_gather_merge": exchange_check}
+        # per-rank split of a step: scoring kernels (library events) and the whole chain; the difference is the exchange,
+        # the merge and the wait for the slowest shard
+        mine = torch.tensor([fast_ms, step_ms_local], device=device, dtype=torch.float64)
+        allr = torch.empty((world, 2), device=device, dtype=torch.float64)
+        dist.all_gather_into_tensor(allr.view(-1), mine)
+        allr = allr.cpu().numpy()
+        line["per_rank"] = {"kernel_ms": [round(float(x), 4) for x in allr[:, 0]], "step_ms": [round(float(x), 4) for x in allr[:, 1]],
+                            "kernel_ms_min": float(allr[:, 0].min()), "kernel_ms_max": float(allr[:, 0].max()),
+                            "exchange_merge_wait_ms": [round(float(b - a), 4) for a, b in allr]}
 
     if rank == 0 and world == 1:
         # the user-facing call, Python lists in -> numpy arrays out (BM25.retrieve of the mirror class,
@@ -457,18 +619,23 @@ def main():
                               "same_scores_as_e2e": bool(np.array_equal(res.scores, e2e_sc))}
         api._dev = None  # the handle belongs to this script
 
-    if rank == 0 and csc_host is not None:
-        cb, (n_s, ref_ids, ref_sc) = cpu_baseline(csc_host, q_tok_h, q_ptr_h, n_docs, k, shift_h, args.cpu_seconds)
-        line["cpu_baseline"] = cb
-        # parity spot-check at full size on the CPU sample: scores bit-equal, ids equal above the k-th score
-        ok = bool(np.array_equal(e2e_sc[:n_s], ref_sc))
-        for qi in range(n_s):
-            kth = ref_sc[qi, -1]
-            ok &= set(e2e_ids[qi][e2e_sc[qi] > kth].tolist()) == set(ref_ids[qi][ref_sc[qi] > kth].tolist())
-        line["parity_vs_cpu_port"] = {"queries": n_s, "ok": ok}
+    if want_cpu:
+        if csc_host is None and not local_shards(args, world):
+            csc_host, _ = unsharded_csc(args, device, local_rank)  # N > 1: rank 0 rebuilds the whole matrix, untimed
+        if csc_host is not None:
+            if args.parity_queries > 0:
+                line["parity_vs_cpu_port"] = oracle_parity(csc_host, q_tok_h, q_ptr_h, n_docs, k, shift_h, e2e_ids, e2e_sc, args.parity_queries)
+            if world == 1:
+                cb = port_baseline(csc_host, q_tok_h, q_ptr_h, n_docs, k, shift_h, args.cpu_seconds)
+                ref = None if args.no_reference_backends else reference_module()
+                if ref is not None:
+                    cb["reference_backends"] = reference_backends(ref, csc_host, no_h, n_docs, n_vocab, args.method, q_lists, k,
+                                                                  seconds=max(2.0, args.cpu_seconds / 3), ours=(e2e_ids, e2e_sc))
+                line["cpu_baseline"] = cb
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -198,6 +198,14 @@ class DeviceIndex:
                                           ptr(indptr, C.c_int64), ptr(nonocc, C.c_float)))
         return data, indices, indptr, nonocc
 
+    def download_nonocc(self):
+        """The non-occurrence array alone (float32[n_vocab]) or None."""
+        if not self.has_nonocc:
+            return None
+        nonocc = np.empty(self.n_vocab, np.float32)
+        check(lib().bm25cu_index_download(self._h, None, None, None, ptr(nonocc, C.c_float)))
+        return nonocc
+
     def retrieve(self, q_tokens, q_ptr, k, shift=None, mask=None, with_stats=False):
         q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
         q_ptr = np.ascontiguousarray(q_ptr, dtype=np.int64)

@@ -142,30 +142,74 @@ class ShardedIndex:
         torch.cuda.synchronize(dev_t)
         return self._exchange
 
-    def retrieve_device(self, q_tokens, q_ptr, k, shift=None, stream=None):
-        """torch CUDA tensors in (flat int32 token ids, int64 pointers, optional float32 shifts), merged
-        (ids int32[Q,k], scores float32[Q,k]) CUDA tensors out on every rank. One chain on `stream` (default: torch's
-        current stream): scoring kernels of this shard, stores into the peers' memory, merge. Returns after the
-        chain has been synchronised and the call's errors have been raised."""
+    def enable_nccl_exchange(self):
+        """The plain alternative to the peer-memory exchange: NCCL all_gather of the shards' rows + bm25cu_topk_merge_device
+        (what north_star describes; kept for comparison and for processes that cannot share CUDA IPC handles)."""
+        self._exchange = None
+        self._nccl_exchange = True
+
+    def retrieve_device_enqueue(self, q_tokens, q_ptr, k, shift=None, stream=None, out=None, work=None):
+        """The chain of `retrieve_device` without its synchronisation: scoring kernels of this shard, stores into the
+        peers' memory and the merge are enqueued on `stream` (default: torch's current stream) and the merged
+        (ids, scores) CUDA tensors are returned at once; call `collect` before reading them on the host. `out` / `work`:
+        optional preallocated (ids int32[Q,k], scores float32[Q,k]) pairs for the merged and the shard-local rows."""
         import torch
 
-        if getattr(self, "_exchange", None) is None and self.world > 1:
-            raise RuntimeError("call enable_peer_exchange(max_queries, k) on every rank first")
+        nccl = getattr(self, "_nccl_exchange", False)
+        if getattr(self, "_exchange", None) is None and self.world > 1 and not nccl:
+            raise RuntimeError("call enable_peer_exchange(max_queries, k) (or enable_nccl_exchange()) on every rank first")
         st = torch.cuda.current_stream() if stream is None else stream
         if getattr(self, "_stream_handle", None) != st.cuda_stream:
             self.dev.set_stream(st.cuda_stream)
             self._stream_handle = st.cuda_stream
         nq = int(q_ptr.numel()) - 1
         n_tok = int(q_tokens.numel())
-        ids = torch.empty((nq, k), dtype=torch.int32, device=q_ptr.device)
-        sc = torch.empty((nq, k), dtype=torch.float32, device=q_ptr.device)
+        if work is None:
+            work = (torch.empty((nq, k), dtype=torch.int32, device=q_ptr.device),
+                    torch.empty((nq, k), dtype=torch.float32, device=q_ptr.device))
+        ids, sc = work
         self.dev.retrieve_device_enqueue(q_tokens.data_ptr(), q_ptr.data_ptr(), nq, n_tok, k, ids.data_ptr(), sc.data_ptr(),
                                          shift_ptr=None if shift is None else shift.data_ptr())
+        self._pending = (nq, n_tok, k, st.cuda_stream)
         if self.world == 1:
-            self.dev.collect(nq, n_tok, k)
             return ids, sc
-        m_ids, m_sc = torch.empty_like(ids), torch.empty_like(sc)
-        self._exchange.merge(ids.data_ptr(), sc.data_ptr(), nq, k, m_ids.data_ptr(), m_sc.data_ptr(), st.cuda_stream)
-        self.dev.collect(nq, n_tok, k)
-        self._exchange.check(st.cuda_stream)
+        if out is None:
+            out = (torch.empty_like(ids), torch.empty_like(sc))
+        m_ids, m_sc = out
+        if self._exchange is not None:
+            self._exchange.merge(ids.data_ptr(), sc.data_ptr(), nq, k, m_ids.data_ptr(), m_sc.data_ptr(), st.cuda_stream)
+            return m_ids, m_sc
+        import torch.distributed as dist
+
+        from . import _lib
+
+        g_ids = torch.empty((self.world, nq, k), dtype=torch.int32, device=q_ptr.device)
+        g_sc = torch.empty((self.world, nq, k), dtype=torch.float32, device=q_ptr.device)
+        with torch.cuda.stream(st):
+            dist.all_gather_into_tensor(g_ids.view(-1), ids.view(-1), group=self.group)
+            dist.all_gather_into_tensor(g_sc.view(-1), sc.view(-1), group=self.group)
+        _lib.check(_lib.lib().bm25cu_topk_merge_device(
+            _lib.C.c_void_p(g_ids.data_ptr()), _lib.C.c_void_p(g_sc.data_ptr()), self.world, nq, k,
+            _lib.C.c_void_p(m_ids.data_ptr()), _lib.C.c_void_p(m_sc.data_ptr()), self.device, _lib.C.c_void_p(st.cuda_stream)))
         return m_ids, m_sc
+
+    def collect(self):
+        """Synchronise the chain enqueued last, raise its errors (token id out of range, a peer that never delivered)
+        and return the scoring kernels' stats."""
+        nq, n_tok, k, stream = self._pending
+        stats = self.dev.collect(nq, n_tok, k)
+        if self.world > 1 and self._exchange is not None:
+            self._exchange.check(stream)
+            stats["launches"] += 2  # push + merge
+        elif self.world > 1:
+            stats["launches"] += 1  # merge (the all_gather is NCCL's)
+        return stats
+
+    def retrieve_device(self, q_tokens, q_ptr, k, shift=None, stream=None):
+        """torch CUDA tensors in (flat int32 token ids, int64 pointers, optional float32 shifts), merged
+        (ids int32[Q,k], scores float32[Q,k]) CUDA tensors out on every rank. One chain on `stream` (default: torch's
+        current stream): scoring kernels of this shard, stores into the peers' memory, merge. Returns after the
+        chain has been synchronised and the call's errors have been raised."""
+        res = self.retrieve_device_enqueue(q_tokens, q_ptr, k, shift=shift, stream=stream)
+        self.collect()
+        return res

@@ -19,7 +19,10 @@ lo, hi = shard_bounds(n_docs, world, rank)
 tok_l = corp.tokens[corp.ptr[lo]:corp.ptr[hi]]
 ptr_l = corp.ptr[lo:hi + 1] - corp.ptr[lo]
 for method in ("lucene", "bm25+"):
-    sh = ShardedIndex.build(tok_l, ptr_l, n_vocab, method=method, rank=rank, world=world, device=local, doc_lo=lo)
+    # doc_lo given for one method, derived from the lower ranks' document counts for the other
+    sh = ShardedIndex.build(tok_l, ptr_l, n_vocab, method=method, rank=rank, world=world, device=local,
+                            doc_lo=lo if method == "lucene" else None)
+    assert sh.dev.doc_lo == lo
     data, indices, indptr, nonocc = O.build_index(corp.to_lists(), n_vocab, method)
     shift = None if nonocc is None else np.array([O.query_shift(nonocc, q) for q in qs.to_lists()], np.float32)
     qt, qp = torch.from_numpy(qs.tokens).to(dev_t), torch.from_numpy(qs.ptr).to(dev_t)
@@ -36,6 +39,9 @@ for method in ("lucene", "bm25+"):
             assert set(ids[q][rsc[q] > kth].tolist()) == set(rid[q][rsc[q] > kth].tolist()), (method, k, q)
         hid, hsc = sh.retrieve(qs.tokens, qs.ptr, k, shift=shift)  # host arrays, NCCL all_gather + merge
         assert np.array_equal(hsc, rsc) and np.array_equal(hid, ids), (method, k, "nccl path")
+    sh.enable_nccl_exchange()  # device tensors, NCCL all_gather + merge kernel instead of the peer-memory exchange
+    nid, nsc = sh.retrieve_device(qt, qp, 100, shift=sd)
+    assert np.array_equal(nsc.cpu().numpy(), rsc) and np.array_equal(nid.cpu().numpy(), ids), (method, "nccl device path")
     if rank == 0:
         print("sharded check ok:", method, "world", world)
 dist.barrier()
