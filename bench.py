@@ -482,6 +482,7 @@ def main():
         dist.all_gather_into_tensor(g_sc.view(-1), work[1].view(-1))
         _lib.check(_lib.lib().bm25cu_topk_merge_device(
             _lib.C.c_void_p(g_ids.data_ptr()), _lib.C.c_void_p(g_sc.data_ptr()), world, n_queries, k,
+            _lib.C.c_void_p(None if shift_d is None else shift_d.data_ptr()),
             _lib.C.c_void_p(c_ids.data_ptr()), _lib.C.c_void_p(c_sc.data_ptr()), local_rank, _lib.C.c_void_p(stream.cuda_stream)))
         torch.cuda.synchronize()
         exchange_check = bool(torch.equal(c_ids, merged[0]) and torch.equal(c_sc.view(torch.int32), merged[1].view(torch.int32)))

@@ -382,11 +382,13 @@ class PeerExchange:
         if barrier is not None:
             barrier()  # nobody may push before everybody has opened the buffers (the caller's job if no barrier is given)
 
-    def merge(self, ids_ptr, scores_ptr, n_queries, k, out_ids_ptr, out_scores_ptr, stream=0):
-        """All pointers are raw device addresses; enqueues two kernels on `stream` (a raw cudaStream_t), no sync."""
+    def merge(self, ids_ptr, scores_ptr, n_queries, k, out_ids_ptr, out_scores_ptr, stream=0, shift_ptr=None):
+        """All pointers are raw device addresses; enqueues two kernels on `stream` (a raw cudaStream_t), no sync.
+        `shift_ptr` (float32[n_queries] on the device or None): the BM25L / BM25+ shift, added after the merge - the
+        shards' rows must have been scored WITHOUT it."""
         check(lib().bm25cu_exchange_merge(self._h, C.c_void_p(ids_ptr), C.c_void_p(scores_ptr), C.c_int32(n_queries),
-                                          C.c_int32(k), C.c_void_p(out_ids_ptr), C.c_void_p(out_scores_ptr),
-                                          C.c_void_p(stream)))
+                                          C.c_int32(k), C.c_void_p(shift_ptr), C.c_void_p(out_ids_ptr),
+                                          C.c_void_p(out_scores_ptr), C.c_void_p(stream)))
 
     def check(self, stream=0):
         check(lib().bm25cu_exchange_check(self._h, C.c_void_p(stream)))

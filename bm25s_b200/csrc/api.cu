@@ -368,10 +368,10 @@ int bm25cu_topk_dense(const void *scores, int32_t is_f64, int64_t n, int32_t k, 
 }
 
 int bm25cu_topk_merge_device(const int32_t *ids, const float *scores, int32_t n_parts, int32_t n_queries, int32_t k,
-                             int32_t *out_ids, float *out_scores, int32_t device, void *stream) {
+                             const float *shift_per_query, int32_t *out_ids, float *out_scores, int32_t device, void *stream) {
     BM25CU_REQUIRE(n_parts >= 1 && n_queries >= 0 && k >= 0, "bm25cu_topk_merge: bad sizes");
     BM25CU_CHECK(cudaSetDevice(device));
-    int rc = topk_merge_device(ids, scores, n_parts, n_queries, k, out_ids, out_scores, (cudaStream_t)stream);
+    int rc = topk_merge_device(ids, scores, n_parts, n_queries, k, shift_per_query, out_ids, out_scores, (cudaStream_t)stream);
     if (rc) return rc;
     BM25CU_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     return BM25CU_OK;
@@ -394,7 +394,7 @@ int bm25cu_topk_merge(const int32_t *ids, const float *scores, int32_t n_parts, 
     if (e == cudaSuccess) e = cudaMemcpy(d_ids, ids, in_elems * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_sc, scores, in_elems * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        rc = topk_merge_device(d_ids, d_sc, n_parts, n_queries, k, d_oi, d_os, 0);
+        rc = topk_merge_device(d_ids, d_sc, n_parts, n_queries, k, nullptr, d_oi, d_os, 0);
         if (rc == BM25CU_OK) e = cudaStreamSynchronize(0);
         if (rc == BM25CU_OK && e == cudaSuccess) e = cudaMemcpy(out_ids, d_oi, out_elems * 4, cudaMemcpyDeviceToHost);
         if (rc == BM25CU_OK && e == cudaSuccess) e = cudaMemcpy(out_scores, d_os, out_elems * 4, cudaMemcpyDeviceToHost);

@@ -124,6 +124,9 @@ struct bm25cu_index {
     unsigned int *d_pbm = nullptr;      // presence bitmaps of the long columns (one bit per 2^s documents)
     long long *d_pbm_off = nullptr;     // i64[n_vocab] start (in 32-bit words) of a column's bitmap, -1: none
     unsigned char *d_pbm_sh = nullptr;  // u8[n_vocab] s
+    void *d_stab = nullptr;             // slot tables of the long columns: 32-byte buckets of four (doc id, score) slots
+    long long *d_stab_off = nullptr;    // i64[n_vocab] first bucket of a column's table, -1: none
+    unsigned char *d_stab_sh = nullptr; // u8[n_vocab] log2 of the bucket width in documents
     size_t aux_bytes = 0;               // bytes of the lookup structures derived at upload (bucket tables + presence bitmaps)
     bool nonneg = true;            // all data >= 0 and finite: the fused streaming kernel is exact
     int sm_count = 148;
@@ -131,6 +134,8 @@ struct bm25cu_index {
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stream_hi = nullptr;  // high-priority side stream: the CTA-wide half of retrieve_ms.cu runs next to the per-warp half
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,
         d_spill, d_order, d_theta, d_fb_list, d_ms_items, d_ms_rows, d_ms_q, d_ms_partial;
@@ -167,6 +172,8 @@ struct Ctrl {
     unsigned int ms_next;        // work-queue cursor of the list-at-a-time kernel (retrieve_ms.cu)
     unsigned int fb_count;       // queries that kernel handed on to the streaming kernel
     unsigned int ms_items;       // work items (query parts) of that kernel
+    unsigned int ms_heavy;       // the first ms_heavy items are served by a whole CTA, the rest one per warp
+    unsigned int msw_next;       // work-queue cursor of the per-warp kernel (counts from ms_heavy)
     unsigned int ms_rows;        // rows handed out in its partial-result buffer
     unsigned int ms_hist[64];    // parts per log2(cost) bucket, and the scatter cursors of the buckets (ms_plan_*_kernel)
     unsigned int ms_cursor[64];
@@ -185,7 +192,7 @@ int launch_scores_dense(bm25cu_index *ix, const int32_t *d_q, int32_t n_tokens, 
 int topk_dense_device(const void *d_scores, int is_f64, int64_t n, int32_t k, int64_t *d_out_ids, void *d_out_scores,
                       cudaStream_t stream);
 int topk_merge_device(const int32_t *ids, const float *scores, int32_t n_parts, int32_t n_queries, int32_t k,
-                      int32_t *out_ids, float *out_scores, cudaStream_t stream);
+                      const float *shift_or_null, int32_t *out_ids, float *out_scores, cudaStream_t stream);
 int finalize_index(bm25cu_index *ix);          // device attributes, events, non-negativity scan
 int alloc_postings(bm25cu_index *ix, int64_t nnz);  // d_data / d_indices with bulk-copy padding
 

@@ -71,25 +71,87 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const int32_t *__res
     }
 }
 
-__global__ void __launch_bounds__(256) exchange_merge_kernel(void *local, int world, long long cap, int parity, unsigned int epoch,
-                                                             int n_queries, int k, int P, int32_t *out_ids, float *out_scores,
-                                                             unsigned int *err) {
-    extern __shared__ unsigned char smem_raw[];
-    uint32_t *key = reinterpret_cast<uint32_t *>(smem_raw);
-    int32_t *id = reinterpret_cast<int32_t *>(key + P);
-    const ExchangeView v = view_of(local, world, cap);
+// Spin until the `world` per-source flags of this buffer parity reached the call's epoch (threads 0 .. world-1 of the
+// CTA, one flag each; 10 s without the peer's rows sets the error bit).
+__device__ __forceinline__ void wait_for_peers(const ExchangeView &v, int world, int parity, unsigned int epoch, unsigned int *err) {
     if (threadIdx.x < world) {
         volatile unsigned int *f = v.flags + parity * kMaxWorld + threadIdx.x;
         unsigned long long t0 = 0, now = 0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         while ((int)(*f - epoch) < 0) {
-            __nanosleep(200);
+            __nanosleep(100);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > 10000000000ull) { atomicOr(err, 1u); break; }  // 10 s: a peer never pushed
+            if (now - t0 > 10000000000ull) { atomicOr(err, 1u); break; }
         }
         __threadfence_system();
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long xshfl64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ unsigned long long xshfl64_xor(unsigned long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// k <= 32: one WARP per query. A row of a rank is loaded one pair per lane as a 64-bit key (order-preserving score key,
+// ~id: score descending, id ascending), sorted in the warp (rows arrive sorted by their pre-shift scores; the sort makes
+// the merge independent of that), and bitonic-merged into the running top-32 held one key per lane. The non-occurrence
+// shift of BM25L / BM25+ is added AFTER the merge, so the order - and with it the rows - do not depend on the number of
+// shards. Eight queries per CTA, one flag wait per CTA.
+__global__ void __launch_bounds__(256) exchange_merge_warp_kernel(void *local, int world, long long cap, int parity, unsigned int epoch,
+                                                                  int n_queries, int k, const float *__restrict__ shift,
+                                                                  int32_t *out_ids, float *out_scores, unsigned int *err) {
+    const ExchangeView v = view_of(local, world, cap);
+    wait_for_peers(v, world, parity, epoch, err);
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= n_queries) return;
+    const int32_t *ids = v.ids[parity];
+    const float *scores = v.scores[parity];
+    unsigned long long t = 0ull;
+    for (int r = 0; r < world; ++r) {
+        unsigned long long b = 0ull;
+        if (lane < k) {
+            const size_t src = (size_t)r * cap + (size_t)q * k + lane;
+            const int32_t d = __ldcv(ids + src);  // written by a peer: never from a stale cache line
+            if (d >= 0) b = ((unsigned long long)bm25cu::f32_key(__ldcv(scores + src)) << 32) | (unsigned int)(~d);
+        }
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const unsigned long long o = xshfl64_xor(b, stride);
+                const bool lower = (lane & stride) == 0, desc = (lane & size) == 0;
+                b = (lower == desc) ? (b > o ? b : o) : (b < o ? b : o);
+            }
+        }
+        const unsigned long long rb = xshfl64(b, 31 - lane);
+        t = t > rb ? t : rb;  // bitonic: the 32 largest of the union
+#pragma unroll
+        for (int stride = 16; stride > 0; stride >>= 1) {
+            const unsigned long long o = xshfl64_xor(t, stride);
+            t = ((lane & stride) == 0) ? (t > o ? t : o) : (t < o ? t : o);
+        }
+    }
+    if (lane < k) {
+        int32_t d = -1;
+        float sc = __int_as_float(0xff800000);
+        if (t != 0ull) {
+            const uint32_t kk = (uint32_t)(t >> 32);
+            sc = __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk);
+            if (shift != nullptr) sc = __fadd_rn(sc, shift[q]);
+            d = (int32_t)~(unsigned int)(t & 0xffffffffu);
+        }
+        out_ids[(size_t)q * k + lane] = d;
+        out_scores[(size_t)q * k + lane] = sc;
+    }
+}
+
+__global__ void __launch_bounds__(256) exchange_merge_kernel(void *local, int world, long long cap, int parity, unsigned int epoch,
+                                                             int n_queries, int k, int P, const float *__restrict__ shift,
+                                                             int32_t *out_ids, float *out_scores, unsigned int *err) {
+    extern __shared__ unsigned char smem_raw[];
+    uint32_t *key = reinterpret_cast<uint32_t *>(smem_raw);
+    int32_t *id = reinterpret_cast<int32_t *>(key + P);
+    const ExchangeView v = view_of(local, world, cap);
+    wait_for_peers(v, world, parity, epoch, err);
     const int q = blockIdx.x;
     const int total = world * k;
     const int32_t *ids = v.ids[parity];
@@ -112,7 +174,11 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(void *local, int wo
         int32_t d = id[j];
         float s;
         if (d == 0x7fffffff) { d = -1; s = __int_as_float(0xff800000); }
-        else { const uint32_t u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk; s = __uint_as_float(u); }
+        else {
+            const uint32_t u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk;
+            s = __uint_as_float(u);
+            if (shift != nullptr) s = __fadd_rn(s, shift[q]);
+        }
         out_ids[(size_t)q * k + j] = d;
         out_scores[(size_t)q * k + j] = s;
     }
@@ -188,7 +254,8 @@ int bm25cu_exchange_connect(bm25cu_exchange *x, const void *handles) {
 }
 
 int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const float *scores_device, int32_t n_queries,
-                          int32_t k, int32_t *out_ids_device, float *out_scores_device, void *stream) {
+                          int32_t k, const float *shift_per_query_device, int32_t *out_ids_device, float *out_scores_device,
+                          void *stream) {
     BM25CU_REQUIRE(x != nullptr, "bm25cu_exchange_merge: null handle");
     BM25CU_REQUIRE(x->connected || x->world == 1, "bm25cu_exchange_merge: bm25cu_exchange_connect has not been called");
     BM25CU_REQUIRE(n_queries >= 0 && k >= 0, "bm25cu_exchange_merge: negative size");
@@ -206,12 +273,18 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
     if (grid > 592) grid = 592;
     exchange_push_kernel<<<grid, 256, 0, st>>>(ids_device, scores_device, n, pp, x->rank, x->world, x->cap, parity, epoch, x->d_counter);
     BM25CU_CHECK(cudaGetLastError());
-    const int P = next_pow2(x->world * k);
-    const size_t smem = (size_t)P * 8;
-    BM25CU_REQUIRE(smem <= 200 * 1024, "bm25cu_exchange_merge: world * k too large for one CTA (max 25600 pairs)");
-    BM25CU_CHECK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    exchange_merge_kernel<<<n_queries, 256, smem, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k, P, out_ids_device,
-                                                       out_scores_device, x->d_counter + 1);
+    if (k <= 32) {
+        exchange_merge_warp_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k,
+                                                                       shift_per_query_device, out_ids_device, out_scores_device,
+                                                                       x->d_counter + 1);
+    } else {
+        const int P = next_pow2(x->world * k);
+        const size_t smem = (size_t)P * 8;
+        BM25CU_REQUIRE(smem <= 200 * 1024, "bm25cu_exchange_merge: world * k too large for one CTA (max 25600 pairs)");
+        BM25CU_CHECK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        exchange_merge_kernel<<<n_queries, 256, smem, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k, P,
+                                                           shift_per_query_device, out_ids_device, out_scores_device, x->d_counter + 1);
+    }
     BM25CU_CHECK(cudaGetLastError());
     return BM25CU_OK;
 }

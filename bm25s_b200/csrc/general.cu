@@ -202,7 +202,7 @@ int topk_dense_device(const void *d_scores, int is_f64, int64_t n, int32_t k, in
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const int32_t *__restrict__ ids, const float *__restrict__ scores, int n_parts, int n_queries, int k,
-                  int P, int32_t *out_ids, float *out_scores) {
+                  int P, const float *__restrict__ shift, int32_t *out_ids, float *out_scores) {
     extern __shared__ unsigned char smem_raw[];
     uint32_t *key = reinterpret_cast<uint32_t *>(smem_raw);
     int32_t *id = reinterpret_cast<int32_t *>(key + P);
@@ -227,20 +227,24 @@ topk_merge_kernel(const int32_t *__restrict__ ids, const float *__restrict__ sco
         int32_t d = id[j];
         float s;
         if (d == 0x7fffffff) { d = -1; s = __int_as_float(0xff800000); }
-        else { uint32_t u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk; s = __uint_as_float(u); }
+        else {
+            uint32_t u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk;
+            s = __uint_as_float(u);
+            if (shift != nullptr) s = __fadd_rn(s, shift[q]);  // BM25L / BM25+: after the merge, so the order does not depend on n_parts
+        }
         out_ids[(size_t)q * k + j] = d;
         out_scores[(size_t)q * k + j] = s;
     }
 }
 
 int topk_merge_device(const int32_t *ids, const float *scores, int32_t n_parts, int32_t n_queries, int32_t k,
-                      int32_t *out_ids, float *out_scores, cudaStream_t stream) {
+                      const float *shift, int32_t *out_ids, float *out_scores, cudaStream_t stream) {
     if (n_queries == 0 || k == 0) return BM25CU_OK;
     const int P = next_pow2(n_parts * k);
     const size_t smem = (size_t)P * 8;
     BM25CU_REQUIRE(smem <= 200 * 1024, "bm25cu_topk_merge: n_parts * k too large for one CTA (max 25600 pairs)");
     BM25CU_CHECK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_merge_kernel<<<n_queries, 256, smem, stream>>>(ids, scores, n_parts, n_queries, k, P, out_ids, out_scores);
+    topk_merge_kernel<<<n_queries, 256, smem, stream>>>(ids, scores, n_parts, n_queries, k, P, shift, out_ids, out_scores);
     BM25CU_CHECK(cudaGetLastError());
     return BM25CU_OK;
 }

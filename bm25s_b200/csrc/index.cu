@@ -343,6 +343,101 @@ static int build_presence_bitmaps(bm25cu_index *ix) {
     return BM25CU_OK;
 }
 
+// ---- slot tables of the long columns (positive lookups of retrieve_ms.cu in ONE load) ------------------------------
+// A column with df >= kBtabMinDf gets a direct-mapped table over buckets of 2^s consecutive document ids, s the largest
+// shift that keeps the average bucket at `load` / 10 postings or fewer (default 2.0: between 1 and 2 postings per bucket).
+// A bucket is one 32-byte sector: four (doc id, score) slots in document order, empty slots hold id 0xffffffff. A bucket
+// that would need more than four slots keeps its first four and sets bit 31 of slot 0's id: "look in the column itself".
+// lookup(d) = one sector load instead of the chain bucket table -> id slice -> score. Derived at upload, not part of the
+// saved index; 16 .. 32 bytes per posting (2 .. 4 times the index: HBM capacity traded for latency, knob STAB=0 drops it).
+__device__ __forceinline__ int stab_shift_of(long long df, int n_docs, int load10) {
+    int s = 0;
+    while (s < 30 && ((df * 10) << (s + 1)) <= (long long)load10 * (long long)n_docs) ++s;
+    return s;
+}
+
+__global__ void stab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_vocab, int32_t n_docs, int load10, long long *sizes,
+                                 unsigned char *shifts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_vocab) return;
+    const long long df = indptr[t + 1] - indptr[t];
+    long long sz = 0;
+    int sh = 0;
+    if (df >= kBtabMinDf) {
+        sh = stab_shift_of(df, n_docs, load10);
+        sz = ((long long)(n_docs - 1) >> sh) + 1;  // buckets
+    }
+    sizes[t] = sz;
+    shifts[t] = (unsigned char)sh;
+}
+
+// one warp per column; rows of a column ascend, so the postings of a bucket are neighbours: a posting's slot is the
+// number of predecessors in its bucket, and the posting in slot 0 sees the overflow by looking four postings ahead
+__global__ void stab_fill_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices, const int64_t *__restrict__ indptr,
+                                 int32_t n_vocab, const unsigned char *__restrict__ shifts, long long *offs /* in: scan, out: -1 for none */,
+                                 uint2 *slots) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_vocab) return;
+    const long long beg = indptr[warp], df = indptr[warp + 1] - beg;
+    if (df < kBtabMinDf) {
+        __syncwarp();
+        if (lane == 0) offs[warp] = -1;
+        return;
+    }
+    const int sh = shifts[warp];
+    uint2 *tab = slots + offs[warp] * 4;
+    const int32_t *col = indices + beg;
+    for (long long i = lane; i < df; i += 32) {
+        const int32_t d = col[i];
+        const unsigned b = (unsigned)d >> sh;
+        int rank = 0;
+        while (rank < 4 && i - rank - 1 >= 0 && ((unsigned)col[i - rank - 1] >> sh) == b) ++rank;
+        if (rank >= 4) continue;  // overflow: found through the column itself
+        unsigned id = (unsigned)d;
+        if (rank == 0 && i + 4 < df && ((unsigned)col[i + 4] >> sh) == b) id |= 0x80000000u;
+        tab[(size_t)b * 4 + rank] = make_uint2(id, __float_as_uint(data[beg + i]));
+    }
+}
+
+static int build_slot_tables(bm25cu_index *ix) {
+    if (ix->n_vocab <= 0 || ix->nnz <= 0 || ix->n_docs <= 0) return BM25CU_OK;
+    if (ix->knobs.get("STAB", 1) == 0 || ix->d_btab == nullptr) return BM25CU_OK;  // overflowing buckets need the bucket tables
+    long long *d_sizes = nullptr, *d_tmp = nullptr;
+    const int V = ix->n_vocab;
+    BM25CU_CHECK(cudaMalloc(&d_sizes, (size_t)V * sizeof(long long)));
+    BM25CU_CHECK(cudaMalloc(&d_tmp, scan_tmp_elems(V) * sizeof(long long)));
+    BM25CU_CHECK(cudaMalloc(&ix->d_stab_off, (size_t)(V + 1) * sizeof(long long)));
+    BM25CU_CHECK(cudaMalloc(&ix->d_stab_sh, (size_t)V));
+    int load10 = ix->knobs.get("STAB_LOAD", 20);  // average postings per bucket, times ten, at most
+    if (load10 < 5) load10 = 5;
+    if (load10 > 40) load10 = 40;
+    stab_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, load10, d_sizes, ix->d_stab_sh);
+    BM25CU_CHECK(cudaGetLastError());
+    BM25CU_CHECK(exclusive_scan<long long>(d_sizes, V, ix->d_stab_off, d_tmp, ix->stream));
+    long long total = 0;
+    BM25CU_CHECK(cudaMemcpyAsync(&total, ix->d_stab_off + V, sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
+    BM25CU_CHECK(cudaStreamSynchronize(ix->stream));
+    cudaFree(d_sizes);
+    cudaFree(d_tmp);
+    const size_t bytes = (size_t)(total > 0 ? total : 1) * 32;
+    cudaError_t e = cudaMalloc(&ix->d_stab, bytes);
+    if (e != cudaSuccess) {  // not enough HBM for the tables: lookups take the bucket-table path
+        cudaGetLastError();
+        cudaFree(ix->d_stab_off); ix->d_stab_off = nullptr;
+        cudaFree(ix->d_stab_sh); ix->d_stab_sh = nullptr;
+        ix->d_stab = nullptr;
+        return BM25CU_OK;
+    }
+    BM25CU_CHECK(cudaMemsetAsync(ix->d_stab, 0xff, bytes, ix->stream));
+    const long long threads = (long long)V * 32;
+    stab_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ix->stream>>>(ix->d_data, ix->d_indices, ix->d_indptr, V, ix->d_stab_sh,
+                                                                                ix->d_stab_off, reinterpret_cast<uint2 *>(ix->d_stab));
+    BM25CU_CHECK(cudaGetLastError());
+    ix->aux_bytes += bytes;
+    return BM25CU_OK;
+}
+
 int finalize_index(bm25cu_index *ix) {
     ix->knobs.load_env();  // the one place the BM25CU_* environment is read for this handle
     cudaDeviceProp prop;
@@ -350,6 +445,13 @@ int finalize_index(bm25cu_index *ix) {
     ix->sm_count = prop.multiProcessorCount;
     ix->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     for (int i = 0; i < 6; ++i) BM25CU_CHECK(cudaEventCreate(&ix->ev[i]));
+    {
+        int least = 0, greatest = 0;
+        BM25CU_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        BM25CU_CHECK(cudaStreamCreateWithPriority(&ix->stream_hi, cudaStreamNonBlocking, greatest));
+        BM25CU_CHECK(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
+        BM25CU_CHECK(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
+    }
     unsigned int *d_flag = nullptr;
     BM25CU_CHECK(cudaMalloc(&d_flag, sizeof(unsigned int)));
     BM25CU_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(unsigned int), ix->stream));
@@ -378,10 +480,13 @@ int finalize_index(bm25cu_index *ix) {
         auto t1 = now();
         if ((rc_bt = build_presence_bitmaps(ix))) return rc_bt;
         auto t2 = now();
+        if ((rc_bt = build_slot_tables(ix))) return rc_bt;
+        auto t3 = now();
         if (timing)
-            fprintf(stderr, "[bm25cu] bucket tables %.1f ms, presence bitmaps %.1f ms, %.1f MB\n",
+            fprintf(stderr, "[bm25cu] bucket tables %.1f ms, presence bitmaps %.1f ms, slot tables %.1f ms, %.1f MB\n",
                     std::chrono::duration<double, std::milli>(t1 - t0).count(),
-                    std::chrono::duration<double, std::milli>(t2 - t1).count(), ix->aux_bytes / 1e6);
+                    std::chrono::duration<double, std::milli>(t2 - t1).count(),
+                    std::chrono::duration<double, std::milli>(t3 - t2).count(), ix->aux_bytes / 1e6);
     }
     unsigned int flag = 0;
     BM25CU_CHECK(cudaMemcpyAsync(&flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost, ix->stream));
@@ -415,6 +520,9 @@ static void destroy(bm25cu_index *ix) {
     cudaFree(ix->d_pbm);
     cudaFree(ix->d_pbm_off);
     cudaFree(ix->d_pbm_sh);
+    cudaFree(ix->d_stab);
+    cudaFree(ix->d_stab_off);
+    cudaFree(ix->d_stab_sh);
     bm25cu::DevBuf *bufs[] = {&ix->d_qtok, &ix->d_qptr, &ix->d_shift, &ix->d_mask, &ix->d_out_ids, &ix->d_out_scores,
                               &ix->d_ctrl, &ix->d_general_list, &ix->d_scratch, &ix->d_spill, &ix->d_order, &ix->d_theta, &ix->d_fb_list, &ix->d_ms_items, &ix->d_ms_rows, &ix->d_ms_q, &ix->d_ms_partial};
     for (auto *b : bufs) b->release();
@@ -422,6 +530,9 @@ static void destroy(bm25cu_index *ix) {
     ix->h_out.release();
     for (int i = 0; i < 6; ++i)
         if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+    if (ix->stream_hi) { cudaStreamSynchronize(ix->stream_hi); cudaStreamDestroy(ix->stream_hi); }
+    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
+    if (ix->ev_join) cudaEventDestroy(ix->ev_join);
     if (ix->stream && ix->owns_stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }

@@ -101,9 +101,11 @@ class ShardedIndex:
         import torch
         import torch.distributed as dist
 
-        ids, sc = self.dev.retrieve(q_tokens, q_ptr, k, shift=shift)
         if self.world == 1:
-            return ids, sc
+            return self.dev.retrieve(q_tokens, q_ptr, k, shift=shift)
+        # shards score WITHOUT the BM25L / BM25+ shift; it is added after the merge, so the merged order (and with it the
+        # rows) does not depend on the number of shards
+        ids, sc = self.dev.retrieve(q_tokens, q_ptr, k)
         nccl = dist.get_backend(self.group) == "nccl"
         dev_t = torch.device("cuda", self.device) if nccl else torch.device("cpu")
         ti, ts = torch.from_numpy(ids).to(dev_t), torch.from_numpy(sc).to(dev_t)
@@ -113,7 +115,11 @@ class ShardedIndex:
         dist.all_gather_into_tensor(gs.view(-1), ts.view(-1), group=self.group)
         from ._lib import topk_merge
 
-        return topk_merge(gi.cpu().numpy(), gs.cpu().numpy(), device=self.device)
+        m_ids, m_sc = topk_merge(gi.cpu().numpy(), gs.cpu().numpy(), device=self.device)
+        if shift is not None:
+            valid = m_ids >= 0
+            m_sc = np.where(valid, (m_sc + np.asarray(shift, np.float32)[:, None]).astype(np.float32), m_sc)
+        return m_ids, m_sc
 
     # ---- device-resident path: queries and results stay in HBM, the exchange runs over NVLink peer memory -------------
     def enable_peer_exchange(self, max_queries: int, k: int):
@@ -168,8 +174,10 @@ class ShardedIndex:
             work = (torch.empty((nq, k), dtype=torch.int32, device=q_ptr.device),
                     torch.empty((nq, k), dtype=torch.float32, device=q_ptr.device))
         ids, sc = work
+        shift_ptr = None if shift is None else shift.data_ptr()
+        # world > 1: the shard scores without the shift, the merge adds it (same rows whatever the number of shards)
         self.dev.retrieve_device_enqueue(q_tokens.data_ptr(), q_ptr.data_ptr(), nq, n_tok, k, ids.data_ptr(), sc.data_ptr(),
-                                         shift_ptr=None if shift is None else shift.data_ptr())
+                                         shift_ptr=shift_ptr if self.world == 1 else None)
         self._pending = (nq, n_tok, k, st.cuda_stream)
         if self.world == 1:
             return ids, sc
@@ -177,7 +185,8 @@ class ShardedIndex:
             out = (torch.empty_like(ids), torch.empty_like(sc))
         m_ids, m_sc = out
         if self._exchange is not None:
-            self._exchange.merge(ids.data_ptr(), sc.data_ptr(), nq, k, m_ids.data_ptr(), m_sc.data_ptr(), st.cuda_stream)
+            self._exchange.merge(ids.data_ptr(), sc.data_ptr(), nq, k, m_ids.data_ptr(), m_sc.data_ptr(), st.cuda_stream,
+                                 shift_ptr=shift_ptr)
             return m_ids, m_sc
         import torch.distributed as dist
 
@@ -189,7 +198,7 @@ class ShardedIndex:
             dist.all_gather_into_tensor(g_ids.view(-1), ids.view(-1), group=self.group)
             dist.all_gather_into_tensor(g_sc.view(-1), sc.view(-1), group=self.group)
         _lib.check(_lib.lib().bm25cu_topk_merge_device(
-            _lib.C.c_void_p(g_ids.data_ptr()), _lib.C.c_void_p(g_sc.data_ptr()), self.world, nq, k,
+            _lib.C.c_void_p(g_ids.data_ptr()), _lib.C.c_void_p(g_sc.data_ptr()), self.world, nq, k, _lib.C.c_void_p(shift_ptr),
             _lib.C.c_void_p(m_ids.data_ptr()), _lib.C.c_void_p(m_sc.data_ptr()), self.device, _lib.C.c_void_p(st.cuda_stream)))
         return m_ids, m_sc
 

@@ -162,8 +162,11 @@ int bm25cu_topk_dense(const void *scores, int32_t is_f64, int64_t n, int32_t k, 
  * single-process); order is score descending, id ascending, independent of n_parts. */
 int bm25cu_topk_merge(const int32_t *ids, const float *scores, int32_t n_parts, int32_t n_queries, int32_t k,
                       int32_t *out_ids, float *out_scores, int32_t device);
+/* _device: all pointers are device pointers; `shift_per_query` (float32[n_queries] or NULL) is the BM25L / BM25+ shift,
+ * added AFTER the merge: shards score WITHOUT it, so the merged order - and the rows - do not depend on n_parts. */
 int bm25cu_topk_merge_device(const int32_t *ids, const float *scores, int32_t n_parts, int32_t n_queries, int32_t k,
-                             int32_t *out_ids, float *out_scores, int32_t device, void *stream);
+                             const float *shift_per_query, int32_t *out_ids, float *out_scores, int32_t device,
+                             void *stream);
 
 /*
  * Exchange of the shards' top-k rows over NVLink peer memory, fused with the merge (doc-range sharding over the GPUs of
@@ -172,8 +175,9 @@ int bm25cu_topk_merge_device(const int32_t *ids, const float *scores, int32_t n_
  * n_queries * k result elements, publishes its bm25cu_exchange_handle (bm25cu_exchange_handle_size() opaque bytes,
  * a CUDA IPC handle) to the others by any means (torch.distributed, MPI, a file), connects with the world handles
  * (rank-major, its own slot is ignored) and, after a barrier, calls bm25cu_exchange_merge once per batch on every rank:
- * the local rows (device pointers, as written by bm25cu_retrieve_device) are stored into every peer's buffer, and the
- * merged rows [n_queries][k] (score descending, id ascending) appear in out_* on every rank. Two kernels on `stream`,
+ * the local rows (device pointers, as written by bm25cu_retrieve_device WITHOUT a shift) are stored into every peer's
+ * buffer, and the merged rows [n_queries][k] (score descending, id ascending; the BM25L / BM25+ shift, if given, added
+ * after the merge) appear in out_* on every rank. Two kernels on `stream`,
  * nothing is synchronised; bm25cu_exchange_check synchronises and reports a peer that never delivered.
  */
 typedef struct bm25cu_exchange bm25cu_exchange;
@@ -182,7 +186,8 @@ int bm25cu_exchange_handle_size(void);
 int bm25cu_exchange_handle(bm25cu_exchange *x, void *handle_out);
 int bm25cu_exchange_connect(bm25cu_exchange *x, const void *handles);
 int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const float *scores_device, int32_t n_queries,
-                          int32_t k, int32_t *out_ids_device, float *out_scores_device, void *stream);
+                          int32_t k, const float *shift_per_query_device, int32_t *out_ids_device,
+                          float *out_scores_device, void *stream);
 int bm25cu_exchange_check(bm25cu_exchange *x, void *stream);
 int bm25cu_exchange_free(bm25cu_exchange *x);
 

@@ -194,7 +194,12 @@ def test_random_corpus_vs_c_oracle(k):
                 {"BM25CU_MS": "0", "BM25CU_THREADS": "128", "BM25CU_PRUNE": "0"}, {"BM25CU_MS": "0", "BM25CU_THREADS": "1024"},
                 {"BM25CU_MS_MAXPARTS": "1"}, {"BM25CU_MS_PARTCOST": "512"}, {"BM25CU_MS_PARTCOST": "2000", "BM25CU_MS_MAXPARTS": "255"},
                 {"BM25CU_MS_BUDGET": "64"}, {"BM25CU_MS_BUDGET": "600", "BM25CU_MS_PARTCOST": "4096"},
-                {"BM25CU_MS_BTAB": "0"}, {"BM25CU_MS_PBM": "0"}, {"BM25CU_MS_BTAB": "0", "BM25CU_MS_PBM": "0", "BM25CU_SEED_KTH": "0"}):
+                {"BM25CU_MS_BTAB": "0"}, {"BM25CU_MS_PBM": "0"}, {"BM25CU_MS_BTAB": "0", "BM25CU_MS_PBM": "0", "BM25CU_SEED_KTH": "0"},
+                # the per-warp kernel (light items): off, everything light, two survivors per lane, light items cut into
+                # parts, light items over the survivor budget (handed on), lookups without tables
+                {"MS_LIGHT": 0}, {"MS_LIGHT": 40}, {"MS_LIGHT": 40, "MSW_R": 2}, {"MS_LIGHT": 40, "MS_PARTCOST": 512, "MS_MAXPARTS": 64},
+                {"MS_LIGHT": 40, "MSW_R": 2, "MS_PARTCOST": 2000, "MS_MAXPARTS": 255}, {"MS_LIGHT": 40, "MS_BUDGET": 64},
+                {"MS_LIGHT": 40, "MS_BTAB": 0, "MS_PBM": 0, "SEED_KTH": 0}, {"MS_LIGHT": 8}, {"MS_LIGHT": 40, "MSW_CTAS": 1}):
         with dev.options(**env):
             ids2, sc2 = dev.retrieve(flat, ptr, k, shift=sh)
         np.testing.assert_array_equal(sc2, sc)
@@ -388,16 +393,18 @@ def test_full_size_against_the_oracle(shape, method, k, n_queries):
     ix.close()
 
 
-def test_peer_exchange_single_rank_epochs():
-    """bm25cu_exchange_* with world = 1 (all a one-GPU box can run; bench.py checks N > 1 against all_gather + merge): the
-    push + merge kernels return the rows in (score desc, id asc) order, call after call (both buffer parities), and
-    rows with fewer than k valid entries keep their -1 / -inf tail."""
+@pytest.mark.parametrize("k", [10, 32, 40])
+def test_peer_exchange_single_rank_epochs(k):
+    """bm25cu_exchange_* with world = 1 (all a one-GPU box can run; bench.py checks N > 1 against all_gather + merge and
+    the oracle): the push + merge kernels - one warp per query for k <= 32, one CTA per query above - return the rows in
+    (score desc, id asc) order, call after call (both buffer parities), rows with fewer than k valid entries keep their
+    -1 / -inf tail, and the BM25L / BM25+ shift is added after the merge (valid entries only)."""
     import torch
 
     from bm25s_b200 import _lib
 
     dev_t = torch.device("cuda")
-    Q, k = 37, 10
+    Q = 37
     g = torch.Generator(device="cpu").manual_seed(5)
     ex = _lib.PeerExchange(0, 0, 1, Q * k, lambda b: [b])
     for call in range(5):
@@ -405,11 +412,16 @@ def test_peer_exchange_single_rank_epochs():
         ids = torch.stack([torch.randperm(1000, generator=g)[:k] for _ in range(Q)]).to(torch.int32)
         ids[3, 6:] = -1
         sc[3, 6:] = float("-inf")
+        shift = torch.rand(Q, generator=g) if call % 2 else None
         d_ids, d_sc = ids.to(dev_t), sc.to(dev_t)
+        d_shift = None if shift is None else shift.to(dev_t)
         o_ids, o_sc = torch.empty_like(d_ids), torch.empty_like(d_sc)
-        ex.merge(d_ids.data_ptr(), d_sc.data_ptr(), Q, k, o_ids.data_ptr(), o_sc.data_ptr(), 0)
+        ex.merge(d_ids.data_ptr(), d_sc.data_ptr(), Q, k, o_ids.data_ptr(), o_sc.data_ptr(), 0,
+                 shift_ptr=None if d_shift is None else d_shift.data_ptr())
         ex.check(0)
         ref_i, ref_s = _lib.topk_merge(ids.numpy()[None], sc.numpy()[None], device=0)
+        if shift is not None:
+            ref_s = np.where(ref_i >= 0, (ref_s + shift.numpy()[:, None]).astype(np.float32), ref_s)
         np.testing.assert_array_equal(o_ids.cpu().numpy(), ref_i, err_msg=f"call {call}")
         np.testing.assert_array_equal(o_sc.cpu().numpy(), ref_s, err_msg=f"call {call}")
     ex.close()
@@ -486,7 +498,8 @@ def test_tie_heavy_corpus(k):
         n_tail = int((sc[q] == sc[q][-1]).sum())
         assert set(ids[q][sc[q] == sc[q][-1]].tolist()) == set(tail[:n_tail].tolist()), q
     for env in ({"BM25CU_MS": "0"}, {"BM25CU_MS_MAXPARTS": "1"}, {"BM25CU_MS_PARTCOST": "256", "BM25CU_MS_MAXPARTS": "64"},
-                {"BM25CU_SEED_KTH": "0"}, {"BM25CU_MS_PBM": "0", "BM25CU_MS_BTAB": "0"}):
+                {"BM25CU_SEED_KTH": "0"}, {"BM25CU_MS_PBM": "0", "BM25CU_MS_BTAB": "0"},
+                {"MS_LIGHT": 0}, {"MS_LIGHT": 40}, {"MS_LIGHT": 40, "MSW_R": 2, "MS_PARTCOST": 256, "MS_MAXPARTS": 64}):
         with dev.options(**env):
             ids2, sc2 = dev.retrieve(flat, ptr, k)
         np.testing.assert_array_equal(sc2, sc, err_msg=str(env))
