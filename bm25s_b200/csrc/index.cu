@@ -345,13 +345,19 @@ static int build_presence_bitmaps(bm25cu_index *ix) {
 
 // ---- slot tables of the long columns (positive lookups of retrieve_ms.cu in ONE load) ------------------------------
 // A column with df >= kBtabMinDf gets a direct-mapped table over buckets of 2^s consecutive document ids, s the largest
-// shift that keeps the average bucket at `load` / 10 postings or fewer (default 2.0: between 1 and 2 postings per bucket).
-// A bucket is one 32-byte sector: four (doc id, score) slots in document order, empty slots hold id 0xffffffff. A bucket
-// that would need more than four slots keeps its first four and sets bit 31 of slot 0's id: "look in the column itself".
-// lookup(d) = one sector load instead of the chain bucket table -> id slice -> score. Derived at upload, not part of the
-// saved index; 16 .. 32 bytes per posting (2 .. 4 times the index: HBM capacity traded for latency, knob STAB=0 drops it).
+// shift that keeps the average bucket at `load` / 10 postings or fewer (default 3.0: between 1.5 and 3 per bucket).
+// A bucket is 64 bytes: two 32-byte sectors, one per HALF of the bucket's document range, of four (doc id, score) slots
+// each; empty slots hold id 0xffffffff. A document is looked up in the sector of its half - one load. A half with more
+// than four postings keeps four and lends the rest to the free slots of the other sector (filled from the top): bit 31 of
+// slot 0's id says "look at the other sector, too" (the same 64-byte line); if they did not fit there either, bit 31 of
+// slot 1's id says "look in the column itself" (about one lookup in a hundred). Replaces the chain bucket table -> id
+// slice -> score. Derived at upload, not part of the saved index; 21 .. 43 bytes per posting (HBM capacity traded for
+// latency; knob STAB=0 drops the tables, STAB_LOAD sizes them).
+constexpr int kStabSlots = 8;
+constexpr int kStabScan = 24;  // postings of one bucket looked at by the fill kernel; longer buckets overflow to the column
+
 __device__ __forceinline__ int stab_shift_of(long long df, int n_docs, int load10) {
-    int s = 0;
+    int s = 1;  // a bucket spans at least two documents: one per half
     while (s < 30 && ((df * 10) << (s + 1)) <= (long long)load10 * (long long)n_docs) ++s;
     return s;
 }
@@ -371,8 +377,9 @@ __global__ void stab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_v
     shifts[t] = (unsigned char)sh;
 }
 
-// one warp per column; rows of a column ascend, so the postings of a bucket are neighbours: a posting's slot is the
-// number of predecessors in its bucket, and the posting in slot 0 sees the overflow by looking four postings ahead
+// One warp per column, one lane per posting. Rows of a column ascend, so the postings of a bucket are neighbours and the
+// postings of its lower half come first: a lane finds its bucket's extent, the two halves' counts and its own rank by
+// looking at most kStabScan postings back and ahead, and derives its slot (or none) and the flags from those alone.
 __global__ void stab_fill_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices, const int64_t *__restrict__ indptr,
                                  int32_t n_vocab, const unsigned char *__restrict__ shifts, long long *offs /* in: scan, out: -1 for none */,
                                  uint2 *slots) {
@@ -386,17 +393,38 @@ __global__ void stab_fill_kernel(const float *__restrict__ data, const int32_t *
         return;
     }
     const int sh = shifts[warp];
-    uint2 *tab = slots + offs[warp] * 4;
+    uint2 *tab = slots + offs[warp] * kStabSlots;
     const int32_t *col = indices + beg;
     for (long long i = lane; i < df; i += 32) {
         const int32_t d = col[i];
         const unsigned b = (unsigned)d >> sh;
-        int rank = 0;
-        while (rank < 4 && i - rank - 1 >= 0 && ((unsigned)col[i - rank - 1] >> sh) == b) ++rank;
-        if (rank >= 4) continue;  // overflow: found through the column itself
+        const int h = (int)(((unsigned)d >> (sh - 1)) & 1u);
+        int before = 0, before_same = 0;  // postings of this bucket in front of this one; those of its own half
+        while (before < kStabScan && i - before - 1 >= 0 && ((unsigned)col[i - before - 1] >> sh) == b) {
+            if ((int)(((unsigned)col[i - before - 1] >> (sh - 1)) & 1u) == h) ++before_same;
+            ++before;
+        }
+        int after = 0, after_same = 0;
+        while (after < kStabScan && i + after + 1 < df && ((unsigned)col[i + after + 1] >> sh) == b) {
+            if ((int)(((unsigned)col[i + after + 1] >> (sh - 1)) & 1u) == h) ++after_same;
+            ++after;
+        }
+        const bool huge = before >= kStabScan || after >= kStabScan;  // extent unknown: everything past four per half overflows to the column
+        const int mine = before_same + 1 + after_same;                 // postings of this half
+        const int other = before + after + 1 - mine;                   // postings of the other half
+        const int rank = before_same;
+        const int room = other >= 4 ? 0 : 4 - other;                   // free slots of the other sector
+        const int extra = mine > 4 ? mine - 4 : 0;
+        const bool fits = !huge && extra <= room;
+        uint2 *sec = tab + (size_t)b * kStabSlots;
         unsigned id = (unsigned)d;
-        if (rank == 0 && i + 4 < df && ((unsigned)col[i + 4] >> sh) == b) id |= 0x80000000u;
-        tab[(size_t)b * 4 + rank] = make_uint2(id, __float_as_uint(data[beg + i]));
+        if (rank < 4) {
+            if (rank == 0 && extra > 0) id |= 0x80000000u;           // look at the other sector, too
+            if (rank == 1 && extra > 0 && !fits) id |= 0x80000000u;  // ... and in the column itself
+            sec[h * 4 + rank] = make_uint2(id, __float_as_uint(data[beg + i]));
+        } else if (!huge && rank - 4 < room) {
+            sec[(1 - h) * 4 + 3 - (rank - 4)] = make_uint2(id, __float_as_uint(data[beg + i]));  // lent slot, from the top
+        }
     }
 }
 
@@ -409,9 +437,9 @@ static int build_slot_tables(bm25cu_index *ix) {
     BM25CU_CHECK(cudaMalloc(&d_tmp, scan_tmp_elems(V) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_stab_off, (size_t)(V + 1) * sizeof(long long)));
     BM25CU_CHECK(cudaMalloc(&ix->d_stab_sh, (size_t)V));
-    int load10 = ix->knobs.get("STAB_LOAD", 20);  // average postings per bucket, times ten, at most
-    if (load10 < 5) load10 = 5;
-    if (load10 > 40) load10 = 40;
+    int load10 = ix->knobs.get("STAB_LOAD", 30);  // average postings per bucket, times ten, at most
+    if (load10 < 10) load10 = 10;
+    if (load10 > 80) load10 = 80;
     stab_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, load10, d_sizes, ix->d_stab_sh);
     BM25CU_CHECK(cudaGetLastError());
     BM25CU_CHECK(exclusive_scan<long long>(d_sizes, V, ix->d_stab_off, d_tmp, ix->stream));
@@ -420,7 +448,7 @@ static int build_slot_tables(bm25cu_index *ix) {
     BM25CU_CHECK(cudaStreamSynchronize(ix->stream));
     cudaFree(d_sizes);
     cudaFree(d_tmp);
-    const size_t bytes = (size_t)(total > 0 ? total : 1) * 32;
+    const size_t bytes = (size_t)(total > 0 ? total : 1) * kStabSlots * 8;
     cudaError_t e = cudaMalloc(&ix->d_stab, bytes);
     if (e != cudaSuccess) {  // not enough HBM for the tables: lookups take the bucket-table path
         cudaGetLastError();

@@ -117,16 +117,24 @@ __device__ __forceinline__ void block_sort_desc(unsigned long long *a, int n, in
     }
 }
 
-// Slot-table lookup of document d (index.cu, build_slot_tables): one 32-byte bucket. 1: found (val), 0: absent,
-// -1: the bucket overflowed and d is not among its four slots - search the column.
+// Slot-table lookup of document d (index.cu, build_slot_tables): the 32-byte sector of d's half of its 64-byte bucket,
+// four (doc id, score) slots; flagged sectors lent postings to the other sector of the line. 1: found (val), 0: absent,
+// -1: the bucket holds more than its slots and d is not among them - search the column.
 __device__ __forceinline__ int slot_lookup(const uint4 *__restrict__ stab, long long first_bucket, int sh, int d, float &val) {
-    const uint4 *bk = stab + ((first_bucket + (long long)((unsigned)d >> sh)) << 1);
-    const uint4 a = __ldg(bk), b = __ldg(bk + 1);
+    const uint4 *bk = stab + ((first_bucket + (long long)((unsigned)d >> sh)) << 2);
+    const unsigned h = ((unsigned)d >> (sh - 1)) & 1u;
+    const uint4 a = __ldg(bk + 2 * h), b = __ldg(bk + 2 * h + 1);
     if ((a.x & 0x7fffffffu) == (unsigned)d) { val = __uint_as_float(a.y); return 1; }
-    if (a.z == (unsigned)d) { val = __uint_as_float(a.w); return 1; }
+    if ((a.z & 0x7fffffffu) == (unsigned)d) { val = __uint_as_float(a.w); return 1; }
     if (b.x == (unsigned)d) { val = __uint_as_float(b.y); return 1; }
     if (b.z == (unsigned)d) { val = __uint_as_float(b.w); return 1; }
-    return ((a.x >> 31) && a.x != 0xffffffffu) ? -1 : 0;
+    if (!((a.x >> 31) && a.x != 0xffffffffu)) return 0;
+    const uint4 c = __ldg(bk + 2 * (1u - h)), e = __ldg(bk + 2 * (1u - h) + 1);  // the other sector of the same 64-byte line
+    if ((c.x & 0x7fffffffu) == (unsigned)d) { val = __uint_as_float(c.y); return 1; }
+    if ((c.z & 0x7fffffffu) == (unsigned)d) { val = __uint_as_float(c.w); return 1; }
+    if (e.x == (unsigned)d) { val = __uint_as_float(e.y); return 1; }
+    if (e.z == (unsigned)d) { val = __uint_as_float(e.w); return 1; }
+    return ((a.z >> 31) && a.z != 0xffffffffu) ? -1 : 0;
 }
 
 template <int NT, int UNROLL, int R, bool BIG>
