@@ -134,8 +134,6 @@ struct bm25cu_index {
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t stream_hi = nullptr;  // high-priority side stream: the CTA-wide half of retrieve_ms.cu runs next to the per-warp half
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,
         d_spill, d_order, d_theta, d_fb_list, d_ms_items, d_ms_rows, d_ms_q, d_ms_partial;
@@ -172,8 +170,6 @@ struct Ctrl {
     unsigned int ms_next;        // work-queue cursor of the list-at-a-time kernel (retrieve_ms.cu)
     unsigned int fb_count;       // queries that kernel handed on to the streaming kernel
     unsigned int ms_items;       // work items (query parts) of that kernel
-    unsigned int ms_heavy;       // the first ms_heavy items are served by a whole CTA, the rest one per warp
-    unsigned int msw_next;       // work-queue cursor of the per-warp kernel (counts from ms_heavy)
     unsigned int ms_rows;        // rows handed out in its partial-result buffer
     unsigned int ms_hist[64];    // parts per log2(cost) bucket, and the scatter cursors of the buckets (ms_plan_*_kernel)
     unsigned int ms_cursor[64];

@@ -473,13 +473,6 @@ int finalize_index(bm25cu_index *ix) {
     ix->sm_count = prop.multiProcessorCount;
     ix->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     for (int i = 0; i < 6; ++i) BM25CU_CHECK(cudaEventCreate(&ix->ev[i]));
-    {
-        int least = 0, greatest = 0;
-        BM25CU_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        BM25CU_CHECK(cudaStreamCreateWithPriority(&ix->stream_hi, cudaStreamNonBlocking, greatest));
-        BM25CU_CHECK(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming));
-        BM25CU_CHECK(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
-    }
     unsigned int *d_flag = nullptr;
     BM25CU_CHECK(cudaMalloc(&d_flag, sizeof(unsigned int)));
     BM25CU_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(unsigned int), ix->stream));
@@ -558,9 +551,6 @@ static void destroy(bm25cu_index *ix) {
     ix->h_out.release();
     for (int i = 0; i < 6; ++i)
         if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
-    if (ix->stream_hi) { cudaStreamSynchronize(ix->stream_hi); cudaStreamDestroy(ix->stream_hi); }
-    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
-    if (ix->ev_join) cudaEventDestroy(ix->ev_join);
     if (ix->stream && ix->owns_stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }

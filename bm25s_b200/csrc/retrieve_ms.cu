@@ -544,7 +544,7 @@ struct Ms {
     __device__ void run() {
         const int tid = threadIdx.x;
         const int k = p.a.k;
-        const unsigned n_items = p.ctrl->ms_heavy;  // the CTA-wide items come first in the list; the light tail is served per warp
+        const unsigned n_items = p.ctrl->ms_items;
         for (;;) {
             if (tid == 0) s.q_slot = atomicAdd(&p.ctrl->ms_next, 1u);
             __syncthreads();
@@ -583,423 +583,6 @@ struct Ms {
             if (s.route && tid == 0) p.qstat[q] = 1u;
             __syncthreads();
         }
-#ifdef BM25CU_PROFILE
-        for (int i = 0; i < 16; ++i)
-            if (cnt[i]) atomicAdd(&p.ctrl->prof[32 + i], cnt[i]);
-#endif
-    }
-};
-
-// ---- light items: one WARP per work item ---------------------------------------------------------------------------
-// The same algorithm as Ms above for items whose cost is small (a shard-sized query, a query of rare tokens): a CTA of
-// 128 threads spends most of such an item in barriers and in the warp-0 prologue. Here every warp of the CTA owns an
-// item of its own: the top list is one 64-bit key per lane in registers, theta / the shared threshold are warp-uniform
-// registers, survivors are compacted into a per-warp queue with one prefix sum per chunk, and the only synchronisation
-// is __syncwarp. Results are identical by construction: the same bounds, the same acceptance rule (key > theta), the
-// same summation order; the order in which documents are met does not matter (see the header of this file).
-template <int UNROLL, int R>
-struct MsW {
-    static constexpr int CHUNK = 32 * 4 * UNROLL;
-    static constexpr int QCAP = CHUNK + 32 * R;
-    struct Sh {  // one per warp
-        long long beg[16];
-        long long bt_off[16];
-        long long pb_off[16];
-        long long st_off[16];
-        int df[16];
-        int bt_sh[16];
-        int pb_sh[16];
-        int st_sh[16];
-        int lo[16], hi[16];
-        float ub[16];
-        float mult[16];
-        float suf[17];
-        unsigned int pend_cnt;
-        unsigned char pos2u[16];
-        unsigned long long pend[32 * R];
-        unsigned int queue[QCAP];
-    };
-    const MsParams &p;
-    Sh &s;
-    const int lane;
-    unsigned long long top = 0ull;        // this lane's entry of the sorted top-32
-    unsigned long long theta_key = 0ull;  // warp-uniform: the k-th best key of this item
-    unsigned int gth = 0u;                // warp-uniform: score bits every part of the query may prune with
-    unsigned int work = 0u;
-    int U = 0, T = 0;
-#ifdef BM25CU_PROFILE
-    unsigned long long cnt[16] = {0};
-#endif
-    __device__ MsW(const MsParams &p_, Sh &s_, int lane_) : p(p_), s(s_), lane(lane_) {}
-
-    __device__ __forceinline__ float threshold() const { return fmaxf(cand_score(theta_key), __uint_as_float(gth)); }
-    __device__ __forceinline__ void refresh(unsigned int *gq) {
-        if (gq) {
-            unsigned g = 0u;
-            if (lane == 0) g = *(volatile unsigned int *)gq;
-            g = __shfl_sync(0xffffffffu, g, 0);
-            if (g > gth) gth = g;
-        }
-    }
-
-    __device__ __forceinline__ bool search(int j, int d, float &val) {
-        const long long so = s.st_off[j];
-        if (so >= 0) {
-            const int r = slot_lookup(p.stab, so, s.st_sh[j], d, val);
-            if (r >= 0) { if (r) MS_CNT(15, 1); return r != 0; }
-        }
-        const long long beg = s.beg[j];
-        int lo = 0, hi = s.df[j];
-        const long long bo = s.bt_off[j];
-        if (bo >= 0) {
-            const unsigned b = (unsigned)d >> s.bt_sh[j];
-            lo = (int)__ldg(p.btab + bo + b);
-            hi = (int)__ldg(p.btab + bo + b + 1);
-        }
-        const int32_t *col = p.indices + beg;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            const int x = __ldg(col + mid);
-            MS_CNT(4, 1);
-            if (x < d) lo = mid + 1;
-            else if (x > d) hi = mid;
-            else { val = __ldg(p.data + beg + mid); MS_CNT(15, 1); return true; }
-        }
-        return false;
-    }
-    __device__ __forceinline__ bool lookup(int j, int d, float &val) {
-        MS_CNT(3, 1);
-        const long long po = s.pb_off[j];
-        if (po >= 0) {
-            const unsigned x = (unsigned)d >> s.pb_sh[j];
-            if (!((__ldg(p.pbm + po + (x >> 5)) >> (x & 31u)) & 1u)) return false;
-            MS_CNT(13, 1);
-        }
-        return search(j, d, val);
-    }
-    __device__ int lower_bound(int j, int d) const {
-        int lo = 0, hi = s.df[j];
-        const long long bo = s.bt_off[j];
-        if (bo >= 0) {
-            const unsigned b = (unsigned)d >> s.bt_sh[j];
-            lo = (int)__ldg(p.btab + bo + b);
-            hi = (int)__ldg(p.btab + bo + b + 1);
-        }
-        const int32_t *col = p.indices + s.beg[j];
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(col + mid) < d) lo = mid + 1; else hi = mid;
-        }
-        return lo;
-    }
-
-    // the pending keys (at most 32 R) merged into the register top list; all 32 lanes
-    __device__ void merge_pending(int k, unsigned int *gq) {
-        const unsigned cnt_p = s.pend_cnt;
-        unsigned long long t = top;
-        for (unsigned base = 0; base < cnt_p; base += 32) {
-            unsigned long long b = (base + lane < cnt_p) ? s.pend[base + lane] : 0ull;
-            if (cnt_p - base > 1) b = warp_sort_desc(b, lane);
-            t = umax64(t, shfl64(b, 31 - lane));
-#pragma unroll
-            for (int stride = 16; stride > 0; stride >>= 1) {
-                const unsigned long long o = shfl64_xor(t, stride);
-                t = ((lane & stride) == 0) ? umax64(t, o) : umin64(t, o);
-            }
-        }
-        top = t;
-        const unsigned long long kth = shfl64(t, k - 1);
-        if (kth > theta_key) {
-            theta_key = kth;
-            if (gq && lane == 0) atomicMax(gq, (unsigned int)(kth >> 32));
-        }
-        __syncwarp();
-        if (lane == 0) s.pend_cnt = 0;
-        __syncwarp();
-    }
-
-    __device__ void finish(int i, int d, float v, unsigned found, const float *vals, unsigned long long tk, float th) {
-        float dummy;
-        for (int j = i - 1; j >= 0; --j)
-            if (lookup(j, d, dummy)) return;
-        float sc = 0.0f;
-        for (int t = 0; t < T; ++t) {
-            const unsigned u = s.pos2u[t];
-            if (u < 16u && ((found >> u) & 1u)) sc = __fadd_rn(sc, (int)u == i ? v : vals[u]);
-        }
-        if (p.a.mask) sc = (float)((double)sc * p.a.mask[d]);
-        const unsigned long long key = pack_cand(sc, d);
-        if (key > tk && sc >= th) { s.pend[atomicAdd(&s.pend_cnt, 1u)] = key; MS_CNT(5, 1); }
-    }
-
-    __device__ void probe_rounds(int i, unsigned n, int k, unsigned int *gq) {
-        const long long beg = s.beg[i];
-        const float m = s.mult[i], rest = s.suf[i + 1];
-        for (unsigned base = 0; base < n; base += 32 * R) {
-            const unsigned long long tk = theta_key;
-            const float th = threshold();
-            if (lane == 0) MS_CNT(6, 1);
-            int d[R];
-            float v[R], acc[R];
-            unsigned found[R];
-            bool alive[R];
-            float vals[R * 16];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const unsigned idx = base + r * 32 + lane;
-                const long long at = beg + ((idx < n) ? s.queue[idx] : 0u);
-                d[r] = __ldg(p.indices + at);
-                v[r] = __ldg(p.data + at);
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                acc[r] = __fmul_ru(m, v[r]);
-                alive[r] = base + r * 32 + lane < n && reaches(acc[r], rest, th);
-                found[r] = 1u << i;
-                if (alive[r]) MS_CNT(2, 1);
-            }
-            for (int j = i + 1; j < U; ++j) {
-                const long long po = s.pb_off[j];
-                const int psh = s.pb_sh[j];
-                unsigned w[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const unsigned x = (unsigned)d[r] >> psh;
-                    w[r] = (po >= 0 && alive[r]) ? __ldg(p.pbm + po + (x >> 5)) : 0xffffffffu;
-                }
-                unsigned todo = 0u;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const unsigned x = (unsigned)d[r] >> psh;
-                    if (alive[r]) { MS_CNT(3, 1); if ((w[r] >> (x & 31u)) & 1u) todo |= 1u << r; }
-                }
-                const float mj = s.mult[j];
-                while (todo) {
-                    const int r = __ffs(todo) - 1;
-                    todo &= todo - 1u;
-                    int dd = d[0];
-#pragma unroll
-                    for (int rr = 1; rr < R; ++rr) dd = (rr == r) ? d[rr] : dd;
-                    float val;
-                    MS_CNT(13, 1);
-                    if (search(j, dd, val)) {
-                        const float add = __fmul_ru(mj, val);
-                        vals[r * 16 + j] = val;
-#pragma unroll
-                        for (int rr = 0; rr < R; ++rr)
-                            if (rr == r) { acc[rr] = __fadd_ru(acc[rr], add); found[rr] |= 1u << j; }
-                    }
-                }
-                const float sufn = s.suf[j + 1];
-                bool any = false;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    alive[r] = alive[r] && reaches(acc[r], sufn, th);
-                    any |= alive[r];
-                }
-                if (!__any_sync(0xffffffffu, any)) break;
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (alive[r]) finish(i, d[r], v[r], found[r], vals + r * 16, tk, th);
-            __syncwarp();
-            refresh(gq);
-            if (s.pend_cnt > 0u) {  // uniform: read behind the warp barrier, reset only inside merge_pending
-                if (lane == 0) MS_CNT(7, 1);
-                merge_pending(k, gq);
-            }
-        }
-        work += n;
-        __syncwarp();
-    }
-
-    __device__ __forceinline__ bool passes(float v, int pos, int df, float m, float rest, float th) const {
-        return __fmul_ru(__fmaf_ru(m, v, rest), 1.00002f) >= th && (unsigned)pos < (unsigned)df;
-    }
-
-    __device__ bool stream(int i, int k, unsigned int *gq) {
-        const int lo = s.lo[i];
-        const long long beg = s.beg[i] + lo;
-        const int df = s.hi[i] - lo;
-        const float m = s.mult[i], rest = s.suf[i + 1];
-        const int head = (int)(beg & 3);
-        const int nvec = (df + head + 3) >> 2;
-        const float4 *vp = reinterpret_cast<const float4 *>(p.data + (beg - head));
-        if (lane == 0) { MS_CNT(0, df); MS_CNT(8, 1); }
-        unsigned qn = 0;  // survivors waiting in the queue (uniform)
-        for (int v0 = 0; v0 < nvec; v0 += 32 * UNROLL) {
-            const float th = threshold();
-            float4 x[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int v = v0 + u * 32 + lane;
-                x[u] = (v < nvec) ? __ldcs(vp + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            unsigned bits = 0u;  // bit 4 u + c: posting c of vector u survives
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int v = v0 + u * 32 + lane;
-                const int pos = 4 * v - head;
-                if (v < nvec) {
-                    if (passes(x[u].x, pos, df, m, rest, th)) bits |= 1u << (4 * u);
-                    if (passes(x[u].y, pos + 1, df, m, rest, th)) bits |= 2u << (4 * u);
-                    if (passes(x[u].z, pos + 2, df, m, rest, th)) bits |= 4u << (4 * u);
-                    if (passes(x[u].w, pos + 3, df, m, rest, th)) bits |= 8u << (4 * u);
-                }
-            }
-            const unsigned c = __popc(bits);
-            unsigned incl = c;  // inclusive prefix sum over the lanes
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += y;
-            }
-            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-            unsigned at = qn + incl - c;
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1u;
-                const int pos = 4 * (v0 + (b >> 2) * 32 + lane) - head + (b & 3);
-                s.queue[at++] = (unsigned)(pos + lo);
-            }
-            MS_CNT(1, c);
-            qn += total;
-            __syncwarp();
-            const bool last = v0 + 32 * UNROLL >= nvec;
-            if (qn >= (unsigned)(32 * R) || (last && qn > 0u)) {
-                probe_rounds(i, qn, k, gq);
-                qn = 0;
-                if (work > p.budget) return false;
-            } else {
-                refresh(gq);
-            }
-        }
-        return true;
-    }
-
-    // tokens -> distinct lists ordered by upper bound, suffix sums, start threshold (cf. Ms::prologue); returns "route"
-    __device__ bool prologue(int q, int part, int P) {
-        const long long qs = p.a.q_ptr[q], qe = p.a.q_ptr[q + 1];
-        const long long Tl = qe - qs;
-        if (p.route_all || Tl > kMaxTok || Tl == 0 || (p.a.mask && p.ctrl->mask_bad)) return true;
-        T = (int)Tl;
-        const int tok = (lane < T) ? p.a.q_tokens[qs + lane] : -1 - lane;
-        long long beg = 0, bo = -1, po = -1, so = -1;
-        int df = 0, bsh = 0, psh = 0, ssh = 0;
-        float mx = 0.0f, kth = 0.0f;
-        if (lane < T) {
-            if ((unsigned)tok >= (unsigned)p.n_vocab) atomicOr(&p.ctrl->error, 1u);
-            else {
-                beg = p.indptr[tok];
-                df = (int)(p.indptr[tok + 1] - beg);
-                mx = p.colmax[tok];
-                if (p.colkth) kth = p.colkth[tok];
-                if (p.btab) { bo = p.btab_off[tok]; bsh = p.btab_sh[tok]; }
-                if (p.pbm) { po = p.pbm_off[tok]; psh = p.pbm_sh[tok]; }
-                if (p.stab) { so = p.stab_off[tok]; ssh = p.stab_sh[tok]; }
-            }
-        }
-        int first = lane, mult = 0;
-        for (int j = 0; j < T; ++j) {
-            const int tj = __shfl_sync(0xffffffffu, tok, j);
-            if (tj == tok) { ++mult; if (j < first) first = j; }
-        }
-        const int uniq = (lane < T && first == lane && df > 0) ? 1 : 0;
-        const float ub = uniq ? __fmul_ru((float)mult, mx) : 0.0f;
-        int rank = 0;
-        for (int j = 0; j < T; ++j) {
-            const float ubj = __shfl_sync(0xffffffffu, ub, j);
-            const int uj = __shfl_sync(0xffffffffu, uniq, j);
-            if (uj && j != lane && (ubj > ub || (ubj == ub && j < lane))) ++rank;
-        }
-        U = __popc(__ballot_sync(0xffffffffu, uniq));
-        if (uniq) {
-            s.beg[rank] = beg;
-            s.df[rank] = df;
-            s.ub[rank] = ub;
-            s.mult[rank] = (float)mult;
-            s.bt_off[rank] = bo;
-            s.bt_sh[rank] = bsh;
-            s.pb_off[rank] = po;
-            s.pb_sh[rank] = psh;
-            s.st_off[rank] = so;
-            s.st_sh[rank] = ssh;
-        }
-        const int myrank = uniq ? rank : 255;
-        const int rf = __shfl_sync(0xffffffffu, myrank, first & 31);
-        if (lane < T) s.pos2u[lane] = (unsigned char)rf;
-        unsigned long long tot = (lane < T) ? (unsigned long long)df : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        const unsigned kb = __reduce_max_sync(0xffffffffu, __float_as_uint(kth));
-        __syncwarp();
-        if (lane == 0) {
-            float acc = 0.0f;
-            s.suf[U] = 0.0f;
-            for (int j = U - 1; j >= 0; --j) { acc = __fadd_ru(acc, s.ub[j]); s.suf[j] = acc; }
-            s.pend_cnt = 0;
-        }
-        top = 0ull;
-        theta_key = 0ull;
-        gth = kb > 0u ? kb - 1u : 0u;
-        if (p.theta_mode == 2) { const unsigned tb = __float_as_uint(p.theta_io[q]); if (tb > gth) gth = tb; }
-        work = 0;
-        __syncwarp();
-        if (tot == 0) return true;
-        if (lane < U) {
-            int lo = 0, hi = s.df[lane];
-            if (P > 1) {
-                const int d0 = (int)((long long)p.n_docs * part / P), d1 = (int)((long long)p.n_docs * (part + 1) / P);
-                if (part > 0) lo = lower_bound(lane, d0);
-                if (part + 1 < P) hi = lower_bound(lane, d1);
-            }
-            s.lo[lane] = lo;
-            s.hi[lane] = hi;
-        }
-        __syncwarp();
-        return false;
-    }
-
-    // the light tail of the item list: this warp pulls items of its own until the list is empty
-    __device__ void run() {
-        const unsigned n_heavy = p.ctrl->ms_heavy, n_items = p.ctrl->ms_items;
-        for (;;) {
-            unsigned slot = 0u;
-            if (lane == 0) slot = n_heavy + atomicAdd(&p.ctrl->msw_next, 1u);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (slot >= n_items) break;
-            item(p.items[slot]);
-        }
-        flush_counters();
-    }
-
-    // one work item, start to finish
-    __device__ void item(unsigned long long it) {
-        const int k = p.a.k;
-        const int q = (int)(unsigned)(it & 0xffffffffull), part = (int)((it >> 32) & 0xffu), P = (int)((it >> 40) & 0xffu);
-        unsigned int *gq = (P > 1) ? p.gtheta + q : nullptr;
-        bool route = prologue(q, part, P);
-        if (!route) {
-            if (gq && lane == 0 && gth) atomicMax(gq, gth);
-            for (int i = 0; i < U; ++i) {
-                if (P > 1) {
-                    refresh(gq);
-                    unsigned ab = 0u;
-                    if (lane == 0) ab = *(volatile unsigned int *)(p.qstat + q);
-                    if (__shfl_sync(0xffffffffu, ab, 0)) break;  // another part gave the query up
-                }
-                if (__fmul_ru(s.suf[i], 1.00002f) < threshold()) { if (lane == 0) MS_CNT(9, U - i); break; }
-                if (s.hi[i] > s.lo[i] && !stream(i, k, gq)) break;
-            }
-            if (work > p.budget) route = true;
-            else if (lane < k) p.partial[((size_t)p.part_base[q] + part) * k + lane] = top;
-        }
-        if (lane == 0) MS_CNT(route ? 11 : 10, 1);
-        if (route && lane == 0) p.qstat[q] = 1u;
-        __syncwarp();
-    }
-
-    __device__ void flush_counters() {
 #ifdef BM25CU_PROFILE
         for (int i = 0; i < 16; ++i)
             if (cnt[i]) atomicAdd(&p.ctrl->prof[32 + i], cnt[i]);
@@ -1048,16 +631,12 @@ __global__ void __launch_bounds__(256) ms_plan_cost_kernel(const int32_t *__rest
 }
 
 __global__ void __launch_bounds__(256) ms_plan_scatter_kernel(int32_t n_queries, const unsigned char *__restrict__ scratch,
-                                                              unsigned long long *items, Ctrl *ctrl, int light_bk) {
+                                                              unsigned long long *items, Ctrl *ctrl) {
     __shared__ unsigned int base[64];
     if (threadIdx.x == 0) {
-        unsigned int acc = 0, heavy = 0;
-        for (int bk = 63; bk >= 0; --bk) {
-            base[bk] = acc;
-            acc += ctrl->ms_hist[bk];
-            if (bk > light_bk) heavy = acc;  // items of at least 2^light_bk postings per part: CTA-wide
-        }
-        if (blockIdx.x == 0) { ctrl->ms_items = acc; ctrl->ms_heavy = heavy; }
+        unsigned int acc = 0;
+        for (int bk = 63; bk >= 0; --bk) { base[bk] = acc; acc += ctrl->ms_hist[bk]; }
+        if (blockIdx.x == 0) ctrl->ms_items = acc;
     }
     __syncthreads();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1113,18 +692,6 @@ __global__ void __launch_bounds__(NT, MINB) retrieve_ms_kernel(const __grid_cons
     extern __shared__ __align__(16) unsigned long long ms_dyn[];
     Ms<NT, UNROLL, R, BIG> m(p, sh, ms_dyn);
     m.run();
-}
-
-// The light tail of the item list (items ms_heavy .. ms_items): every warp pulls items of its own. Runs next to
-// retrieve_ms_kernel (two streams): its CTAs move in as the CTA-wide kernel's CTAs run out of items.
-constexpr int kLightUnroll = 2;  // 256 postings per warp and streaming step
-constexpr int kLightWarps = 4;
-
-template <int R, int MINB>
-__global__ void __launch_bounds__(kLightWarps * 32, MINB) retrieve_msw_kernel(const __grid_constant__ MsParams p) {
-    __shared__ typename MsW<kLightUnroll, R>::Sh sh[kLightWarps];
-    MsW<kLightUnroll, R> w(p, sh[threadIdx.x >> 5], threadIdx.x & 31);
-    w.run();
 }
 
 // k > 32: one CTA per query, the parts' rows are rank-merged one after the other in shared memory
@@ -1245,11 +812,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     ms_plan_cost_kernel<<<qblocks, 256, 0, ix->stream>>>(a.q_tokens, a.q_ptr, a.n_queries, ix->d_indptr, ix->n_vocab, part_cost, max_parts,
                                                          part_base, qtot, gtheta, qstat, scratch, d_ctrl);
     BM25CU_CHECK(cudaGetLastError());
-    // items whose cost per part is below 2^MS_LIGHT postings are served one per warp (k <= 32 only); 0: none
-    int light_bk = p.kcap <= 32 ? ix->knobs.get("MS_LIGHT", 0) : -1;
-    if (light_bk <= 0) light_bk = -1;
-    if (light_bk > 62) light_bk = 62;
-    ms_plan_scatter_kernel<<<qblocks, 256, 0, ix->stream>>>(a.n_queries, scratch, items, d_ctrl, light_bk);
+    ms_plan_scatter_kernel<<<qblocks, 256, 0, ix->stream>>>(a.n_queries, scratch, items, d_ctrl);
     BM25CU_CHECK(cudaGetLastError());
     p.items = items;
     p.part_base = part_base;
@@ -1259,32 +822,9 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     const int per_sm = ix->knobs.get("MS_CTAS", 9);  // 55 registers: nine 128-thread CTAs are resident per SM
     const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 9);
     const size_t dyn = p.kcap > 32 ? (size_t)2 * p.kcap * 8 : 0;
-    const bool light = light_bk >= 0 && ix->stream_hi != nullptr;
-    // With a light tail the CTA-wide kernel runs on the handle's high-priority side stream and the per-warp kernel on
-    // the main stream: both pull from the same item list (its head / its tail), the per-warp CTAs move in as the
-    // CTA-wide ones run out of items, and the merge waits for both.
-    cudaStream_t heavy_stream = ix->stream;
-    if (light) {
-        BM25CU_CHECK(cudaEventRecord(ix->ev_fork, ix->stream));
-        BM25CU_CHECK(cudaStreamWaitEvent(ix->stream_hi, ix->ev_fork, 0));
-        heavy_stream = ix->stream_hi;
-    }
-    if (p.kcap <= 32) retrieve_ms_kernel<128, 4, 4, 8, false><<<grid, 128, 0, heavy_stream>>>(p);
-    else retrieve_ms_kernel<128, 4, 4, 8, true><<<grid, 128, dyn, heavy_stream>>>(p);
+    if (p.kcap <= 32) retrieve_ms_kernel<128, 4, 4, 8, false><<<grid, 128, 0, ix->stream>>>(p);
+    else retrieve_ms_kernel<128, 4, 4, 8, true><<<grid, 128, dyn, ix->stream>>>(p);
     BM25CU_CHECK(cudaGetLastError());
-    if (light) {
-        BM25CU_CHECK(cudaEventRecord(ix->ev_join, ix->stream_hi));
-        // R survivors per lane and probe round: 4 (64 registers, 8 CTAs per SM) or 2 (48 registers, 10 CTAs per SM)
-        const int wr = ix->knobs.get("MSW_R", 4);
-        const int occ = wr == 2 ? 10 : 8;
-        const int per_sm_w = ix->knobs.get("MSW_CTAS", occ);
-        const int wgrid = ix->sm_count * (per_sm_w > 0 ? per_sm_w : occ);
-        if (wr == 2) retrieve_msw_kernel<2, 10><<<wgrid, kLightWarps * 32, 0, ix->stream>>>(p);
-        else retrieve_msw_kernel<4, 8><<<wgrid, kLightWarps * 32, 0, ix->stream>>>(p);
-        BM25CU_CHECK(cudaGetLastError());
-        BM25CU_CHECK(cudaStreamWaitEvent(ix->stream, ix->ev_join, 0));
-        if (launches) ++*launches;
-    }
     if (p.kcap <= 32)
         ms_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ix->stream>>>(scratch + nq, part_base, p.partial, qstat, qtot, a, ix->doc_base,
                                                                                   d_ctrl, d_fb_list, p.theta_mode == 1 ? p.theta_io : nullptr);

@@ -195,11 +195,8 @@ def test_random_corpus_vs_c_oracle(k):
                 {"BM25CU_MS_MAXPARTS": "1"}, {"BM25CU_MS_PARTCOST": "512"}, {"BM25CU_MS_PARTCOST": "2000", "BM25CU_MS_MAXPARTS": "255"},
                 {"BM25CU_MS_BUDGET": "64"}, {"BM25CU_MS_BUDGET": "600", "BM25CU_MS_PARTCOST": "4096"},
                 {"BM25CU_MS_BTAB": "0"}, {"BM25CU_MS_PBM": "0"}, {"BM25CU_MS_BTAB": "0", "BM25CU_MS_PBM": "0", "BM25CU_SEED_KTH": "0"},
-                # the per-warp kernel (light items): off, everything light, two survivors per lane, light items cut into
-                # parts, light items over the survivor budget (handed on), lookups without tables
-                {"MS_LIGHT": 0}, {"MS_LIGHT": 40}, {"MS_LIGHT": 40, "MSW_R": 2}, {"MS_LIGHT": 40, "MS_PARTCOST": 512, "MS_MAXPARTS": 64},
-                {"MS_LIGHT": 40, "MSW_R": 2, "MS_PARTCOST": 2000, "MS_MAXPARTS": 255}, {"MS_LIGHT": 40, "MS_BUDGET": 64},
-                {"MS_LIGHT": 40, "MS_BTAB": 0, "MS_PBM": 0, "SEED_KTH": 0}, {"MS_LIGHT": 8}, {"MS_LIGHT": 40, "MSW_CTAS": 1}):
+                # lookups without the slot tables (bucket table + id slice + score), slot tables with many parts
+                {"MS_STAB": 0}, {"MS_STAB": 0, "MS_PBM": 0}, {"MS_PARTCOST": 512, "MS_PBM": 0}):
         with dev.options(**env):
             ids2, sc2 = dev.retrieve(flat, ptr, k, shift=sh)
         np.testing.assert_array_equal(sc2, sc)
@@ -498,8 +495,7 @@ def test_tie_heavy_corpus(k):
         n_tail = int((sc[q] == sc[q][-1]).sum())
         assert set(ids[q][sc[q] == sc[q][-1]].tolist()) == set(tail[:n_tail].tolist()), q
     for env in ({"BM25CU_MS": "0"}, {"BM25CU_MS_MAXPARTS": "1"}, {"BM25CU_MS_PARTCOST": "256", "BM25CU_MS_MAXPARTS": "64"},
-                {"BM25CU_SEED_KTH": "0"}, {"BM25CU_MS_PBM": "0", "BM25CU_MS_BTAB": "0"},
-                {"MS_LIGHT": 0}, {"MS_LIGHT": 40}, {"MS_LIGHT": 40, "MSW_R": 2, "MS_PARTCOST": 256, "MS_MAXPARTS": 64}):
+                {"BM25CU_SEED_KTH": "0"}, {"BM25CU_MS_PBM": "0", "BM25CU_MS_BTAB": "0"}, {"MS_STAB": 0}, {"MS_PBM": 0}):
         with dev.options(**env):
             ids2, sc2 = dev.retrieve(flat, ptr, k)
         np.testing.assert_array_equal(sc2, sc, err_msg=str(env))
