@@ -220,19 +220,74 @@ def oracle_parity(csc_host, q_tok, q_ptr, n_docs, k, shift, ids, scores, n_rows)
     rows = np.unique(np.linspace(0, nq - 1, num=min(n_rows, nq)).astype(np.int64))
     s_tok, s_ptr = sub_batch(q_tok, q_ptr, rows)
     rid, rsc = CO.retrieve(data, indices, indptr, n_docs, s_tok, s_ptr, k, shift=None if shift is None else shift[rows])
-    ok = bool(np.array_equal(scores[rows].view(np.int32), rsc.view(np.int32)))
+    bad = {"score_rows": 0, "id_sets": 0, "dense_scores": 0, "tail": 0}
+    first_bad = None
     for j, q in enumerate(rows):
+        if not np.array_equal(scores[q].view(np.int32), rsc[j].view(np.int32)):
+            bad["score_rows"] += 1
+            first_bad = first_bad if first_bad is not None else int(q)
         kth = rsc[j, -1]
-        ok &= set(ids[q][scores[q] > kth].tolist()) == set(rid[j][rsc[j] > kth].tolist())
+        if set(ids[q][scores[q] > kth].tolist()) != set(rid[j][rsc[j] > kth].tolist()):
+            bad["id_sets"] += 1
+            first_bad = first_bad if first_bad is not None else int(q)
     dense_rows = rows[:: max(1, len(rows) // 8)]
     for q in dense_rows:
         dense = CO.scores_dense(data, indices, indptr, n_docs, q_tok[q_ptr[q]:q_ptr[q + 1]], shift=None if shift is None else shift[q])
-        ok &= bool(np.array_equal(dense[ids[q]], scores[q]))
+        if not np.array_equal(dense[ids[q]], scores[q]):
+            bad["dense_scores"] += 1
+            first_bad = first_bad if first_bad is not None else int(q)
         rest = dense.copy()
         rest[ids[q]] = -np.inf
-        ok &= bool(rest.max() <= scores[q, -1])
-    return {"queries": int(len(rows)), "dense_rows": int(len(dense_rows)), "ok": bool(ok),
-            "what": "scores bit-equal, id sets equal above the k-th score, dense-vector check of returned ids and of the tail"}
+        if not rest.max() <= scores[q, -1]:
+            bad["tail"] += 1
+            first_bad = first_bad if first_bad is not None else int(q)
+    ok = not any(bad.values())
+    out = {"queries": int(len(rows)), "dense_rows": int(len(dense_rows)), "ok": bool(ok),
+           "what": "scores bit-equal, id sets equal above the k-th score, dense-vector check of returned ids and of the tail"}
+    if not ok:
+        q = first_bad
+        out["failures"] = bad
+        out["first_bad_query"] = {"q": q, "tokens": q_tok[q_ptr[q]:q_ptr[q + 1]].tolist(), "ours_ids": ids[q].tolist(), "ours_scores": scores[q].tolist(),
+                                  "oracle_ids": rid[list(rows).index(q)].tolist(), "oracle_scores": rsc[list(rows).index(q)].tolist()}
+    return out
+
+
+def sharded_oracle_parity(dev, rank, world, q_tok, q_ptr, k, shift, ids, scores, n_rows, threads):
+    """Corpora too large to rebuild unsharded (100 M docs): every rank downloads ITS shard and scores a strided sample of the
+    batch with the C oracle on it (dense vector over the shard + selection), the shards' oracle rows are gathered and merged
+    on rank 0 under the library's order (score desc, id asc; shift after the merge) and compared with the GPU rows: scores
+    bit-equal, id sets equal above the k-th score. SURVEY.md 8c's plan for the 100 M-doc configuration."""
+    import torch.distributed as dist
+
+    from bm25s_b200.sharded import merge_topk_numpy
+    from oracle import c_oracle as CO
+
+    data, indices, indptr, _ = dev.download()
+    nq = len(q_ptr) - 1
+    rows = np.unique(np.linspace(0, nq - 1, num=min(n_rows, nq)).astype(np.int64))
+    s_tok, s_ptr = sub_batch(q_tok, q_ptr, rows)
+    rid, rsc = CO.retrieve(data, indices, indptr, dev.n_docs, s_tok, s_ptr, k, n_threads=threads)
+    rid = np.where(rid >= 0, rid + dev.doc_lo, -1).astype(np.int32)
+    del data, indices, indptr
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (rid, rsc))
+    if rank != 0:
+        return None
+    g_ids = np.stack([g[0] for g in gathered])
+    g_sc = np.stack([g[1] for g in gathered])
+    m_ids, m_sc = merge_topk_numpy(g_ids, g_sc, k)
+    if shift is not None:
+        m_sc = (m_sc + shift[rows][:, None]).astype(np.float32)
+    bad = {"score_rows": 0, "id_sets": 0}
+    for j, q in enumerate(rows):
+        if not np.array_equal(scores[q].view(np.int32), m_sc[j].view(np.int32)):
+            bad["score_rows"] += 1
+        kth = m_sc[j, -1]
+        if set(ids[q][scores[q] > kth].tolist()) != set(m_ids[j][m_sc[j] > kth].tolist()):
+            bad["id_sets"] += 1
+    return {"queries": int(len(rows)), "ok": not any(bad.values()), "failures": bad,
+            "what": "per-shard C oracle (dense vector over the downloaded shard + selection) on every rank, rows merged on rank 0 "
+                    "(score desc, id asc) and compared with the GPU rows: scores bit-equal, id sets equal above the k-th score"}
 
 
 def reference_module():
@@ -620,6 +675,12 @@ def main():
                               "same_scores_as_e2e": bool(np.array_equal(res.scores, e2e_sc))}
         api._dev = None  # the handle belongs to this script
 
+    if local_shards(args, world) and not args.no_cpu_baseline and args.parity_queries > 0:
+        # every rank takes part (its own shard, its share of the host threads)
+        par = sharded_oracle_parity(dev, rank, world, q_tok_h, q_ptr_h, k, shift_h, e2e_ids, e2e_sc, min(args.parity_queries, 96),
+                                    threads=max(1, (os.cpu_count() or world) // world))
+        if rank == 0:
+            line["parity_vs_cpu_port"] = par
     if want_cpu:
         if csc_host is None and not local_shards(args, world):
             csc_host, _ = unsharded_csc(args, device, local_rank)  # N > 1: rank 0 rebuilds the whole matrix, untimed

@@ -85,6 +85,7 @@ def make_corpus_torch(n_docs: int, avg_len: float, n_vocab: int, seed: int = 0, 
         u = torch.rand(n, device=device, dtype=torch.float64, generator=g)
         x = torch.exp(u * la + (1.0 - u) * lb) - s
         tokens[o:o + n] = x.floor_().clamp_(0, n_vocab - 1).to(torch.int32)
+    torch.cuda.synchronize(device)  # the library reads these buffers on its own streams
     return tokens, ptr
 
 
@@ -103,6 +104,7 @@ def make_queries_torch(n_queries: int, n_vocab: int, seed: int = 1, mean_extra: 
     u = torch.rand(total, device=device, dtype=torch.float64, generator=g)
     x = torch.exp(u * math.log(n_vocab + s) + (1.0 - u) * math.log(s)) - s
     tokens = x.floor_().clamp_(0, n_vocab - 1).to(torch.int32)
+    torch.cuda.synchronize(device)
     return tokens, ptr
 
 

@@ -341,6 +341,7 @@ def test_full_size_against_the_oracle(shape, method, k, n_queries):
     dev_t = torch.device("cuda")
     tokens, ptr = synth.make_corpus_torch(n_docs, avg_len, n_vocab, seed=0, device=dev_t)
     ix = DeviceIndex.build_device(tokens.data_ptr(), ptr.data_ptr(), n_docs, n_vocab, method, method, 1.5, 0.75, 0.5)
+    assert ix.nnz > 0.9 * n_docs * avg_len  # the corpus really has the named shape (most tokens of a document are distinct)
     del tokens, ptr
     torch.cuda.empty_cache()
     qt, qp = synth.make_queries_torch(n_queries, n_vocab, seed=1, device=dev_t)
