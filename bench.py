@@ -687,6 +687,29 @@ def main():
         if csc_host is not None:
             if args.parity_queries > 0:
                 line["parity_vs_cpu_port"] = oracle_parity(csc_host, q_tok_h, q_ptr_h, n_docs, k, shift_h, e2e_ids, e2e_sc, args.parity_queries)
+            if world > 1:
+                # The drop-in multi-GPU form, untimed region of the torchrun job: ONE process (this rank) drives all N GPUs
+                # through bm25cu_group_* - what BM25(backend="cuda", devices=[0..N-1]) calls. Host arrays in and out.
+                try:
+                    from bm25s_b200 import DeviceGroup
+
+                    t0 = time.perf_counter()
+                    grp = DeviceGroup.upload(*csc_host, n_docs, nonocc=no_h, devices=list(range(world)))
+                    up_s = time.perf_counter() - t0
+                    for _ in range(2):
+                        g_ids, g_sc = grp.retrieve(q_tok_h, q_ptr_h, k, shift=shift_h)
+                    n_rep = max(1, min(args.steps, 5))
+                    t0 = time.perf_counter()
+                    for _ in range(n_rep):
+                        g_ids, g_sc = grp.retrieve(q_tok_h, q_ptr_h, k, shift=shift_h)
+                    g_s = (time.perf_counter() - t0) / n_rep
+                    line["e2e_single_process"] = {"value": n_queries / g_s, "unit": UNIT, "n_gpus": world, "upload_s": round(up_s, 2),
+                                                  "api": "bm25cu_group_retrieve (host numpy arrays in/out; one process, one host thread per GPU, "
+                                                         "peer copies to GPU 0 + merge) = BM25(backend='cuda', devices=[0..N-1]).retrieve",
+                                                  "result_digest": digest_of(g_ids, g_sc), "same_rows_as_e2e": digest_of(g_ids, g_sc) == digest}
+                    grp.close()
+                except Exception as e:  # noqa: BLE001
+                    line["e2e_single_process"] = {"error": repr(e)[:300]}
             if world == 1:
                 cb = port_baseline(csc_host, q_tok_h, q_ptr_h, n_docs, k, shift_h, args.cpu_seconds)
                 ref = None if args.no_reference_backends else reference_module()

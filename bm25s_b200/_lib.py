@@ -25,6 +25,9 @@ EXPORTED_SYMBOLS = [
     "bm25cu_debug_colkth", "bm25cu_debug_prof",
     "bm25cu_exchange_create", "bm25cu_exchange_handle_size", "bm25cu_exchange_handle", "bm25cu_exchange_connect",
     "bm25cu_exchange_merge", "bm25cu_exchange_check", "bm25cu_exchange_free",
+    "bm25cu_group_upload", "bm25cu_group_build", "bm25cu_group_sizes", "bm25cu_group_shard", "bm25cu_group_set_option",
+    "bm25cu_group_unset_option", "bm25cu_group_download", "bm25cu_group_retrieve", "bm25cu_group_scores_dense",
+    "bm25cu_group_free",
 ]
 
 
@@ -262,6 +265,106 @@ class DeviceIndex:
     def close(self):
         if self._h is not None and _lib is not None:
             _lib.bm25cu_index_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceGroup:
+    """Owns one bm25cu_group handle: ONE index sharded by contiguous doc-id ranges over several devices of the box, driven
+    from this process (include/bm25cu.h, bm25cu_group_*). Same surface as DeviceIndex where `BM25` uses it."""
+
+    def __init__(self, handle, devices):
+        self._h = handle
+        self._lock = threading.Lock()
+        self._opts = {}
+        self.devices = list(devices)
+        nnz, nv, nd, ns, hn = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib().bm25cu_group_sizes(self._h, C.byref(nnz), C.byref(nv), C.byref(nd), C.byref(ns), C.byref(hn)))
+        self.nnz, self.n_vocab, self.n_docs, self.n_shards, self.has_nonocc = nnz.value, nv.value, nd.value, ns.value, bool(hn.value)
+        self.doc_lo = 0
+
+    @staticmethod
+    def _devs(devices):
+        return np.ascontiguousarray(list(devices), dtype=np.int32)
+
+    @classmethod
+    def upload(cls, data, indices, indptr, n_docs, nonocc=None, devices=(0,)):
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        nonocc = None if nonocc is None else np.ascontiguousarray(nonocc, dtype=np.float32)
+        devs = cls._devs(devices)
+        h = C.c_void_p()
+        check(lib().bm25cu_group_upload(ptr(data, C.c_float), ptr(indices, C.c_int32), ptr(indptr, C.c_int64), C.c_int64(len(data)),
+                                        C.c_int32(len(indptr) - 1), C.c_int32(n_docs), ptr(nonocc, C.c_float),
+                                        ptr(devs, C.c_int32), C.c_int32(len(devs)), C.byref(h)))
+        return cls(h, devs.tolist())
+
+    @classmethod
+    def build(cls, tokens, doc_ptr, n_vocab, method, idf_method, k1, b, delta, devices=(0,)):
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        doc_ptr = np.ascontiguousarray(doc_ptr, dtype=np.int64)
+        devs = cls._devs(devices)
+        h = C.c_void_p()
+        check(lib().bm25cu_group_build(ptr(tokens, C.c_int32), ptr(doc_ptr, C.c_int64), C.c_int32(len(doc_ptr) - 1), C.c_int32(n_vocab),
+                                       C.c_int32(METHOD_CODES[method]), C.c_int32(METHOD_CODES[idf_method]), C.c_double(k1),
+                                       C.c_double(b), C.c_double(delta), ptr(devs, C.c_int32), C.c_int32(len(devs)), C.byref(h)))
+        return cls(h, devs.tolist())
+
+    def set_option(self, name: str, value: int):
+        with self._lock:
+            check(lib().bm25cu_group_set_option(self._h, name.encode(), C.c_int32(int(value))))
+        self._opts[name] = int(value)
+
+    def unset_option(self, name: str):
+        with self._lock:
+            check(lib().bm25cu_group_unset_option(self._h, name.encode()))
+        self._opts.pop(name, None)
+
+    options = DeviceIndex.options
+
+    def download(self):
+        data = np.empty(self.nnz, np.float32)
+        indices = np.empty(self.nnz, np.int32)
+        indptr = np.empty(self.n_vocab + 1, np.int64)
+        nonocc = np.empty(self.n_vocab, np.float32) if self.has_nonocc else None
+        check(lib().bm25cu_group_download(self._h, ptr(data, C.c_float), ptr(indices, C.c_int32), ptr(indptr, C.c_int64),
+                                          ptr(nonocc, C.c_float)))
+        return data, indices, indptr, nonocc
+
+    def retrieve(self, q_tokens, q_ptr, k, shift=None, mask=None, with_stats=False):
+        q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
+        q_ptr = np.ascontiguousarray(q_ptr, dtype=np.int64)
+        nq = len(q_ptr) - 1
+        shift = None if shift is None else np.ascontiguousarray(shift, dtype=np.float32)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.float64)
+        ids = np.empty((nq, k), np.int32)
+        scores = np.empty((nq, k), np.float32)
+        st = Stats()
+        with self._lock:
+            check(lib().bm25cu_group_retrieve(self._h, ptr(q_tokens, C.c_int32), ptr(q_ptr, C.c_int64), C.c_int32(nq), C.c_int32(k),
+                                              ptr(shift, C.c_float), ptr(mask, C.c_double), ptr(ids, C.c_int32),
+                                              ptr(scores, C.c_float), C.byref(st)))
+        return (ids, scores, st.as_dict()) if with_stats else (ids, scores)
+
+    def scores_dense(self, q_tokens, shift=None, mask=None):
+        q_tokens = np.ascontiguousarray(q_tokens, dtype=np.int32)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.float64)
+        out = np.empty(self.n_docs, np.float32)
+        with self._lock:
+            check(lib().bm25cu_group_scores_dense(self._h, ptr(q_tokens, C.c_int32), C.c_int32(len(q_tokens)),
+                                                  C.c_int32(shift is not None), C.c_float(0.0 if shift is None else float(shift)),
+                                                  ptr(mask, C.c_double), ptr(out, C.c_float)))
+        return out
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.bm25cu_group_free(self._h)
         self._h = None
 
     def __del__(self):

@@ -77,10 +77,13 @@ def _flatten(id_lists) -> Tuple[np.ndarray, np.ndarray]:
 
 class BM25:
     def __init__(self, k1=1.5, b=0.75, delta=0.5, method="lucene", idf_method=None, dtype="float32",
-                 int_dtype="int32", corpus=None, backend="cuda", csc_backend="cuda", auto_compile=True, device=0):
+                 int_dtype="int32", corpus=None, backend="cuda", csc_backend="cuda", auto_compile=True, device=0,
+                 devices=None):
         """Same parameters as the reference constructor (bm25s/__init__.py:144-157). `backend` must be "cuda"
         (or "auto"); `csc_backend` and `auto_compile` are accepted for signature compatibility and ignored (the
-        CSC matrix is assembled on the GPU). `device` selects the CUDA device (extra, optional)."""
+        CSC matrix is assembled on the GPU). Extra, optional: `device` selects the CUDA device; `devices=[0, 1, ...]` (or
+        the environment variable BM25CU_DEVICES="0,1,...") shards the index by contiguous doc-id ranges over several GPUs
+        of the box, driven from this one process - `index / retrieve / get_scores / save / load` work unchanged."""
         self.k1 = k1
         self.b = b
         self.delta = delta
@@ -93,6 +96,13 @@ class BM25:
         self._original_version = __version__
         self.csc_backend = csc_backend
         self.device = device
+        if devices is None and os.environ.get("BM25CU_DEVICES"):
+            devices = [int(x) for x in os.environ["BM25CU_DEVICES"].replace(";", ",").split(",") if x.strip() != ""]
+        self.devices = None if devices is None else [int(d) for d in devices]
+        if self.devices is not None:
+            if len(self.devices) == 0:
+                raise ValueError("`devices` must be a non-empty list of CUDA device ids")
+            self.device = self.devices[0]
         if backend == "auto":
             backend = "cuda"
         if backend != "cuda":
@@ -113,7 +123,8 @@ class BM25:
         """What the HBM copy was made from: the array OBJECTS themselves (kept alive by the key, so an id cannot be
         reused by another array) plus the sizes. In-place edits of the arrays are not seen: call `invalidate()`."""
         sc = self.scores
-        return (sc["data"], sc["indices"], sc["indptr"], sc["num_docs"], len(sc["data"]), self.nonoccurrence_array, self.device)
+        return (sc["data"], sc["indices"], sc["indptr"], sc["num_docs"], len(sc["data"]), self.nonoccurrence_array,
+                tuple(self.devices) if self.devices else self.device)
 
     @staticmethod
     def _same_key(a, b):
@@ -138,8 +149,12 @@ class BM25:
                     self._dev.close()
                     self._dev = None
                 sc = self.scores
-                self._dev = _lib.DeviceIndex.upload(sc["data"], sc["indices"], sc["indptr"], int(sc["num_docs"]),
-                                                    nonocc=self.nonoccurrence_array, device=self.device)
+                if self.devices is not None and len(self.devices) > 1:
+                    self._dev = _lib.DeviceGroup.upload(sc["data"], sc["indices"], sc["indptr"], int(sc["num_docs"]),
+                                                        nonocc=self.nonoccurrence_array, devices=self.devices)
+                else:
+                    self._dev = _lib.DeviceIndex.upload(sc["data"], sc["indices"], sc["indptr"], int(sc["num_docs"]),
+                                                        nonocc=self.nonoccurrence_array, device=self.device)
                 self._dev_key = key
             return self._dev
 
@@ -186,8 +201,12 @@ class BM25:
         tokens, doc_ptr = _flatten(corpus_token_ids)
         if len(tokens) and (tokens.min() < 0 or tokens.max() >= n_vocab):
             raise ValueError("corpus token ids must lie in [0, len(unique_token_ids))")
-        dev = _lib.DeviceIndex.build(tokens.astype(np.int32), doc_ptr, n_vocab, self.method, self.idf_method,
-                                     float(self.k1), float(self.b), float(self.delta), device=self.device)
+        if self.devices is not None and len(self.devices) > 1:
+            dev = _lib.DeviceGroup.build(tokens.astype(np.int32), doc_ptr, n_vocab, self.method, self.idf_method,
+                                         float(self.k1), float(self.b), float(self.delta), devices=self.devices)
+        else:
+            dev = _lib.DeviceIndex.build(tokens.astype(np.int32), doc_ptr, n_vocab, self.method, self.idf_method,
+                                         float(self.k1), float(self.b), float(self.delta), device=self.device)
         self._adopt_device_index(dev, len(corpus_token_ids))
         return self.scores
 

@@ -191,5 +191,7 @@ int topk_merge_device(const int32_t *ids, const float *scores, int32_t n_parts, 
                       const float *shift_or_null, int32_t *out_ids, float *out_scores, cudaStream_t stream);
 int finalize_index(bm25cu_index *ix);          // device attributes, events, non-negativity scan
 int alloc_postings(bm25cu_index *ix, int64_t nnz);  // d_data / d_indices with bulk-copy padding
+// structural checks of a CSC on the device (indptr monotone, ids in range, rows strictly ascending): BM25CU_EINVAL if not
+int validate_csc(const int32_t *d_indices, const int64_t *d_indptr, int32_t n_vocab, int64_t nnz, int32_t n_docs, cudaStream_t stream);
 
 }  // namespace bm25cu

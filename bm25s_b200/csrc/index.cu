@@ -82,8 +82,8 @@ __global__ void validate_csc_kernel(const int32_t *__restrict__ indices, const i
     if (bad) atomicOr(flags, bad);
 }
 
-static int validate_csc(const int32_t *d_indices, const int64_t *d_indptr, int32_t n_vocab, int64_t nnz, int32_t n_docs,
-                        cudaStream_t stream) {
+int validate_csc(const int32_t *d_indices, const int64_t *d_indptr, int32_t n_vocab, int64_t nnz, int32_t n_docs,
+                 cudaStream_t stream) {
     if (n_vocab <= 0) return BM25CU_OK;
     unsigned int *d_flag = nullptr, flag = 0;
     BM25CU_CHECK(cudaMalloc(&d_flag, sizeof(unsigned int)));

@@ -193,6 +193,38 @@ int bm25cu_exchange_free(bm25cu_exchange *x);
 
 int bm25cu_index_free(bm25cu_index *ix);
 
+/*
+ * One index over SEVERAL GPUs of the box, driven from one process - the multi-device form of the entry points above
+ * (the reference's seam is one constructor string, bm25s/__init__.py:154 / :847; the Python mirror passes
+ * `BM25(backend="cuda", devices=[0, 1, ...])`). Documents are sharded by contiguous doc-id ranges, shard r =
+ * [n_docs * r / n, n_docs * (r + 1) / n) on devices[r]; only a shard's rows travel to its device (_upload) or are built
+ * there (_build: shard-local counting, document frequencies summed on the host, shard-local scoring). _retrieve has the
+ * contract of bm25cu_retrieve: every shard scores the whole batch (the calls are enqueued by one host thread per
+ * device), the shards' rows are copied to devices[0] over NVLink, merged there (score descending, id ascending; the
+ * shift added after the merge, so the rows do not depend on the number of shards) and returned. `weight_mask` is the
+ * whole float64[n_docs] mask. _download returns the whole matrix in the reference's layout (global ids), _scores_dense
+ * fills float32[n_docs]. A group is not thread-safe. No torch, no process group.
+ */
+typedef struct bm25cu_group bm25cu_group;
+int bm25cu_group_upload(const float *data, const int32_t *indices, const int64_t *indptr, int64_t nnz, int32_t n_vocab,
+                        int32_t n_docs, const float *nonocc, const int32_t *devices, int32_t n_devices,
+                        bm25cu_group **out);
+int bm25cu_group_build(const int32_t *tokens, const int64_t *doc_ptr, int32_t n_docs, int32_t n_vocab,
+                       int32_t tfc_method, int32_t idf_method, double k1, double bparam, double delta,
+                       const int32_t *devices, int32_t n_devices, bm25cu_group **out);
+int bm25cu_group_sizes(const bm25cu_group *g, int64_t *nnz, int32_t *n_vocab, int32_t *n_docs, int32_t *n_shards,
+                       int32_t *has_nonocc);
+int bm25cu_group_shard(bm25cu_group *g, int32_t i, bm25cu_index **ix); /* borrowed: freed with the group */
+int bm25cu_group_set_option(bm25cu_group *g, const char *name, int32_t value);
+int bm25cu_group_unset_option(bm25cu_group *g, const char *name);
+int bm25cu_group_download(const bm25cu_group *g, float *data, int32_t *indices, int64_t *indptr, float *nonocc);
+int bm25cu_group_retrieve(bm25cu_group *g, const int32_t *q_tokens, const int64_t *q_ptr, int32_t n_queries, int32_t k,
+                          const float *shift_per_query, const double *weight_mask, int32_t *out_ids,
+                          float *out_scores, bm25cu_stats *stats);
+int bm25cu_group_scores_dense(bm25cu_group *g, const int32_t *q_tokens, int32_t n_tokens, int32_t has_shift,
+                              float shift, const double *weight_mask, float *out);
+int bm25cu_group_free(bm25cu_group *g);
+
 #ifdef __cplusplus
 }
 #endif
