@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "bm25cu_build_free", "bm25cu_index_build", "bm25cu_index_sizes", "bm25cu_index_download", "bm25cu_retrieve",
     "bm25cu_retrieve_device", "bm25cu_retrieve_device_enqueue", "bm25cu_retrieve_collect", "bm25cu_scores_dense", "bm25cu_topk_dense", "bm25cu_topk_merge",
     "bm25cu_topk_merge_device", "bm25cu_index_free", "bm25cu_index_set_option", "bm25cu_index_unset_option",
-    "bm25cu_debug_colkth", "bm25cu_debug_prof",
+    "bm25cu_debug_colkth", "bm25cu_debug_prof", "bm25cu_index_set_mask", "bm25cu_group_set_mask",
     "bm25cu_exchange_create", "bm25cu_exchange_handle_size", "bm25cu_exchange_handle", "bm25cu_exchange_connect",
     "bm25cu_exchange_merge", "bm25cu_exchange_check", "bm25cu_exchange_free",
     "bm25cu_group_upload", "bm25cu_group_build", "bm25cu_group_sizes", "bm25cu_group_shard", "bm25cu_group_set_option",
@@ -97,6 +97,26 @@ def ptr(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 
 
+MASK_NONE, MASK_BITS, MASK_F64 = 0, 1, 2
+
+
+def pack_weight_mask(mask: np.ndarray):
+    """A weight mask in the form the library keeps resident (include/bm25cu.h, bm25cu_index_set_mask): 0/1 masks of any
+    dtype (bool, integers, floats) become one bit per document - multiplying a score by 1 or by 0 is exact, so the bit
+    carries the whole mask - anything else the exact float64 copy. Returns (kind, array)."""
+    m = np.asarray(mask)
+    if m.dtype == np.bool_:
+        keep = m
+    elif m.dtype.kind in "iuf" and (np.count_nonzero(m == 0) + np.count_nonzero(m == 1)) == m.size:
+        keep = m != 0
+    else:
+        return MASK_F64, np.ascontiguousarray(m, dtype=np.float64)
+    packed = np.packbits(keep, bitorder="little")
+    words = np.zeros((len(packed) + 3) // 4 + 1, dtype=np.uint32)
+    words.view(np.uint8)[: len(packed)] = packed
+    return MASK_BITS, words
+
+
 def device_count() -> int:
     n = C.c_int32(0)
     check(lib().bm25cu_device_count(C.byref(n)))
@@ -167,6 +187,12 @@ class DeviceIndex:
                     self.unset_option(k)
                 else:
                     self.set_option(k, v)
+
+    def set_mask(self, kind: int, arr=None):
+        """Resident weight mask of this shard: kind MASK_BITS (uint32 words, bit d%32 of word d//32 = keep local document
+        d), MASK_F64 (float64[n_docs]) or MASK_NONE; applied by every retrieve call that passes no mask of its own."""
+        with self._lock:
+            check(lib().bm25cu_index_set_mask(self._h, C.c_int32(kind), None if arr is None else arr.ctypes.data_as(C.c_void_p)))
 
     def set_stream(self, stream_handle: int):
         check(lib().bm25cu_index_set_stream(self._h, C.c_void_p(stream_handle)))
@@ -327,6 +353,11 @@ class DeviceGroup:
         self._opts.pop(name, None)
 
     options = DeviceIndex.options
+
+    def set_mask(self, kind: int, arr=None):
+        """Resident weight mask over the WHOLE index (the shards take their ranges); see DeviceIndex.set_mask."""
+        with self._lock:
+            check(lib().bm25cu_group_set_mask(self._h, C.c_int32(kind), None if arr is None else arr.ctypes.data_as(C.c_void_p)))
 
     def download(self):
         data = np.empty(self.nnz, np.float32)

@@ -116,6 +116,9 @@ class BM25:
         self._dev = None
         self._dev_key = None
         self._dev_lock = threading.Lock()
+        self._mask_key = None     # what the resident device mask was made from (None: no mask resident)
+        self._mask_sticky = False  # set through set_weight_mask: applies to calls that pass no mask
+        self._mask_keepalive = None
         _lib.lib()  # fail loudly, now, if the CUDA library is missing
 
     # ------------------------------------------------------------------ device residency
@@ -139,6 +142,49 @@ class BM25:
                 self._dev.close()
             self._dev = None
             self._dev_key = None
+            if not self._mask_sticky:
+                self._mask_key = None
+
+    # ------------------------------------------------------------------ weight masks (bm25s/__init__.py:610-612, 833-845)
+    def _check_mask(self, weight_mask):
+        if not isinstance(weight_mask, np.ndarray):
+            raise ValueError("weight_mask must be a numpy array.")
+        if weight_mask.ndim != 1:
+            raise ValueError("weight_mask must be a 1D array.")
+        if len(weight_mask) != self.scores["num_docs"]:
+            raise ValueError("The length of the weight_mask must be the same as the length of the corpus.")
+
+    def _load_mask(self, dev, weight_mask, sticky):
+        """Make `weight_mask` the device-resident mask of `dev` (bit-packed if it is a 0/1 mask). A mask that cannot have
+        changed since it was loaded - the same read-only array object - is not packed or uploaded again."""
+        key = (id(weight_mask), weight_mask.__array_interface__["data"][0], weight_mask.dtype.str, len(weight_mask), id(dev))
+        if self._mask_key == key and not weight_mask.flags.writeable:
+            self._mask_sticky = sticky
+            return
+        kind, arr = _lib.pack_weight_mask(weight_mask)
+        dev.set_mask(kind, arr)
+        self._mask_key = key
+        self._mask_sticky = sticky
+        self._mask_keepalive = weight_mask  # keeps the id from being reused while it is the key
+
+    def set_weight_mask(self, weight_mask):
+        """Extension: keep `weight_mask` resident on the device; every later `retrieve` without a `weight_mask` argument is
+        filtered / weighted by it (no per-call packing or upload). `clear_weight_mask()` removes it."""
+        self._check_mask(weight_mask)
+        with self._mask_lock():
+            self._load_mask(self._device_index(), weight_mask, sticky=True)
+
+    def clear_weight_mask(self):
+        with self._mask_lock():
+            if self._dev is not None and self._mask_key is not None:
+                self._dev.set_mask(_lib.MASK_NONE)
+            self._mask_key, self._mask_sticky, self._mask_keepalive = None, False, None
+
+    def _mask_lock(self):
+        lk = getattr(self, "_mask_lk", None)
+        if lk is None:
+            lk = self._mask_lk = threading.RLock()
+        return lk
 
     def _device_index(self) -> _lib.DeviceIndex:
         """Upload `self.scores` on first use; re-upload if the arrays were swapped (load_scores, direct assignment)."""
@@ -156,6 +202,13 @@ class BM25:
                     self._dev = _lib.DeviceIndex.upload(sc["data"], sc["indices"], sc["indptr"], int(sc["num_docs"]),
                                                         nonocc=self.nonoccurrence_array, device=self.device)
                 self._dev_key = key
+                if self._mask_sticky and self._mask_keepalive is not None:  # a new device copy: the resident mask moves along
+                    kind, arr = _lib.pack_weight_mask(self._mask_keepalive)
+                    self._dev.set_mask(kind, arr)
+                    mk = self._mask_keepalive
+                    self._mask_key = (id(mk), mk.__array_interface__["data"][0], mk.dtype.str, len(mk), id(self._dev))
+                else:
+                    self._mask_key = None
             return self._dev
 
     def _adopt_device_index(self, dev: _lib.DeviceIndex, num_docs: int):
@@ -490,8 +543,15 @@ class BM25:
             out = (np.zeros((nq, k), np.float32), np.zeros((nq, k), np.int64))
             return out + ({},) if with_stats else out
         shift = self._query_shifts(flat, ptr)
-        mask = self._mask_f64(weight_mask)
-        res = self._device_index().retrieve(flat, ptr, k, shift=shift, mask=mask, with_stats=with_stats)
+        dev = self._device_index()
+        with self._mask_lock():
+            if weight_mask is not None:
+                self._check_mask(weight_mask)
+                self._load_mask(dev, weight_mask, sticky=False)  # resident on the device: 1 bit per document for 0/1 masks
+            elif self._mask_key is not None and not self._mask_sticky:
+                dev.set_mask(_lib.MASK_NONE)  # the mask of an earlier call does not outlive it
+                self._mask_key, self._mask_keepalive = None, None
+            res = dev.retrieve(flat, ptr, k, shift=shift, mask=None, with_stats=with_stats)
         ids, scores = res[0], res[1]
         out = (scores, ids.astype(np.int64))
         return out + (res[2],) if with_stats else out

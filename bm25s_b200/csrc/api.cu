@@ -46,6 +46,16 @@ __global__ void mask_check_kernel(const double *__restrict__ mask, int64_t n, Ct
     if (__syncthreads_or(bad) && threadIdx.x == 0) ctrl->mask_bad = 1u;
 }
 
+// The weight mask of a call: the argument if given, else the handle's resident mask (bm25cu_index_set_mask)
+void resolve_mask(const bm25cu_index *ix, const double *call_mask_device, RetrieveArgs &a) {
+    a.mask = call_mask_device;
+    a.mask_bits = nullptr;
+    if (call_mask_device == nullptr) {
+        if (ix->rmask_kind == BM25CU_MASK_F64) a.mask = ix->d_rmask.as<double>();
+        else if (ix->rmask_kind == BM25CU_MASK_BITS) a.mask_bits = ix->d_rmask.as<unsigned int>();
+    }
+}
+
 int run_retrieve_on_device(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, int64_t n_query_tokens,
                            bool time_total_already_started) {
     (void)time_total_already_started;
@@ -148,6 +158,24 @@ int bm25cu_index_set_option(bm25cu_index *ix, const char *name, int32_t value) {
     return BM25CU_OK;
 }
 
+int bm25cu_index_set_mask(bm25cu_index *ix, int32_t kind, const void *mask_host) {
+    BM25CU_REQUIRE(ix != nullptr, "bm25cu_index_set_mask: null handle");
+    BM25CU_REQUIRE(kind == BM25CU_MASK_NONE || kind == BM25CU_MASK_BITS || kind == BM25CU_MASK_F64, "bm25cu_index_set_mask: unknown kind");
+    BM25CU_CHECK(cudaSetDevice(ix->device));
+    BM25CU_CHECK(cudaStreamSynchronize(ix->stream));  // no call in flight reads the old mask
+    ix->rmask_kind = BM25CU_MASK_NONE;
+    if (kind == BM25CU_MASK_NONE) return BM25CU_OK;
+    BM25CU_REQUIRE(mask_host != nullptr, "bm25cu_index_set_mask: null mask");
+    const size_t n = (size_t)(ix->n_docs > 0 ? ix->n_docs : 1);
+    const size_t bytes = kind == BM25CU_MASK_BITS ? ((n + 31) / 32) * 4 : n * sizeof(double);
+    int rc = ix->d_rmask.reserve(bytes);
+    if (rc) return rc;
+    BM25CU_CHECK(cudaMemcpyAsync(ix->d_rmask.p, mask_host, bytes, cudaMemcpyHostToDevice, ix->stream));
+    BM25CU_CHECK(cudaStreamSynchronize(ix->stream));
+    ix->rmask_kind = kind;
+    return BM25CU_OK;
+}
+
 int bm25cu_index_unset_option(bm25cu_index *ix, const char *name) {
     BM25CU_REQUIRE(ix != nullptr && name != nullptr && *name, "bm25cu_index_unset_option: null handle or name");
     ix->knobs.unset(name);
@@ -228,7 +256,7 @@ int bm25cu_retrieve(bm25cu_index *ix, const int32_t *q_tokens, const int64_t *q_
     a.n_queries = n_queries;
     a.k = k;
     a.shift = shift_per_query ? ix->d_shift.as<float>() : nullptr;
-    a.mask = weight_mask ? ix->d_mask.as<double>() : nullptr;
+    resolve_mask(ix, weight_mask ? ix->d_mask.as<double>() : nullptr, a);
     a.out_ids = ix->d_out_ids.as<int32_t>();
     a.out_scores = ix->d_out_scores.as<float>();
     if ((rc = run_retrieve_on_device(ix, a, stats, n_tok, true))) return rc;
@@ -257,7 +285,7 @@ int bm25cu_retrieve_device(bm25cu_index *ix, const int32_t *q_tokens, const int6
     a.n_queries = n_queries;
     a.k = k;
     a.shift = shift_per_query;
-    a.mask = weight_mask;
+    resolve_mask(ix, weight_mask, a);
     a.out_ids = out_ids;
     a.out_scores = out_scores;
     int rc;
@@ -279,7 +307,7 @@ int bm25cu_retrieve_device_enqueue(bm25cu_index *ix, const int32_t *q_tokens, co
     a.n_queries = n_queries;
     a.k = k;
     a.shift = shift_per_query;
-    a.mask = weight_mask;
+    resolve_mask(ix, weight_mask, a);
     a.out_ids = out_ids;
     a.out_scores = out_scores;
     return run_retrieve_on_device(ix, a, nullptr, n_query_tokens, false);

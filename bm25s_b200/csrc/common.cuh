@@ -136,12 +136,14 @@ struct bm25cu_index {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,
-        d_spill, d_order, d_theta, d_fb_list, d_ms_items, d_ms_rows, d_ms_q, d_ms_partial;
+        d_spill, d_order, d_theta, d_fb_list, d_ms_items, d_ms_rows, d_ms_q, d_ms_partial;  // (d_rmask below is not per call)
     int last_launches = 0;         // kernels launched by the last retrieve call
     bool ms_ran = false;           // the last call ran retrieve_ms.cu (ev[5] is recorded behind it)
     bool order_valid = false;      // d_order holds the pull order of the current batch
     bm25cu::PinBuf h_in, h_out;
     int general_rows = 0;
+    int rmask_kind = 0;            // resident weight mask (bm25cu_index_set_mask): 0 none, 1 bitmap, 2 float64; in d_rmask
+    bm25cu::DevBuf d_rmask;
     bm25cu::Knobs knobs;           // BM25CU_* environment at creation + bm25cu_index_set_option
 };
 
@@ -154,7 +156,8 @@ struct RetrieveArgs {
     int32_t n_queries;
     int32_t k;
     const float *shift;  // device or null
-    const double *mask;  // device or null
+    const double *mask;  // device or null: float64 weight per document
+    const unsigned int *mask_bits;  // device or null: a 0/1 weight mask as one bit per document (1 = keep); excludes `mask`
     int32_t *out_ids;    // device [n_queries * k]
     float *out_scores;   // device
 };

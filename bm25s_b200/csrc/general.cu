@@ -81,6 +81,10 @@ retrieve_general_kernel(const float *__restrict__ data, const int32_t *__restric
             for (int64_t d = threadIdx.x; d < n_docs; d += blockDim.x)
                 row[d] = (float)__dmul_rn((double)row[d], a.mask[d]);
             __syncthreads();
+        } else if (a.mask_bits && nq > 0) {  // 0/1 mask as a bitmap: times one is exact, times zero is zero
+            for (int64_t d = threadIdx.x; d < n_docs; d += blockDim.x)
+                if (!((a.mask_bits[d >> 5] >> (d & 31)) & 1u)) row[d] = 0.0f;
+            __syncthreads();
         }
         const float shift = (a.shift && nq > 0) ? a.shift[q] : 0.0f;  // empty query: zeros, no shift (:653-657)
         const bool has_shift = (a.shift != nullptr) && nq > 0;

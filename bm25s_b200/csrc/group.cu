@@ -386,6 +386,34 @@ int bm25cu_group_set_option(bm25cu_group *g, const char *name, int32_t value) {
     return BM25CU_OK;
 }
 
+int bm25cu_group_set_mask(bm25cu_group *g, int32_t kind, const void *mask_host) {
+    BM25CU_REQUIRE(g != nullptr, "bm25cu_group_set_mask: null handle");
+    BM25CU_REQUIRE(kind == BM25CU_MASK_NONE || mask_host != nullptr, "bm25cu_group_set_mask: null mask");
+    for (int r = 0; r < g->n; ++r) {
+        bm25cu_index *ix = g->shard[(size_t)r];
+        int rc;
+        if (kind == BM25CU_MASK_BITS && g->n > 1) {
+            // the shard's bits [lo, hi) of the whole bitmap, shifted down to bit 0
+            const uint32_t *w = static_cast<const uint32_t *>(mask_host);
+            const int64_t lo = ix->doc_base, n = ix->n_docs;
+            std::vector<uint32_t> local((size_t)((n + 31) / 32 + 1), 0u);
+            const int sh = (int)(lo & 31);
+            const int64_t w0 = lo >> 5, n_src = ((int64_t)g->n_docs + 31) / 32;
+            for (int64_t i = 0; i < (n + 31) / 32; ++i) {
+                const uint32_t a = (w0 + i < n_src) ? w[w0 + i] : 0u, b = (w0 + i + 1 < n_src) ? w[w0 + i + 1] : 0u;
+                local[(size_t)i] = sh ? ((a >> sh) | (b << (32 - sh))) : a;
+            }
+            rc = bm25cu_index_set_mask(ix, kind, local.data());
+        } else if (kind == BM25CU_MASK_F64) {
+            rc = bm25cu_index_set_mask(ix, kind, static_cast<const double *>(mask_host) + ix->doc_base);
+        } else {
+            rc = bm25cu_index_set_mask(ix, kind, mask_host);
+        }
+        if (rc) return rc;
+    }
+    return BM25CU_OK;
+}
+
 int bm25cu_group_unset_option(bm25cu_group *g, const char *name) {
     BM25CU_REQUIRE(g != nullptr, "bm25cu_group_unset_option: null handle");
     for (auto *ix : g->shard) {

@@ -547,6 +547,7 @@ static void destroy(bm25cu_index *ix) {
     bm25cu::DevBuf *bufs[] = {&ix->d_qtok, &ix->d_qptr, &ix->d_shift, &ix->d_mask, &ix->d_out_ids, &ix->d_out_scores,
                               &ix->d_ctrl, &ix->d_general_list, &ix->d_scratch, &ix->d_spill, &ix->d_order, &ix->d_theta, &ix->d_fb_list, &ix->d_ms_items, &ix->d_ms_rows, &ix->d_ms_q, &ix->d_ms_partial};
     for (auto *b : bufs) b->release();
+    ix->d_rmask.release();
     ix->h_in.release();
     ix->h_out.release();
     for (int i = 0; i < 6; ++i)

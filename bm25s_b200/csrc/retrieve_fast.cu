@@ -392,6 +392,8 @@ struct Fast {
         if (p.a.mask) {  // weight mask in [0, 1]: numpy multiplies in the promoted type and rounds back to float32
             s = (float)((double)s * p.a.mask[d]);
             if (!(s > *reinterpret_cast<volatile float *>(&h->theta))) return;
+        } else if (p.a.mask_bits) {  // 0/1 mask, one bit per document: a removed document scores 0 and never beats theta >= 0
+            if (!((__ldg(p.a.mask_bits + ((unsigned)d >> 5)) >> ((unsigned)d & 31u)) & 1u)) return;
         }
         const unsigned int slot = atomicAdd(&h->cb_cnt, 1u);
         const unsigned long long c = pack_cand(s, d);
@@ -996,7 +998,7 @@ struct Fast {
                     if (c > best_c) { best_c = c; best_t = t; }
                 }
                 const int m = min(best_c, p.cbcap);
-                if (m >= k && p.a.mask == nullptr && theta == 0.0f) {  // only when the k-th-largest table gave no start value
+                if (m >= k && p.a.mask == nullptr && p.a.mask_bits == nullptr && theta == 0.0f) {  // only when the k-th-largest table gave no start value
                     const int P = next_pow2(m);
                     const float *sc = bpf + h->w_sc[b][best_t];
                     for (int i = ctid; i < P; i += CNT) cb[i] = (i < m) ? ((unsigned long long)__float_as_uint(sc[i]) << 32) : 0ull;
@@ -1300,7 +1302,7 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     p.qcount = qlist ? qcount : nullptr;
     // the k-th-largest table holds ranks 10 / 100 / 1000: rank r bounds every k <= r (k = 1 uses the column maxima)
     p.colkth = nullptr;
-    if (ix->knobs.get("SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {  // a mask may remove the documents behind the bound
+    if (ix->knobs.get("SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr && a.mask_bits == nullptr) {  // a mask may remove the documents behind the bound
         if (a.k == 1) p.colkth = ix->d_colmax;
         else if (a.k <= 10) p.colkth = ix->d_colkth;
         else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
@@ -1326,7 +1328,7 @@ int launch_retrieve_fast(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, 
     if (cb_auto > 4096) cb_auto = 2 * kcap > 4096 ? 2 * kcap : 4096;
     p.cbcap = cb_auto < cb_min ? next_pow2(cb_min) : cb_auto;
     p.route_all_general = (!ix->nonneg) || (a.k > 2048) || ix->knobs.get("FORCE_GENERAL", 0) ||
-                          (a.mask != nullptr && ix->knobs.get("MASK_FAST", 1) == 0);
+                          ((a.mask != nullptr || a.mask_bits != nullptr) && ix->knobs.get("MASK_FAST", 1) == 0);
     const int budget = ix->max_smem_optin / (ctas_per_sm > 0 ? ctas_per_sm : 1) - (ctas_per_sm > 1 ? 1024 : 0);
     const int nw = threads / 32 - 1;
     p.nwarps = nw;

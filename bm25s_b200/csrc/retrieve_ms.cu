@@ -137,7 +137,7 @@ __device__ __forceinline__ int slot_lookup(const uint4 *__restrict__ stab, long 
     return ((a.z >> 31) && a.z != 0xffffffffu) ? -1 : 0;
 }
 
-template <int NT, int UNROLL, int R, bool BIG>
+template <int NT, int UNROLL, int R, bool BIG, bool MB>  // MB: a 0/1 weight mask as a bitmap (its own instantiation: registers)
 struct Ms {
     static constexpr int CHUNK = NT * 4 * UNROLL;
     static constexpr int QCAP = CHUNK + NT * R;
@@ -273,7 +273,7 @@ struct Ms {
             const unsigned u = s.pos2u[t];
             if (u < 16u && ((found >> u) & 1u)) sc = __fadd_rn(sc, (int)u == i ? v : vals[u]);
         }
-        if (p.a.mask) sc = (float)((double)sc * p.a.mask[d]);
+        if (p.a.mask) sc = (float)((double)sc * p.a.mask[d]);  // (a bitmap mask dropped its documents at the start of the round)
         const unsigned long long key = pack_cand(sc, d);
         if (key > tk && sc >= th) { s.pend[atomicAdd(&s.pend_cnt, 1u)] = key; MS_CNT(5, 1); }
     }
@@ -315,6 +315,11 @@ struct Ms {
                 alive[r] = base + r * NT + tid < n && reaches(acc[r], rest, th);
                 found[r] = 1u << i;
                 if (alive[r]) MS_CNT(2, 1);
+            }
+            if (MB) {  // 0/1 weight mask: a document it removes scores 0 and ends here, before any lookup
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (alive[r]) alive[r] = (__ldg(p.a.mask_bits + ((unsigned)d[r] >> 5)) >> ((unsigned)d[r] & 31u)) & 1u;
             }
             // The other lists, largest upper bound first. Per list: the presence tests of the R survivors go out together,
             // the (few) position searches run with the lanes that need one side by side, then the bounds are re-checked.
@@ -686,11 +691,11 @@ __global__ void __launch_bounds__(256) ms_merge_kernel(const unsigned char *__re
     if (lane == 0) atomicAdd(&ctrl->posting_count, qtot[q]);
 }
 
-template <int NT, int UNROLL, int R, int MINB, bool BIG>
+template <int NT, int UNROLL, int R, int MINB, bool BIG, bool MB>
 __global__ void __launch_bounds__(NT, MINB) retrieve_ms_kernel(const __grid_constant__ MsParams p) {
-    __shared__ typename Ms<NT, UNROLL, R, BIG>::Sh sh;
+    __shared__ typename Ms<NT, UNROLL, R, BIG, MB>::Sh sh;
     extern __shared__ __align__(16) unsigned long long ms_dyn[];
-    Ms<NT, UNROLL, R, BIG> m(p, sh, ms_dyn);
+    Ms<NT, UNROLL, R, BIG, MB> m(p, sh, ms_dyn);
     m.run();
 }
 
@@ -735,7 +740,7 @@ __global__ void __launch_bounds__(128) ms_merge_big_kernel(const unsigned char *
 // The batch-wide conditions under which every query would be handed on: the caller skips this file altogether then.
 bool retrieve_ms_takes(const bm25cu_index *ix, const RetrieveArgs &a) {
     const int kmax = ix->knobs.get("MS_KMAX", 1024);  // larger k: the streaming kernel
-    return ix->nonneg && a.k <= kmax && a.k <= 1024 && !(a.mask != nullptr && ix->knobs.get("MASK_FAST", 1) == 0) &&
+    return ix->nonneg && a.k <= kmax && a.k <= 1024 && !((a.mask != nullptr || a.mask_bits != nullptr) && ix->knobs.get("MASK_FAST", 1) == 0) &&
            !ix->knobs.get("FORCE_GENERAL", 0);
 }
 
@@ -746,7 +751,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.indptr = ix->d_indptr;
     p.colmax = ix->d_colmax;
     p.colkth = nullptr;
-    if (ix->knobs.get("SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr) {
+    if (ix->knobs.get("SEED_KTH", 1) && ix->d_colkth && a.mask == nullptr && a.mask_bits == nullptr) {
         if (a.k == 1) p.colkth = ix->d_colmax;
         else if (a.k <= 10) p.colkth = ix->d_colkth;
         else if (a.k <= 100) p.colkth = ix->d_colkth + (size_t)ix->n_vocab;
@@ -822,8 +827,14 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     const int per_sm = ix->knobs.get("MS_CTAS", 9);  // 55 registers: nine 128-thread CTAs are resident per SM
     const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 9);
     const size_t dyn = p.kcap > 32 ? (size_t)2 * p.kcap * 8 : 0;
-    if (p.kcap <= 32) retrieve_ms_kernel<128, 4, 4, 8, false><<<grid, 128, 0, ix->stream>>>(p);
-    else retrieve_ms_kernel<128, 4, 4, 8, true><<<grid, 128, dyn, ix->stream>>>(p);
+    const bool mb = a.mask_bits != nullptr;
+    if (p.kcap <= 32) {
+        if (mb) retrieve_ms_kernel<128, 4, 4, 8, false, true><<<grid, 128, 0, ix->stream>>>(p);
+        else retrieve_ms_kernel<128, 4, 4, 8, false, false><<<grid, 128, 0, ix->stream>>>(p);
+    } else {
+        if (mb) retrieve_ms_kernel<128, 4, 4, 8, true, true><<<grid, 128, dyn, ix->stream>>>(p);
+        else retrieve_ms_kernel<128, 4, 4, 8, true, false><<<grid, 128, dyn, ix->stream>>>(p);
+    }
     BM25CU_CHECK(cudaGetLastError());
     if (p.kcap <= 32)
         ms_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, ix->stream>>>(scratch + nq, part_base, p.partial, qstat, qtot, a, ix->doc_base,

@@ -103,6 +103,16 @@ int bm25cu_index_build(const int32_t *tokens, const int64_t *doc_ptr, int32_t n_
 int bm25cu_index_set_option(bm25cu_index *ix, const char *name, int32_t value);
 int bm25cu_index_unset_option(bm25cu_index *ix, const char *name);
 
+/* Resident weight mask of a handle (bm25s/__init__.py:610-612, 833-845): uploaded once, applied by every later retrieve
+ * call whose weight_mask argument is NULL, until replaced or cleared - a filter used call after call costs nothing per
+ * call. BM25CU_MASK_BITS: a 0/1 mask as uint32 words, bit (d % 32) of word (d / 32) = keep shard-local document d
+ * (multiplying by 1 or by 0 is exact, so one bit per document carries the mask; its documents are dropped before any
+ * lookup). BM25CU_MASK_F64: float64[n_docs_local], as the weight_mask argument. BM25CU_MASK_NONE clears. */
+#define BM25CU_MASK_NONE 0
+#define BM25CU_MASK_BITS 1
+#define BM25CU_MASK_F64 2
+int bm25cu_index_set_mask(bm25cu_index *ix, int32_t kind, const void *mask_host);
+
 /* Diagnostics. _colkth: the upload-time table of the 10th / 100th / 1000th largest score of every column,
  * float32[3][n_vocab] (start values of the pruning threshold). _prof: 48 uint64 phase counters of the last retrieve call
  * (all zero unless the library was built with -DBM25CU_PROFILE: `make prof`). */
@@ -217,6 +227,7 @@ int bm25cu_group_sizes(const bm25cu_group *g, int64_t *nnz, int32_t *n_vocab, in
 int bm25cu_group_shard(bm25cu_group *g, int32_t i, bm25cu_index **ix); /* borrowed: freed with the group */
 int bm25cu_group_set_option(bm25cu_group *g, const char *name, int32_t value);
 int bm25cu_group_unset_option(bm25cu_group *g, const char *name);
+int bm25cu_group_set_mask(bm25cu_group *g, int32_t kind, const void *mask_host); /* the WHOLE mask; shards take their ranges */
 int bm25cu_group_download(const bm25cu_group *g, float *data, int32_t *indices, int64_t *indptr, float *nonocc);
 int bm25cu_group_retrieve(bm25cu_group *g, const int32_t *q_tokens, const int64_t *q_ptr, int32_t n_queries, int32_t k,
                           const float *shift_per_query, const double *weight_mask, int32_t *out_ids,

@@ -240,6 +240,84 @@ def test_weight_mask_fast_path():
     dev.close()
 
 
+def test_resident_weight_masks_bitmap_and_float():
+    """bm25cu_index_set_mask / bm25cu_group_set_mask: a 0/1 mask kept on the device as one bit per document
+    (its documents are dropped before any lookup) and a float64 mask kept resident return exactly what the per-call
+    float64 mask returns - the reference's own masked fixtures - on one device and sharded at unaligned boundaries; the
+    mask stays until cleared."""
+    from bm25s_b200 import DeviceGroup, DeviceIndex, _lib
+
+    g = load_golden("synth_medium")
+    queries = lists_from_flat(g["query_tokens"], g["query_ptr"])
+    k = int(g["k"])
+    N = len(g["corpus_ptr"]) - 1
+    for m in ("lucene", "bm25+"):
+        data, indices, indptr = g[f"{key(m)}_data"], g[f"{key(m)}_indices"], g[f"{key(m)}_indptr"]
+        nonocc = g[f"{key(m)}_nonocc"] if f"{key(m)}_nonocc" in g else None
+        sh = _shifts(nonocc, queries)
+        handles = [DeviceIndex.upload(data, indices, indptr, N, nonocc=nonocc),
+                   DeviceGroup.upload(data, indices, indptr, N, nonocc=nonocc, devices=[0, 0, 0])]
+        for dev in handles:
+            ids0, sc0 = dev.retrieve(g["query_tokens"], g["query_ptr"], k, shift=sh)
+            for mk, want_kind in (("mask01", _lib.MASK_BITS), ("maskf64", _lib.MASK_F64)):
+                kind, arr = _lib.pack_weight_mask(g[mk])
+                assert kind == want_kind
+                dev.set_mask(kind, arr)
+                for variant in ({}, {"MS": 0}, {"FORCE_GENERAL": 1}, {"MS_PARTCOST": 512}):
+                    with dev.options(**variant):
+                        ids, sc, st = dev.retrieve(g["query_tokens"], g["query_ptr"], k, shift=sh, with_stats=True)
+                    np.testing.assert_array_equal(sc, g[f"{key(m)}_scores_{mk}"], err_msg=f"{m} {mk} {variant}")
+                    dfn = lambda qi: O.get_scores(data, indptr, indices, N, queries[qi], nonocc, g[mk])  # noqa: E731
+                    check_topk_rows(ids, sc, ids, g[f"{key(m)}_scores_{mk}"], dfn, what=f"resident {m} {mk} {variant}")
+                # a mask given with the call wins over the resident one
+                ids_c, sc_c = dev.retrieve(g["query_tokens"], g["query_ptr"], k, shift=sh, mask=np.ones(N))
+                np.testing.assert_array_equal(sc_c, sc0)
+            dev.set_mask(_lib.MASK_NONE)
+            ids1, sc1 = dev.retrieve(g["query_tokens"], g["query_ptr"], k, shift=sh)
+            np.testing.assert_array_equal(sc1, sc0)
+            np.testing.assert_array_equal(ids1, ids0)
+            dev.close()
+
+
+def test_bm25_weight_mask_dtypes_and_sticky_mask():
+    """BM25.retrieve(weight_mask=...) with bool / int32 / float32 / float64 0-1 masks (bit-packed on the host, resident on
+    the device) and a fractional mask equals the reference fixtures; a mask does not outlive its call unless it was set
+    with set_weight_mask; a read-only mask object is uploaded once."""
+    from bm25s_b200 import BM25, _lib
+
+    g = load_golden("synth_small")
+    corpus = lists_from_flat(g["corpus_tokens"], g["corpus_ptr"])
+    queries = lists_from_flat(g["query_tokens"], g["query_ptr"])
+    V, k = int(g["n_vocab"]), int(g["k"])
+    r = BM25(method="bm25l", backend="cuda")
+    r.index((corpus, {i: i for i in range(V)}), create_empty_token=False, show_progress=False)
+    plain = r.retrieve(queries, k=k).scores
+    want01, wantf = g["bm25l_scores_mask01"], g["bm25l_scores_maskf64"]
+    for dt in (bool, np.int32, np.float32, np.float64):
+        res = r.retrieve(queries, k=k, weight_mask=g["mask01"].astype(dt))
+        np.testing.assert_array_equal(res.scores, want01, err_msg=str(dt))
+        np.testing.assert_array_equal(r.retrieve(queries, k=k).scores, plain)  # gone with the call
+    np.testing.assert_array_equal(r.retrieve(queries, k=k, weight_mask=g["maskf64"]).scores, wantf)
+    ro = g["mask01"].astype(bool)
+    ro.setflags(write=False)
+    calls = []
+    orig = _lib.DeviceIndex.set_mask
+    _lib.DeviceIndex.set_mask = lambda self, kind, arr=None: (calls.append(kind), orig(self, kind, arr))[1]
+    try:
+        for _ in range(3):
+            np.testing.assert_array_equal(r.retrieve(queries, k=k, weight_mask=ro).scores, want01)
+        assert calls == [_lib.MASK_BITS]  # packed and uploaded once
+    finally:
+        _lib.DeviceIndex.set_mask = orig
+    r.set_weight_mask(g["mask01"])
+    np.testing.assert_array_equal(r.retrieve(queries, k=k).scores, want01)
+    np.testing.assert_array_equal(r.retrieve(queries, k=k).scores, want01)
+    r.clear_weight_mask()
+    np.testing.assert_array_equal(r.retrieve(queries, k=k).scores, plain)
+    with pytest.raises(ValueError):
+        r.retrieve(queries, k=k, weight_mask=np.ones(3))
+
+
 def test_kth_largest_table_and_seeded_threshold():
     """The upload-time table of per-column 10th / 100th / 1000th largest scores (start value of the pruning threshold)
     equals numpy's, and results with and without the seeded threshold are identical."""
