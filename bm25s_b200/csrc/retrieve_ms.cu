@@ -144,7 +144,7 @@ struct Ms {
     struct Sh {
         long long beg[16];
         unsigned long long top[32];
-        unsigned long long pend[BIG ? 1024 : NT * R + 32];  // BIG: sorted in place, padded to a power of two
+        unsigned long long pend[BIG ? (NT * R + 512 <= 1024 ? 1024 : 2048) : NT * R + 32];  // BIG: sorted in place, padded to a power of two (a round adds at most NT * R keys to at most 512 waiting ones)
         unsigned long long theta_key;
         int df[16];
         float ub[16];
@@ -783,7 +783,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
         if (rc0) return rc0;
         p.theta_io = ix->d_theta.as<float>();
     }
-    p.big_merge_at = (unsigned int)ix->knobs.get("MS_BIGMERGE", 128);
+    p.big_merge_at = (unsigned int)ix->knobs.get("MS_BIGMERGE", 512);
     if (p.big_merge_at > 512u) p.big_merge_at = 512u;
     if (p.big_merge_at < 1u) p.big_merge_at = 1u;
     // plan: parts of at most `part_cost` postings (BM25CU_MS_PARTCOST), at most BM25CU_MS_MAXPARTS per query
@@ -800,7 +800,10 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     // 1.34 -> 1.20 ms; a 1/8 shard of the MS-MARCO shape: 0.81 -> 0.68 ms)
     const int per_sm_cfg = ix->knobs.get("MS_CTAS", 9);
     const bool small = a.n_queries < 3 * ix->sm_count * per_sm_cfg || ix->nnz < 300000000ll;
-    const long long part_cost = (long long)ix->knobs.get("MS_PARTCOST", small ? 32768 : 65536);
+    // larger top lists: every part has to fill a top list of its own before it prunes, so parts are made coarser
+    // (k = 1000 at the MS-MARCO shape: 13.2 ms with 65 536, 9.5 ms with 524 288 postings per part)
+    const int k_scale = p.kcap <= 32 ? 1 : (p.kcap <= 64 ? 2 : (p.kcap <= 128 ? 4 : 8));
+    const long long part_cost = (long long)ix->knobs.get("MS_PARTCOST", (small ? 32768 : 65536) * k_scale);
     const size_t nq = (size_t)a.n_queries;
     int rc;
     if ((rc = ix->d_ms_items.reserve(nq * (size_t)max_parts * 8))) return rc;
@@ -831,6 +834,18 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     if (p.kcap <= 32) {
         if (mb) retrieve_ms_kernel<128, 4, 4, 8, false, true><<<grid, 128, 0, ix->stream>>>(p);
         else retrieve_ms_kernel<128, 4, 4, 8, false, false><<<grid, 128, 0, ix->stream>>>(p);
+    } else if (ix->knobs.get("MS_BIG_NT", 256) == 256) {
+        // shared-memory top lists: CTAs of 256 threads, four per SM - twice the survivors per probe round and per merge of
+        // the pending keys (k = 1000 at the MS-MARCO shape: 9.5 -> 8.7 ms)
+        const int per_sm_b = ix->knobs.get("MS_CTAS", 4);
+        const int grid_b = ix->sm_count * (per_sm_b > 0 ? per_sm_b : 4);
+        if (mb) {
+            BM25CU_CHECK(cudaFuncSetAttribute(retrieve_ms_kernel<256, 4, 4, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            retrieve_ms_kernel<256, 4, 4, 4, true, true><<<grid_b, 256, dyn, ix->stream>>>(p);
+        } else {
+            BM25CU_CHECK(cudaFuncSetAttribute(retrieve_ms_kernel<256, 4, 4, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            retrieve_ms_kernel<256, 4, 4, 4, true, false><<<grid_b, 256, dyn, ix->stream>>>(p);
+        }
     } else {
         if (mb) retrieve_ms_kernel<128, 4, 4, 8, true, true><<<grid, 128, dyn, ix->stream>>>(p);
         else retrieve_ms_kernel<128, 4, 4, 8, true, false><<<grid, 128, dyn, ix->stream>>>(p);

@@ -196,7 +196,9 @@ def test_random_corpus_vs_c_oracle(k):
                 {"BM25CU_MS_BUDGET": "64"}, {"BM25CU_MS_BUDGET": "600", "BM25CU_MS_PARTCOST": "4096"},
                 {"BM25CU_MS_BTAB": "0"}, {"BM25CU_MS_PBM": "0"}, {"BM25CU_MS_BTAB": "0", "BM25CU_MS_PBM": "0", "BM25CU_SEED_KTH": "0"},
                 # lookups without the slot tables (bucket table + id slice + score), slot tables with many parts
-                {"MS_STAB": 0}, {"MS_STAB": 0, "MS_PBM": 0}, {"MS_PARTCOST": 512, "MS_PBM": 0}):
+                {"MS_STAB": 0}, {"MS_STAB": 0, "MS_PBM": 0}, {"MS_PARTCOST": 512, "MS_PBM": 0},
+                # top lists in shared memory (k > 32): 128-thread CTAs, early / late merges of the pending keys
+                {"MS_BIG_NT": 128}, {"MS_BIG_NT": 128, "MS_BIGMERGE": 1}, {"MS_BIGMERGE": 64, "MS_PARTCOST": 2048}):
         with dev.options(**env):
             ids2, sc2 = dev.retrieve(flat, ptr, k, shift=sh)
         np.testing.assert_array_equal(sc2, sc)
