@@ -11,7 +11,8 @@ import threading
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "libbm25cu.so")
+# BM25CU_LIBRARY=checked | prof selects the instrumented builds of the same sources (`make checked`, `make prof`)
+SO_PATH = os.path.join(_PKG, {"checked": "libbm25cu_checked.so", "prof": "libbm25cu_prof.so"}.get(os.environ.get("BM25CU_LIBRARY", ""), "libbm25cu.so"))
 CSRC = os.path.join(_PKG, "csrc")
 
 METHOD_CODES = {"robertson": 0, "lucene": 1, "atire": 2, "bm25l": 3, "bm25+": 4}

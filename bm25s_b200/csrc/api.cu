@@ -116,6 +116,10 @@ int finish_stats(bm25cu_index *ix, const RetrieveArgs &a, bm25cu_stats *stats, i
         set_error("The maximum token ID in the query is higher than the number of tokens in the index.");
         return BM25CU_EINVAL;
     }
+    if (h.error & 8u) {
+        set_error("internal error: a bounds check of the checked build failed in retrieve_ms.cu");
+        return BM25CU_ECUDA;
+    }
     if (h.error & 4u) {
         set_error("internal error: candidate buffer overflow in the fused kernel");
         return BM25CU_ECUDA;

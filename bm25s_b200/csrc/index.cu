@@ -266,6 +266,7 @@ static int build_bucket_tables(bm25cu_index *ix) {
                                                                                 ix->d_btab_sh, ix->d_btab_off, ix->d_btab);
     BM25CU_CHECK(cudaGetLastError());
     ix->aux_bytes += (size_t)total * 4;
+    ix->btab_len = total;
     return BM25CU_OK;
 }
 
@@ -340,6 +341,7 @@ static int build_presence_bitmaps(bm25cu_index *ix) {
                                                                                ix->d_pbm_off, ix->d_pbm);
     BM25CU_CHECK(cudaGetLastError());
     ix->aux_bytes += (size_t)total * 4;
+    ix->pbm_len = total;
     return BM25CU_OK;
 }
 
@@ -463,6 +465,7 @@ static int build_slot_tables(bm25cu_index *ix) {
                                                                                 ix->d_stab_off, reinterpret_cast<uint2 *>(ix->d_stab));
     BM25CU_CHECK(cudaGetLastError());
     ix->aux_bytes += bytes;
+    ix->stab_len = total;
     return BM25CU_OK;
 }
 

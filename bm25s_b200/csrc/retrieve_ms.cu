@@ -39,6 +39,7 @@ struct MsParams {
     const unsigned int *pbm;    // presence bitmaps (index.cu) or nullptr
     const long long *pbm_off;
     const unsigned char *pbm_sh;
+    long long nnz, btab_len, pbm_len, stab_len, partial_rows;  // array extents, read by the bounds checks of `make checked` only
     const uint4 *stab;          // slot tables (index.cu) or nullptr: a bucket is two uint4 = four (doc id, score) slots
     const long long *stab_off;
     const unsigned char *stab_sh;
@@ -59,6 +60,15 @@ struct MsParams {
     float *theta_io;                  // experiment (BM25CU_DEBUG_THETA): 1 = the merge kernel records every query's final
     int theta_mode;                   // threshold, 2 = every part starts from the recorded value (what a perfect start buys)
 };
+
+// `make checked` (-DBM25CU_CHECKED; compute-sanitizer is not available on the GPU pool): every index this kernel computes
+// into the posting arrays, the lookup structures, the shared-memory queues and the partial-result rows is compared with
+// the array's extent; a violation sets error bit 3 ("bounds check failed") and the access is skipped.
+#ifdef BM25CU_CHECKED
+#define MS_OK(cond) ((cond) ? true : (atomicOr(&p.ctrl->error, 8u), false))
+#else
+#define MS_OK(cond) true
+#endif
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ unsigned long long shfl64_xor(unsigned long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
@@ -183,6 +193,7 @@ struct Ms {
         const long long po = s.pb_off[j];
         if (po >= 0) {
             const unsigned x = (unsigned)d >> s.pb_sh[j];
+            if (!MS_OK(po + (x >> 5) < p.pbm_len)) return false;
             if (!((__ldg(p.pbm + po + (x >> 5)) >> (x & 31u)) & 1u)) return false;
             MS_CNT(13, 1);
         }
@@ -238,6 +249,7 @@ struct Ms {
     __device__ __forceinline__ bool search(int j, int d, float &val) {
         const long long so = s.st_off[j];
         if (so >= 0) {
+            if (!MS_OK(so + (long long)((unsigned)d >> s.st_sh[j]) < p.stab_len)) return false;
             const int r = slot_lookup(p.stab, so, s.st_sh[j], d, val);
             if (r >= 0) { if (r) MS_CNT(15, 1); return r != 0; }
         }
@@ -246,8 +258,10 @@ struct Ms {
         const long long bo = s.bt_off[j];
         if (bo >= 0) {
             const unsigned b = (unsigned)d >> s.bt_sh[j];
+            if (!MS_OK(bo + b + 1 < p.btab_len)) return false;
             lo = (int)__ldg(p.btab + bo + b);
             hi = (int)__ldg(p.btab + bo + b + 1);
+            if (!MS_OK(lo >= 0 && hi <= s.df[j])) return false;
         }
         const int32_t *col = p.indices + beg;
         while (lo < hi) {
@@ -275,7 +289,11 @@ struct Ms {
         }
         if (p.a.mask) sc = (float)((double)sc * p.a.mask[d]);  // (a bitmap mask dropped its documents at the start of the round)
         const unsigned long long key = pack_cand(sc, d);
-        if (key > tk && sc >= th) { s.pend[atomicAdd(&s.pend_cnt, 1u)] = key; MS_CNT(5, 1); }
+        if (key > tk && sc >= th) {
+            const unsigned at = atomicAdd(&s.pend_cnt, 1u);
+            if (MS_OK(at < sizeof(s.pend) / sizeof(s.pend[0]))) s.pend[at] = key;
+            MS_CNT(5, 1);
+        }
     }
 
     // A round: every thread takes R survivors; their (doc, score) loads and the presence test of the next list are
@@ -305,7 +323,8 @@ struct Ms {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const unsigned idx = base + r * NT + tid;
-                const long long at = beg + ((idx < n) ? s.queue[idx] : 0u);
+                long long at = beg + ((idx < n) ? s.queue[idx] : 0u);
+                if (!MS_OK(idx >= n || (idx < (unsigned)QCAP && at >= 0 && at < p.nnz))) at = beg;
                 d[r] = __ldg(p.indices + at);
                 v[r] = __ldg(p.data + at);
             }
@@ -330,7 +349,7 @@ struct Ms {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const unsigned x = (unsigned)d[r] >> psh;
-                    w[r] = (po >= 0 && alive[r]) ? __ldg(p.pbm + po + (x >> 5)) : 0xffffffffu;
+                    w[r] = (po >= 0 && alive[r] && MS_OK(po + (x >> 5) < p.pbm_len)) ? __ldg(p.pbm + po + (x >> 5)) : 0xffffffffu;
                 }
                 unsigned todo = 0u;
 #pragma unroll
@@ -386,7 +405,11 @@ struct Ms {
 
     __device__ __forceinline__ void check(float v, int pos, int df, int lo, float m, float rest, float th) {
         if (__fmul_ru(__fmaf_ru(m, v, rest), 1.00002f) >= th && (unsigned)pos < (unsigned)df)
-        { s.queue[atomicAdd(&s.q_cnt, 1u)] = (unsigned)(pos + lo); MS_CNT(1, 1); }
+        {
+            const unsigned at = atomicAdd(&s.q_cnt, 1u);
+            if (MS_OK(at < (unsigned)QCAP)) s.queue[at] = (unsigned)(pos + lo);
+            MS_CNT(1, 1);
+        }
     }
 
     __device__ bool stream(int i, int tid, int k, unsigned int *gq) {
@@ -577,10 +600,11 @@ struct Ms {
                     if (tid == 0) s.route = 1;
                 } else if (BIG) {
                     const unsigned long long *cur = big + (s.top_sel ? kcap : 0);
-                    for (int t = tid; t < k; t += NT) p.partial[((size_t)p.part_base[q] + part) * k + t] = cur[t];
+                    if (MS_OK((long long)p.part_base[q] + part < p.partial_rows))
+                        for (int t = tid; t < k; t += NT) p.partial[((size_t)p.part_base[q] + part) * k + t] = cur[t];
                 } else if (tid < 32) {
                     // the part's top list (sorted, zeros = empty); merged, checked and written by ms_merge_kernel
-                    if (tid < k) p.partial[((size_t)p.part_base[q] + part) * k + tid] = s.top[tid];
+                    if (tid < k && MS_OK((long long)p.part_base[q] + part < p.partial_rows)) p.partial[((size_t)p.part_base[q] + part) * k + tid] = s.top[tid];
                 }
                 __syncthreads();
             }
@@ -767,6 +791,11 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.stab = (use_bt && ix->knobs.get("MS_STAB", 1) && ix->d_stab) ? reinterpret_cast<const uint4 *>(ix->d_stab) : nullptr;
     p.stab_off = ix->d_stab_off;
     p.stab_sh = ix->d_stab_sh;
+    p.nnz = ix->nnz + kPadElems;
+    p.btab_len = ix->btab_len;
+    p.pbm_len = ix->pbm_len;
+    p.stab_len = ix->stab_len;
+    p.partial_rows = 0;  // set below, once the number of parts is known
     p.n_docs = ix->n_docs;
     p.n_vocab = ix->n_vocab;
     p.doc_base = ix->doc_base;
@@ -827,6 +856,7 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     p.gtheta = gtheta;
     p.qstat = qstat;
     p.partial = ix->d_ms_partial.as<unsigned long long>();
+    p.partial_rows = (long long)nq * max_parts;
     const int per_sm = ix->knobs.get("MS_CTAS", 9);  // 55 registers: nine 128-thread CTAs are resident per SM
     const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 9);
     const size_t dyn = p.kcap > 32 ? (size_t)2 * p.kcap * 8 : 0;

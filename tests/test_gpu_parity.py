@@ -320,6 +320,25 @@ def test_bm25_weight_mask_dtypes_and_sticky_mask():
         r.retrieve(queries, k=k, weight_mask=np.ones(3))
 
 
+def test_checked_build_finds_no_out_of_range_access():
+    """`make checked` (bm25s_b200/libbm25cu_checked.so: -DBM25CU_CHECKED, device-side bounds checks of every index the
+    list-at-a-time kernel computes; compute-sanitizer is not available on the GPU pool): the workload of
+    tools/sanitizer_workload.py - every kernel path, masks, parts, several shards - runs clean and equals the oracle."""
+    import subprocess
+    import sys
+
+    from bm25s_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(os.path.dirname(_lib.SO_PATH), "libbm25cu_checked.so")
+    if not os.path.exists(so):
+        pytest.skip("libbm25cu_checked.so has not been built (make -C bm25s_b200/csrc checked)")
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitizer_workload.py")], capture_output=True, text=True,
+                         timeout=900, cwd=root, env=dict(os.environ, BM25CU_LIBRARY="checked"))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "sanitizer workload ok" in res.stdout and "libbm25cu_checked.so" in res.stdout
+
+
 def test_kth_largest_table_and_seeded_threshold():
     """The upload-time table of per-column 10th / 100th / 1000th largest scores (start value of the pruning threshold)
     equals numpy's, and results with and without the seeded threshold are identical."""

@@ -10,6 +10,6 @@ run --shape msmarco --k 10
 run --shape msmarco --k 100
 run --shape msmarco --k 1000
 run --shape nq --k 10
-run --shape nq --k 10 --method bm25+
-run --shape nq --k 10 --method bm25l
+run --shape nq --k 10 --method bm25+ --queries 10000
+run --shape nq --k 10 --method bm25l --queries 10000
 run --shape scifact --k 10
