@@ -563,6 +563,7 @@ def main():
         ev[it][0].record()
         step_device(q_tok, q_ptr)
         ev[it][1].record()
+    sh.join()  # N > 1: the last merges run on the exchange's side stream; the timed region ends behind them
     ev1.record()
     barrier()
     stats = sh.collect()  # one synchronisation; errors of the last call, stats of its scoring kernels
@@ -655,15 +656,16 @@ def main():
             "n_general": int(stats_acc[-1]["n_general"]), "nnz_local": int(nnz), "index_build_s": round(build_s, 3)}
     if world > 1:
         line["exchange"] = {"kind": args.exchange, "same_as_all_gather_merge": exchange_check}
-        # per-rank split of a step: scoring kernels (library events) and the whole chain; the difference is the exchange,
-        # the merge and the wait for the slowest shard
+        # per-rank split of a step: the scoring kernels (library events, separately collected steps) and what a step takes
+        # on the rank's main stream in the timed loop (scoring + push; the merge and the wait for the slowest shard run on
+        # the exchange's side stream, next to the following step's scoring)
         mine = torch.tensor([fast_ms, step_ms_local], device=device, dtype=torch.float64)
         allr = torch.empty((world, 2), device=device, dtype=torch.float64)
         dist.all_gather_into_tensor(allr.view(-1), mine)
         allr = allr.cpu().numpy()
-        line["per_rank"] = {"kernel_ms": [round(float(x), 4) for x in allr[:, 0]], "step_ms": [round(float(x), 4) for x in allr[:, 1]],
+        line["per_rank"] = {"kernel_ms": [round(float(x), 4) for x in allr[:, 0]], "main_stream_step_ms": [round(float(x), 4) for x in allr[:, 1]],
                             "kernel_ms_min": float(allr[:, 0].min()), "kernel_ms_max": float(allr[:, 0].max()),
-                            "exchange_merge_wait_ms": [round(float(b - a), 4) for a, b in allr]}
+                            "ms_per_step_minus_slowest_kernel": round(ms_per_step - float(allr[:, 0].max()), 4)}
 
     if rank == 0 and world == 1:
         # the user-facing call, Python lists in -> numpy arrays out (BM25.retrieve of the mirror class,
@@ -693,6 +695,8 @@ def main():
                                     threads=max(1, (os.cpu_count() or world) // world))
         if rank == 0:
             line["parity_vs_cpu_port"] = par
+    if world > 1:
+        barrier()  # every rank is idle from here on; ranks > 0 wait on the host for rank 0's untimed checks
     if want_cpu:
         if csc_host is None and not local_shards(args, world):
             csc_host, _ = unsharded_csc(args, device, local_rank)  # N > 1: rank 0 rebuilds the whole matrix, untimed
@@ -732,9 +736,23 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        host_side_rendezvous(dist, rank, world, "bm25_bench_rank0_done")
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def host_side_rendezvous(dist, rank, world, tag):
+    """Ranks > 0 wait on the host (process-group store) until rank 0 has passed the same point: unlike dist.barrier() no
+    kernel spins on their GPUs meanwhile, so rank 0 can measure on ALL devices of the box (the single-process group)."""
+    try:
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set(tag, "1")
+        else:
+            store.wait([tag])
+    except Exception:  # noqa: BLE001
+        pass
 
 
 if __name__ == "__main__":

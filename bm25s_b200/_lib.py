@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "bm25cu_topk_merge_device", "bm25cu_index_free", "bm25cu_index_set_option", "bm25cu_index_unset_option",
     "bm25cu_debug_colkth", "bm25cu_debug_prof", "bm25cu_index_set_mask", "bm25cu_group_set_mask",
     "bm25cu_exchange_create", "bm25cu_exchange_handle_size", "bm25cu_exchange_handle", "bm25cu_exchange_connect",
-    "bm25cu_exchange_merge", "bm25cu_exchange_check", "bm25cu_exchange_free",
+    "bm25cu_exchange_merge", "bm25cu_exchange_check", "bm25cu_exchange_join", "bm25cu_exchange_free",
     "bm25cu_group_upload", "bm25cu_group_build", "bm25cu_group_sizes", "bm25cu_group_shard", "bm25cu_group_set_option",
     "bm25cu_group_unset_option", "bm25cu_group_download", "bm25cu_group_retrieve", "bm25cu_group_scores_dense",
     "bm25cu_group_free",
@@ -526,7 +526,12 @@ class PeerExchange:
                                           C.c_void_p(out_scores_ptr), C.c_void_p(stream)))
 
     def check(self, stream=0):
+        """Make `stream` wait for the last merge, synchronise it and raise if a peer never delivered."""
         check(lib().bm25cu_exchange_check(self._h, C.c_void_p(stream)))
+
+    def join(self, stream=0):
+        """Make `stream` wait (on the device) for the merge enqueued last - it runs on a side stream of the exchange."""
+        check(lib().bm25cu_exchange_join(self._h, C.c_void_p(stream)))
 
     def close(self):
         if self._h is not None and _lib is not None:

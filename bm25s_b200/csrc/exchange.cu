@@ -7,16 +7,20 @@
 //      writes), fences them system-wide and raises a per-source flag on every peer to the call's epoch;
 //   2. runs the MERGE kernel on its own copy: a CTA per query waits until the world flags reached the epoch, then sorts
 //      the world * k pairs in shared memory (same order as bm25cu_topk_merge: score descending, id ascending).
-// Two kernels on the caller's stream, no host round trip, no collective library call. Buffers are double-buffered by
-// epoch parity: a rank can start pushing call e + 2 only after its merge of call e + 1 ended, which needs every peer's
-// push of e + 1, which every peer enqueues behind its own merge of call e - so nobody overwrites rows still being read.
+// Two kernels, no host round trip, no collective library call. The push runs on the caller's stream, the merge on a side
+// stream of the exchange (behind an event): waiting for the slowest shard and merging overlap the scoring kernels of the
+// caller's NEXT batch; bm25cu_exchange_check / _join make the caller's stream wait for the merge. Buffers are
+// double-buffered by epoch parity; a rank's merge of call e ends by raising a "consumed" flag on every peer, and the
+// push of call e + 2 - the next user of that parity - waits for all peers' flags, so nobody overwrites rows still being
+// read (the wait is over before it starts unless a peer is a whole call behind).
 #include "common.cuh"
 #include "select.cuh"
 
 namespace {
 
 constexpr int kMaxWorld = 16;
-constexpr size_t kFlagBytes = 512;  // unsigned int flags[2][kMaxWorld], padded
+constexpr size_t kFlagBytes = 512;  // unsigned int flags[2][kMaxWorld] (rows arrived), consumed[kMaxWorld] at word 64, padded
+constexpr int kConsumedWord = 64;
 
 struct ExchangeView {
     int32_t *ids[2];   // [world][cap]
@@ -44,7 +48,22 @@ struct PeerPtrs {
 
 __global__ void __launch_bounds__(256) exchange_push_kernel(const int32_t *__restrict__ ids, const float *__restrict__ scores,
                                                             long long n, PeerPtrs peers, int rank, int world, long long cap,
-                                                            int parity, unsigned int epoch, unsigned int *done_counter) {
+                                                            int parity, unsigned int epoch, unsigned int *done_counter,
+                                                            unsigned int *err) {
+    // every peer has merged call epoch - 2, the previous user of this parity's buffers (its merge raised consumed[peer]
+    // in OUR memory); normally long true
+    if (epoch > 2u && threadIdx.x < world) {
+        const ExchangeView mine = view_of(peers.p[rank], world, cap);
+        volatile unsigned int *c = mine.flags + kConsumedWord + threadIdx.x;
+        unsigned long long t0 = 0, now = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(*c - (epoch - 2u)) < 0) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 10000000000ull) { atomicOr(err, 2u); break; }
+        }
+    }
+    __syncthreads();
     for (int pr = 0; pr < world; ++pr) {
         const ExchangeView v = view_of(peers.p[pr], world, cap);
         int32_t *di = v.ids[parity] + (size_t)rank * cap;
@@ -88,6 +107,25 @@ __device__ __forceinline__ void wait_for_peers(const ExchangeView &v, int world,
     __syncthreads();
 }
 
+// End of a merge kernel: the last block to finish tells every peer that this rank is done reading the rows of `epoch`.
+__device__ __forceinline__ void raise_consumed(PeerPtrs peers, int rank, int world, long long cap, unsigned int epoch,
+                                               unsigned int *merge_counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(merge_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *merge_counter = 0u;
+            __threadfence_system();
+            for (int pr = 0; pr < world; ++pr) {
+                const ExchangeView v = view_of(peers.p[pr], world, cap);
+                volatile unsigned int *c = v.flags + kConsumedWord + rank;
+                *c = epoch;
+            }
+            __threadfence_system();
+        }
+    }
+}
+
 __device__ __forceinline__ unsigned long long xshfl64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ unsigned long long xshfl64_xor(unsigned long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
@@ -98,11 +136,12 @@ __device__ __forceinline__ unsigned long long xshfl64_xor(unsigned long long v, 
 // shards. Eight queries per CTA, one flag wait per CTA.
 __global__ void __launch_bounds__(256) exchange_merge_warp_kernel(void *local, int world, long long cap, int parity, unsigned int epoch,
                                                                   int n_queries, int k, const float *__restrict__ shift,
-                                                                  int32_t *out_ids, float *out_scores, unsigned int *err) {
+                                                                  int32_t *out_ids, float *out_scores, unsigned int *err,
+                                                                  PeerPtrs peers, int rank, unsigned int *merge_counter) {
     const ExchangeView v = view_of(local, world, cap);
     wait_for_peers(v, world, parity, epoch, err);
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (q >= n_queries) return;
+    if (q >= n_queries) { raise_consumed(peers, rank, world, cap, epoch, merge_counter); return; }
     const int32_t *ids = v.ids[parity];
     const float *scores = v.scores[parity];
     unsigned long long t = 0ull;
@@ -142,11 +181,13 @@ __global__ void __launch_bounds__(256) exchange_merge_warp_kernel(void *local, i
         out_ids[(size_t)q * k + lane] = d;
         out_scores[(size_t)q * k + lane] = sc;
     }
+    raise_consumed(peers, rank, world, cap, epoch, merge_counter);
 }
 
 __global__ void __launch_bounds__(256) exchange_merge_kernel(void *local, int world, long long cap, int parity, unsigned int epoch,
                                                              int n_queries, int k, int P, const float *__restrict__ shift,
-                                                             int32_t *out_ids, float *out_scores, unsigned int *err) {
+                                                             int32_t *out_ids, float *out_scores, unsigned int *err,
+                                                             PeerPtrs peers, int rank, unsigned int *merge_counter) {
     extern __shared__ unsigned char smem_raw[];
     uint32_t *key = reinterpret_cast<uint32_t *>(smem_raw);
     int32_t *id = reinterpret_cast<int32_t *>(key + P);
@@ -182,6 +223,7 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(void *local, int wo
         out_ids[(size_t)q * k + j] = d;
         out_scores[(size_t)q * k + j] = s;
     }
+    raise_consumed(peers, rank, world, cap, epoch, merge_counter);
 }
 
 }  // namespace
@@ -193,8 +235,11 @@ struct bm25cu_exchange {
     void *peer[kMaxWorld] = {nullptr};
     bool connected = false;
     unsigned int epoch = 0;
-    unsigned int *d_counter = nullptr;  // [0] block counter of the push kernel, [1] error bits of the merge kernel
+    unsigned int *d_counter = nullptr;  // [0] block counter of the push kernel, [1] error bits, [2] block counter of the merge kernel
     size_t bytes = 0;
+    cudaStream_t side = nullptr;        // the merge runs here, behind ev_pushed; ev_merged marks its end
+    cudaEvent_t ev_pushed = nullptr, ev_merged = nullptr;
+    bool merged_pending = false;
 };
 
 using namespace bm25cu;
@@ -214,12 +259,18 @@ int bm25cu_exchange_create(int32_t device, int32_t rank, int32_t world, int64_t 
     x->bytes = kFlagBytes + (size_t)2 * 2 * world * x->cap * 4;
     cudaError_t e = cudaMalloc(&x->local, x->bytes);
     if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&x->d_counter, 2 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(x->d_counter, 0, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_counter, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(x->d_counter, 0, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_pushed, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_merged, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         set_error(std::string("bm25cu_exchange_create: ") + cudaGetErrorString(e));
         cudaFree(x->local);
         cudaFree(x->d_counter);
+        if (x->side) cudaStreamDestroy(x->side);
+        if (x->ev_pushed) cudaEventDestroy(x->ev_pushed);
+        if (x->ev_merged) cudaEventDestroy(x->ev_merged);
         delete x;
         return e == cudaErrorMemoryAllocation ? BM25CU_ENOMEM : BM25CU_ECUDA;
     }
@@ -271,21 +322,29 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
     for (int r = 0; r < kMaxWorld; ++r) pp.p[r] = r < x->world ? x->peer[r] : nullptr;
     int grid = (int)((n + 255) / 256);
     if (grid > 592) grid = 592;
-    exchange_push_kernel<<<grid, 256, 0, st>>>(ids_device, scores_device, n, pp, x->rank, x->world, x->cap, parity, epoch, x->d_counter);
+    exchange_push_kernel<<<grid, 256, 0, st>>>(ids_device, scores_device, n, pp, x->rank, x->world, x->cap, parity, epoch, x->d_counter,
+                                               x->d_counter + 1);
     BM25CU_CHECK(cudaGetLastError());
+    // the merge (and its wait for the slowest shard) runs on the side stream: the caller's stream is free for the next batch
+    BM25CU_CHECK(cudaEventRecord(x->ev_pushed, st));
+    BM25CU_CHECK(cudaStreamWaitEvent(x->side, x->ev_pushed, 0));
+    st = x->side;
     if (k <= 32) {
         exchange_merge_warp_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k,
                                                                        shift_per_query_device, out_ids_device, out_scores_device,
-                                                                       x->d_counter + 1);
+                                                                       x->d_counter + 1, pp, x->rank, x->d_counter + 2);
     } else {
         const int P = next_pow2(x->world * k);
         const size_t smem = (size_t)P * 8;
         BM25CU_REQUIRE(smem <= 200 * 1024, "bm25cu_exchange_merge: world * k too large for one CTA (max 25600 pairs)");
         BM25CU_CHECK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         exchange_merge_kernel<<<n_queries, 256, smem, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k, P,
-                                                           shift_per_query_device, out_ids_device, out_scores_device, x->d_counter + 1);
+                                                           shift_per_query_device, out_ids_device, out_scores_device, x->d_counter + 1,
+                                                           pp, x->rank, x->d_counter + 2);
     }
     BM25CU_CHECK(cudaGetLastError());
+    BM25CU_CHECK(cudaEventRecord(x->ev_merged, x->side));
+    x->merged_pending = true;
     return BM25CU_OK;
 }
 
@@ -293,13 +352,23 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
 int bm25cu_exchange_check(bm25cu_exchange *x, void *stream) {
     BM25CU_REQUIRE(x != nullptr, "bm25cu_exchange_check: null handle");
     BM25CU_CHECK(cudaSetDevice(x->device));
+    if (x->merged_pending) BM25CU_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, x->ev_merged, 0));
     unsigned int err = 0;
     BM25CU_CHECK(cudaMemcpyAsync(&err, x->d_counter + 1, sizeof(err), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     BM25CU_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     if (err) {
-        set_error("bm25cu_exchange: a peer's rows did not arrive within 10 s");
+        set_error(err & 1u ? "bm25cu_exchange: a peer's rows did not arrive within 10 s"
+                           : "bm25cu_exchange: a peer did not finish merging the call before last within 10 s");
         return BM25CU_ECUDA;
     }
+    return BM25CU_OK;
+}
+
+/* make `stream` wait for the merge enqueued last (no host synchronisation): work enqueued on it afterwards sees the rows */
+int bm25cu_exchange_join(bm25cu_exchange *x, void *stream) {
+    BM25CU_REQUIRE(x != nullptr, "bm25cu_exchange_join: null handle");
+    BM25CU_CHECK(cudaSetDevice(x->device));
+    if (x->merged_pending) BM25CU_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, x->ev_merged, 0));
     return BM25CU_OK;
 }
 
@@ -311,6 +380,9 @@ int bm25cu_exchange_free(bm25cu_exchange *x) {
         if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
     cudaFree(x->local);
     cudaFree(x->d_counter);
+    if (x->side) cudaStreamDestroy(x->side);
+    if (x->ev_pushed) cudaEventDestroy(x->ev_pushed);
+    if (x->ev_merged) cudaEventDestroy(x->ev_merged);
     delete x;
     return BM25CU_OK;
 }

@@ -7,6 +7,7 @@
 // come back to the host. No torch, no process group: `torch.distributed` + the peer-memory exchange of exchange.cu stay
 // the form for one process per GPU.
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -501,6 +502,9 @@ int bm25cu_group_retrieve(bm25cu_group *g, const int32_t *q_tokens, const int64_
     std::memcpy(hin, q_ptr, ptr_bytes);
     if (n_tok) std::memcpy(hin + off_tok, q_tokens, (size_t)n_tok * sizeof(int32_t));
     if (shift_per_query) std::memcpy(hin + off_shift, shift_per_query, (size_t)n_queries * 4);
+    const bool timing = g->shard[0]->knobs.get("TIME", 0) != 0;  // debugging: host time of the phases of a call
+    auto tick = []() { return std::chrono::steady_clock::now(); };
+    auto t0 = tick();
     // every shard: queries up, scoring kernels (no shift: it is added after the merge), rows over to the first device
     rc = g->pool->run([&](int r) {
         bm25cu_index *ix = g->shard[(size_t)r];
@@ -528,6 +532,7 @@ int bm25cu_group_retrieve(bm25cu_group *g, const int32_t *q_tokens, const int64_
         return BM25CU_OK;
     });
     if (rc) return rc;
+    auto t1 = tick();
     // the first device: wait for every shard's rows, merge, rows down
     BM25CU_CHECK(cudaSetDevice(root));
     cudaStream_t st = g->shard[0]->stream;
@@ -540,6 +545,7 @@ int bm25cu_group_retrieve(bm25cu_group *g, const int32_t *q_tokens, const int64_
     char *hout = g->h_out.as<char>();
     BM25CU_CHECK(cudaMemcpyAsync(hout, g->m_ids.p, rows * 4, cudaMemcpyDeviceToHost, st));
     BM25CU_CHECK(cudaMemcpyAsync(hout + rows * 4, g->m_scores.p, rows * 4, cudaMemcpyDeviceToHost, st));
+    auto t2 = tick();
     // errors / stats of the shards (synchronises their streams), then the first device's stream
     bm25cu_stats acc;
     std::memset(&acc, 0, sizeof(acc));
@@ -556,6 +562,12 @@ int bm25cu_group_retrieve(bm25cu_group *g, const int32_t *q_tokens, const int64_
     }
     BM25CU_CHECK(cudaSetDevice(root));
     BM25CU_CHECK(cudaStreamSynchronize(st));
+    if (timing) {
+        auto t3 = tick();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[bm25cu group] enqueue on %d shards %.3f ms, merge enqueue %.3f ms, collect + sync %.3f ms (kernels %.3f ms)\n", g->n,
+                ms(t0, t1), ms(t1, t2), ms(t2, t3), acc.kernel_ms);
+    }
     acc.launches += 1;  // the merge
     acc.n_fast = n_queries - acc.n_general;
     acc.algorithmic_bytes = acc.posting_bytes + 20 * n_tok + (int64_t)8 * k * n_queries;

@@ -157,7 +157,7 @@ class ShardedIndex:
     def retrieve_device_enqueue(self, q_tokens, q_ptr, k, shift=None, stream=None, out=None, work=None):
         """The chain of `retrieve_device` without its synchronisation: scoring kernels of this shard, stores into the
         peers' memory and the merge are enqueued on `stream` (default: torch's current stream) and the merged
-        (ids, scores) CUDA tensors are returned at once; call `collect` before reading them on the host. `out` / `work`:
+        (ids, scores) CUDA tensors are returned at once; call `collect` (or `join`, to stay on the device) before reading them. `out` / `work`:
         optional preallocated (ids int32[Q,k], scores float32[Q,k]) pairs for the merged and the shard-local rows."""
         import torch
 
@@ -201,6 +201,13 @@ class ShardedIndex:
             _lib.C.c_void_p(g_ids.data_ptr()), _lib.C.c_void_p(g_sc.data_ptr()), self.world, nq, k, _lib.C.c_void_p(shift_ptr),
             _lib.C.c_void_p(m_ids.data_ptr()), _lib.C.c_void_p(m_sc.data_ptr()), self.device, _lib.C.c_void_p(st.cuda_stream)))
         return m_ids, m_sc
+
+    def join(self, stream=None):
+        """Make `stream` (default: the stream of the last enqueue) wait on the device for the merge enqueued last: with the
+        peer-memory exchange the merge runs on a side stream, so that the scoring kernels of the next batch need not wait
+        for the slowest shard of this one."""
+        if self.world > 1 and getattr(self, "_exchange", None) is not None and getattr(self, "_pending", None) is not None:
+            self._exchange.join(self._pending[3] if stream is None else stream.cuda_stream)
 
     def collect(self):
         """Synchronise the chain enqueued last, raise its errors (token id out of range, a peer that never delivered)

@@ -187,8 +187,10 @@ int bm25cu_topk_merge_device(const int32_t *ids, const float *scores, int32_t n_
  * (rank-major, its own slot is ignored) and, after a barrier, calls bm25cu_exchange_merge once per batch on every rank:
  * the local rows (device pointers, as written by bm25cu_retrieve_device WITHOUT a shift) are stored into every peer's
  * buffer, and the merged rows [n_queries][k] (score descending, id ascending; the BM25L / BM25+ shift, if given, added
- * after the merge) appear in out_* on every rank. Two kernels on `stream`,
- * nothing is synchronised; bm25cu_exchange_check synchronises and reports a peer that never delivered.
+ * after the merge) appear in out_* on every rank. The push kernel runs on `stream`, the merge kernel - which waits for the
+ * slowest shard - on a side stream of the exchange, so `stream` is free for the scoring kernels of the next batch;
+ * nothing is synchronised. bm25cu_exchange_join makes a stream wait for the last merge (device-side), bm25cu_exchange_check
+ * does that, synchronises the stream and reports a peer that never delivered: call one of them before out_* is read.
  */
 typedef struct bm25cu_exchange bm25cu_exchange;
 int bm25cu_exchange_create(int32_t device, int32_t rank, int32_t world, int64_t max_elems, bm25cu_exchange **out);
@@ -199,6 +201,7 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
                           int32_t k, const float *shift_per_query_device, int32_t *out_ids_device,
                           float *out_scores_device, void *stream);
 int bm25cu_exchange_check(bm25cu_exchange *x, void *stream);
+int bm25cu_exchange_join(bm25cu_exchange *x, void *stream);
 int bm25cu_exchange_free(bm25cu_exchange *x);
 
 int bm25cu_index_free(bm25cu_index *ix);
