@@ -184,41 +184,34 @@ __global__ void __launch_bounds__(256) exchange_merge_warp_kernel(void *local, i
     raise_consumed(peers, rank, world, cap, epoch, merge_counter);
 }
 
+// k > 32: one CTA per query; the ranks' rows (sorted by their producers) are rank-merged one after the other in shared
+// memory (select.cuh, block_merge_sorted_rows) - for k = 1000 and 8 ranks 16 k binary searches per query where a bitonic
+// sort of all world * k pairs took 370 k compare-exchanges.
 __global__ void __launch_bounds__(256) exchange_merge_kernel(void *local, int world, long long cap, int parity, unsigned int epoch,
-                                                             int n_queries, int k, int P, const float *__restrict__ shift,
+                                                             int n_queries, int k, int kcap, const float *__restrict__ shift,
                                                              int32_t *out_ids, float *out_scores, unsigned int *err,
                                                              PeerPtrs peers, int rank, unsigned int *merge_counter) {
-    extern __shared__ unsigned char smem_raw[];
-    uint32_t *key = reinterpret_cast<uint32_t *>(smem_raw);
-    int32_t *id = reinterpret_cast<int32_t *>(key + P);
+    extern __shared__ __align__(16) unsigned long long xm[];  // cur, nxt, row: kcap keys each
     const ExchangeView v = view_of(local, world, cap);
     wait_for_peers(v, world, parity, epoch, err);
     const int q = blockIdx.x;
-    const int total = world * k;
     const int32_t *ids = v.ids[parity];
     const float *scores = v.scores[parity];
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        uint32_t kk = 0u;
-        int32_t ii = 0x7fffffff;
-        if (i < total) {
-            const int p = i / k, j = i - p * k;
-            const size_t src = (size_t)p * cap + (size_t)q * k + j;
-            const int32_t d = __ldcv(ids + src);  // written by a peer: never from a stale cache line
-            if (d >= 0) { kk = bm25cu::f32_key(__ldcv(scores + src)); ii = d; }
-        }
-        key[i] = kk;
-        id[i] = ii;
-    }
-    bm25cu::block_bitonic_sort_desc<uint32_t, int32_t>(key, id, P);
+    auto load = [&](int r, int j) -> unsigned long long {
+        const size_t src = (size_t)r * cap + (size_t)q * k + j;
+        const int32_t d = __ldcv(ids + src);  // written by a peer: never from a stale cache line
+        return d >= 0 ? (((unsigned long long)bm25cu::f32_key(__ldcv(scores + src)) << 32) | (unsigned int)(~d)) : 0ull;
+    };
+    const unsigned long long *top = bm25cu::block_merge_sorted_rows(world, k, kcap, xm, xm + kcap, xm + 2 * kcap, load);
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        const uint32_t kk = key[j];
-        int32_t d = id[j];
-        float s;
-        if (d == 0x7fffffff) { d = -1; s = __int_as_float(0xff800000); }
-        else {
-            const uint32_t u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk;
-            s = __uint_as_float(u);
+        const unsigned long long t = top[j];
+        int32_t d = -1;
+        float s = __int_as_float(0xff800000);
+        if (t != 0ull) {
+            const uint32_t kk = (uint32_t)(t >> 32);
+            s = __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk);
             if (shift != nullptr) s = __fadd_rn(s, shift[q]);
+            d = (int32_t)~(unsigned int)(t & 0xffffffffu);
         }
         out_ids[(size_t)q * k + j] = d;
         out_scores[(size_t)q * k + j] = s;
@@ -334,11 +327,11 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
                                                                        shift_per_query_device, out_ids_device, out_scores_device,
                                                                        x->d_counter + 1, pp, x->rank, x->d_counter + 2);
     } else {
-        const int P = next_pow2(x->world * k);
-        const size_t smem = (size_t)P * 8;
-        BM25CU_REQUIRE(smem <= 200 * 1024, "bm25cu_exchange_merge: world * k too large for one CTA (max 25600 pairs)");
+        const int kcap = next_pow2(k);
+        const size_t smem = (size_t)3 * kcap * 8;
+        BM25CU_REQUIRE(smem <= 200 * 1024, "bm25cu_exchange_merge: k too large for one CTA (max 8192)");
         BM25CU_CHECK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        exchange_merge_kernel<<<n_queries, 256, smem, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k, P,
+        exchange_merge_kernel<<<n_queries, 256, smem, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k, kcap,
                                                            shift_per_query_device, out_ids_device, out_scores_device, x->d_counter + 1,
                                                            pp, x->rank, x->d_counter + 2);
     }

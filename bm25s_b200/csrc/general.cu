@@ -204,6 +204,7 @@ int topk_dense_device(const void *d_scores, int is_f64, int64_t n, int32_t k, in
 // ---------------------------------------------------------------------------------------------------------
 // Merge of per-shard top-k lists (doc-range sharding): one CTA per query sorts n_parts * k pairs.
 // ---------------------------------------------------------------------------------------------------------
+// Small n_parts * k: one CTA bitonic-sorts all pairs.
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const int32_t *__restrict__ ids, const float *__restrict__ scores, int n_parts, int n_queries, int k,
                   int P, const float *__restrict__ shift, int32_t *out_ids, float *out_scores) {
@@ -241,9 +242,45 @@ topk_merge_kernel(const int32_t *__restrict__ ids, const float *__restrict__ sco
     }
 }
 
+// Larger k: the parts' rows (sorted by their producers) are rank-merged one after the other (select.cuh,
+// block_merge_sorted_rows); same total order - score descending, id ascending.
+__global__ void __launch_bounds__(256)
+topk_merge_rows_kernel(const int32_t *__restrict__ ids, const float *__restrict__ scores, int n_parts, int n_queries, int k,
+                       int kcap, const float *__restrict__ shift, int32_t *out_ids, float *out_scores) {
+    extern __shared__ __align__(16) unsigned long long tm[];  // cur, nxt, row: kcap keys each
+    const int q = blockIdx.x;
+    auto load = [&](int r, int j) -> unsigned long long {
+        const size_t src = ((size_t)r * n_queries + q) * k + j;
+        const int32_t d = ids[src];
+        return d >= 0 ? (((unsigned long long)f32_key(scores[src]) << 32) | (unsigned int)(~d)) : 0ull;
+    };
+    const unsigned long long *top = block_merge_sorted_rows(n_parts, k, kcap, tm, tm + kcap, tm + 2 * kcap, load);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const unsigned long long t = top[j];
+        int32_t d = -1;
+        float s = __int_as_float(0xff800000);
+        if (t != 0ull) {
+            const uint32_t kk = (uint32_t)(t >> 32);
+            s = __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk);
+            if (shift != nullptr) s = __fadd_rn(s, shift[q]);
+            d = (int32_t)~(unsigned int)(t & 0xffffffffu);
+        }
+        out_ids[(size_t)q * k + j] = d;
+        out_scores[(size_t)q * k + j] = s;
+    }
+}
+
 int topk_merge_device(const int32_t *ids, const float *scores, int32_t n_parts, int32_t n_queries, int32_t k,
                       const float *shift, int32_t *out_ids, float *out_scores, cudaStream_t stream) {
     if (n_queries == 0 || k == 0) return BM25CU_OK;
+    const int kcap = next_pow2(k);
+    if (n_parts * k > 256 && (size_t)3 * kcap * 8 <= 200 * 1024) {
+        const size_t smem = (size_t)3 * kcap * 8;
+        BM25CU_CHECK(cudaFuncSetAttribute(topk_merge_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        topk_merge_rows_kernel<<<n_queries, 256, smem, stream>>>(ids, scores, n_parts, n_queries, k, kcap, shift, out_ids, out_scores);
+        BM25CU_CHECK(cudaGetLastError());
+        return BM25CU_OK;
+    }
     const int P = next_pow2(n_parts * k);
     const size_t smem = (size_t)P * 8;
     BM25CU_REQUIRE(smem <= 200 * 1024, "bm25cu_topk_merge: n_parts * k too large for one CTA (max 25600 pairs)");

@@ -94,39 +94,6 @@ __device__ __forceinline__ bool reaches(float acc, float rest, float th) {
     return __fmul_ru(__fadd_ru(acc, rest), 1.00002f) >= th;
 }
 
-// Block-wide: `add[0..cnt)` (descending, distinct non-zero keys) merged into `cur[0..cap)` (descending, zeros = empty);
-// the cap largest go to `nxt` (rank of an element = its index + how many keys of the other list beat it).
-__device__ __forceinline__ void rank_merge(const unsigned long long *cur, unsigned long long *nxt, int cap,
-                                           const unsigned long long *add, int cnt, int tid, int nt) {
-    for (int a = tid; a < cap; a += nt) {
-        const unsigned long long key = cur[a];
-        int lo = 0, hi = cnt;  // first add[i] <= key
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (add[mid] > key) lo = mid + 1; else hi = mid; }
-        if (a + lo < cap) nxt[a + lo] = key;
-    }
-    for (int b = tid; b < cnt; b += nt) {
-        const unsigned long long key = add[b];
-        int lo = 0, hi = cap;  // first cur[i] < key
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cur[mid] > key) lo = mid + 1; else hi = mid; }
-        if (b + lo < cap) nxt[b + lo] = key;
-    }
-}
-
-// Block-wide bitonic sort, descending, n a power of two, keys in shared memory
-__device__ __forceinline__ void block_sort_desc(unsigned long long *a, int n, int tid, int nt) {
-    for (int size = 2; size <= n; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (n >> 1); t += nt) {
-                const int lo = ((t / stride) * stride << 1) + (t % stride), hi = lo + stride;
-                const bool desc = (lo & size) == 0;
-                const unsigned long long x = a[lo], y = a[hi];
-                if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 // Slot-table lookup of document d (index.cu, build_slot_tables): the 32-byte sector of d's half of its 64-byte bucket,
 // four (doc id, score) slots; flagged sectors lent postings to the other sector of the line. 1: found (val), 0: absent,
 // -1: the bucket holds more than its slots and d is not among them - search the column.
