@@ -127,6 +127,7 @@ struct bm25cu_index {
     void *d_stab = nullptr;             // slot tables of the long columns: 32-byte buckets of four (doc id, score) slots
     long long *d_stab_off = nullptr;    // i64[n_vocab] first bucket of a column's table, -1: none
     unsigned char *d_stab_sh = nullptr; // u8[n_vocab] log2 of the bucket width in documents
+    bool stab_compact = false;          // the tables use the compact sector format: 16-bit doc offsets, five slots per sector (STAB_COMPACT)
     long long btab_len = 0, pbm_len = 0, stab_len = 0;  // entries of d_btab / words of d_pbm / buckets of d_stab (bounds checks of `make checked`)
     size_t aux_bytes = 0;               // bytes of the lookup structures derived at upload (bucket tables + presence bitmaps)
     bool nonneg = true;            // all data >= 0 and finite: the fused streaming kernel is exact

@@ -364,8 +364,8 @@ __device__ __forceinline__ int stab_shift_of(long long df, int n_docs, int load1
     return s;
 }
 
-__global__ void stab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_vocab, int32_t n_docs, int load10, long long *sizes,
-                                 unsigned char *shifts) {
+__global__ void stab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_vocab, int32_t n_docs, int load10, int compact,
+                                 long long *sizes, unsigned char *shifts) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_vocab) return;
     const long long df = indptr[t + 1] - indptr[t];
@@ -373,7 +373,8 @@ __global__ void stab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_v
     int sh = 0;
     if (df >= kBtabMinDf) {
         sh = stab_shift_of(df, n_docs, load10);
-        sz = ((long long)(n_docs - 1) >> sh) + 1;  // buckets
+        // compact format: buckets wider than 16-bit offsets reach get no table (rare columns, searched through their bucket tables)
+        if (!compact || sh <= 16) sz = ((long long)(n_docs - 1) >> sh) + 1;  // buckets
     }
     sizes[t] = sz;
     shifts[t] = (unsigned char)sh;
@@ -382,20 +383,28 @@ __global__ void stab_size_kernel(const int64_t *__restrict__ indptr, int32_t n_v
 // One warp per column, one lane per posting. Rows of a column ascend, so the postings of a bucket are neighbours and the
 // postings of its lower half come first: a lane finds its bucket's extent, the two halves' counts and its own rank by
 // looking at most kStabScan postings back and ahead, and derives its slot (or none) and the flags from those alone.
+// Two sector formats, one per index (knob STAB_COMPACT):
+//   wide    four slots, uint2 {doc id, score bits}; bit 31 of slot 0's id = "look at the other sector, too", bit 31 of slot
+//           1's id = "look in the column itself"
+//   compact (lossless compression by tile-local 16-bit doc offsets, applied where the bytes are) a doc id is
+//           stored as its 16-bit offset inside the bucket (the bucket number is the rest of the id), which makes room for
+//           FIVE slots per 32-byte sector: words 0..2 = offsets 0..4 and a 16-bit meta field, words 3..7 = the five scores.
+//           meta is stored inverted (an untouched sector, all ones, decodes to "empty"): bits 0..4 = slot valid, bit 5 =
+//           "look at the other sector, too", bit 6 = "look in the column itself".
 __global__ void stab_fill_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices, const int64_t *__restrict__ indptr,
                                  int32_t n_vocab, const unsigned char *__restrict__ shifts, long long *offs /* in: scan, out: -1 for none */,
-                                 uint2 *slots) {
+                                 const long long *__restrict__ sizes, unsigned int *slots, int compact) {
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n_vocab) return;
     const long long beg = indptr[warp], df = indptr[warp + 1] - beg;
-    if (df < kBtabMinDf) {
+    if (sizes[warp] == 0) {  // short column, or buckets wider than 16-bit offsets reach: no table
         __syncwarp();
         if (lane == 0) offs[warp] = -1;
         return;
     }
     const int sh = shifts[warp];
-    uint2 *tab = slots + offs[warp] * kStabSlots;
+    unsigned int *tab = slots + offs[warp] * 16;  // 16 words per bucket, sector h = words 8 h .. 8 h + 7
     const int32_t *col = indices + beg;
     for (long long i = lane; i < df; i += 32) {
         const int32_t d = col[i];
@@ -411,21 +420,49 @@ __global__ void stab_fill_kernel(const float *__restrict__ data, const int32_t *
             if ((int)(((unsigned)col[i + after + 1] >> (sh - 1)) & 1u) == h) ++after_same;
             ++after;
         }
-        const bool huge = before >= kStabScan || after >= kStabScan;  // extent unknown: everything past four per half overflows to the column
+        const int S = compact ? 5 : 4;                                 // slots per sector
+        const bool huge = before >= kStabScan || after >= kStabScan;  // extent unknown: everything past S per half overflows to the column
         const int mine = before_same + 1 + after_same;                 // postings of this half
         const int other = before + after + 1 - mine;                   // postings of the other half
         const int rank = before_same;
-        const int room = other >= 4 ? 0 : 4 - other;                   // free slots of the other sector
-        const int extra = mine > 4 ? mine - 4 : 0;
+        const int room = other >= S ? 0 : S - other;                   // free slots of the other sector
+        const int extra = mine > S ? mine - S : 0;
         const bool fits = !huge && extra <= room;
-        uint2 *sec = tab + (size_t)b * kStabSlots;
-        unsigned id = (unsigned)d;
-        if (rank < 4) {
-            if (rank == 0 && extra > 0) id |= 0x80000000u;           // look at the other sector, too
-            if (rank == 1 && extra > 0 && !fits) id |= 0x80000000u;  // ... and in the column itself
-            sec[h * 4 + rank] = make_uint2(id, __float_as_uint(data[beg + i]));
-        } else if (!huge && rank - 4 < room) {
-            sec[(1 - h) * 4 + 3 - (rank - 4)] = make_uint2(id, __float_as_uint(data[beg + i]));  // lent slot, from the top
+        unsigned int *bk = tab + (size_t)b * 16;
+        const unsigned sbits = __float_as_uint(data[beg + i]);
+        if (!compact) {
+            uint2 *sec = reinterpret_cast<uint2 *>(bk);
+            unsigned id = (unsigned)d;
+            if (rank < 4) {
+                if (rank == 0 && extra > 0) id |= 0x80000000u;           // look at the other sector, too
+                if (rank == 1 && extra > 0 && !fits) id |= 0x80000000u;  // ... and in the column itself
+                sec[h * 4 + rank] = make_uint2(id, sbits);
+            } else if (!huge && rank - 4 < room) {
+                sec[(1 - h) * 4 + 3 - (rank - 4)] = make_uint2(id, sbits);  // lent slot, from the top
+            }
+            continue;
+        }
+        const unsigned short off16 = (unsigned short)((unsigned)d & ((1u << sh) - 1u));
+        unsigned short *own16 = reinterpret_cast<unsigned short *>(bk + h * 8), *sib16 = reinterpret_cast<unsigned short *>(bk + (1 - h) * 8);
+        if (rank < 5) {
+            own16[rank] = off16;
+            bk[h * 8 + 3 + rank] = sbits;
+        } else if (!huge && rank - 5 < room) {
+            const int slot = 4 - (rank - 5);  // lent slot of the other sector, from the top
+            sib16[slot] = off16;
+            bk[(1 - h) * 8 + 3 + slot] = sbits;
+        }
+        if (rank == 0) {
+            // the first posting of a half writes the sector's meta field: its own slots, the slots lent to it, the flags
+            const int lent_in = huge ? 0 : min(max(other - 5, 0), 5 - min(mine, 5));
+            unsigned meta = ((1u << min(mine, 5)) - 1u) | (((1u << lent_in) - 1u) << (5 - lent_in));
+            if (extra > 0) meta |= 32u;
+            if (extra > 0 && !fits) meta |= 64u;
+            own16[5] = (unsigned short)~meta;
+            if (other == 0 && extra > 0 && !huge) {  // the other half has no posting of its own: its meta is written here, too
+                const int lent = min(extra, 5);
+                sib16[5] = (unsigned short)~(((1u << lent) - 1u) << (5 - lent));
+            }
         }
     }
 }
@@ -442,18 +479,19 @@ static int build_slot_tables(bm25cu_index *ix) {
     int load10 = ix->knobs.get("STAB_LOAD", 30);  // average postings per bucket, times ten, at most
     if (load10 < 10) load10 = 10;
     if (load10 > 80) load10 = 80;
-    stab_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, load10, d_sizes, ix->d_stab_sh);
+    ix->stab_compact = ix->knobs.get("STAB_COMPACT", 0) != 0;
+    stab_size_kernel<<<(V + 255) / 256, 256, 0, ix->stream>>>(ix->d_indptr, V, ix->n_docs, load10, ix->stab_compact ? 1 : 0, d_sizes, ix->d_stab_sh);
     BM25CU_CHECK(cudaGetLastError());
     BM25CU_CHECK(exclusive_scan<long long>(d_sizes, V, ix->d_stab_off, d_tmp, ix->stream));
     long long total = 0;
     BM25CU_CHECK(cudaMemcpyAsync(&total, ix->d_stab_off + V, sizeof(long long), cudaMemcpyDeviceToHost, ix->stream));
     BM25CU_CHECK(cudaStreamSynchronize(ix->stream));
-    cudaFree(d_sizes);
     cudaFree(d_tmp);
     const size_t bytes = (size_t)(total > 0 ? total : 1) * kStabSlots * 8;
     cudaError_t e = cudaMalloc(&ix->d_stab, bytes);
     if (e != cudaSuccess) {  // not enough HBM for the tables: lookups take the bucket-table path
         cudaGetLastError();
+        cudaFree(d_sizes);
         cudaFree(ix->d_stab_off); ix->d_stab_off = nullptr;
         cudaFree(ix->d_stab_sh); ix->d_stab_sh = nullptr;
         ix->d_stab = nullptr;
@@ -462,8 +500,11 @@ static int build_slot_tables(bm25cu_index *ix) {
     BM25CU_CHECK(cudaMemsetAsync(ix->d_stab, 0xff, bytes, ix->stream));
     const long long threads = (long long)V * 32;
     stab_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ix->stream>>>(ix->d_data, ix->d_indices, ix->d_indptr, V, ix->d_stab_sh,
-                                                                                ix->d_stab_off, reinterpret_cast<uint2 *>(ix->d_stab));
+                                                                                ix->d_stab_off, d_sizes, reinterpret_cast<unsigned int *>(ix->d_stab),
+                                                                                ix->stab_compact ? 1 : 0);
     BM25CU_CHECK(cudaGetLastError());
+    BM25CU_CHECK(cudaStreamSynchronize(ix->stream));
+    cudaFree(d_sizes);
     ix->aux_bytes += bytes;
     ix->stab_len = total;
     return BM25CU_OK;

@@ -40,7 +40,7 @@ struct MsParams {
     const long long *pbm_off;
     const unsigned char *pbm_sh;
     long long nnz, btab_len, pbm_len, stab_len, partial_rows;  // array extents, read by the bounds checks of `make checked` only
-    const uint4 *stab;          // slot tables (index.cu) or nullptr: a bucket is two uint4 = four (doc id, score) slots
+    const uint4 *stab;          // slot tables (index.cu) or nullptr: a bucket is four uint4 = two sectors
     const long long *stab_off;
     const unsigned char *stab_sh;
     int32_t n_docs, n_vocab, doc_base;
@@ -94,13 +94,34 @@ __device__ __forceinline__ bool reaches(float acc, float rest, float th) {
     return __fmul_ru(__fadd_ru(acc, rest), 1.00002f) >= th;
 }
 
-// Slot-table lookup of document d (index.cu, build_slot_tables): the 32-byte sector of d's half of its 64-byte bucket,
-// four (doc id, score) slots; flagged sectors lent postings to the other sector of the line. 1: found (val), 0: absent,
-// -1: the bucket holds more than its slots and d is not among them - search the column.
+// Slot-table lookup of document d (index.cu, build_slot_tables): the 32-byte sector of d's half of its 64-byte bucket;
+// flagged sectors lent postings to the other sector of the line. 1: found (val), 0: absent, -1: the bucket holds more
+// than its slots and d is not among them - search the column. Two sector formats, one per index (STAB_COMPACT):
+//   wide    four (doc id, score) pairs;
+//   compact five 16-bit doc offsets inside the bucket + a meta field (words 0..2), then the five scores (words 3..7).
+__device__ __forceinline__ bool sector_match(const uint4 a, const uint4 b, unsigned off, unsigned meta, float &val) {
+    if ((meta & 1u) && (a.x & 0xffffu) == off) { val = __uint_as_float(a.w); return true; }
+    if ((meta & 2u) && (a.x >> 16) == off) { val = __uint_as_float(b.x); return true; }
+    if ((meta & 4u) && (a.y & 0xffffu) == off) { val = __uint_as_float(b.y); return true; }
+    if ((meta & 8u) && (a.y >> 16) == off) { val = __uint_as_float(b.z); return true; }
+    if ((meta & 16u) && (a.z & 0xffffu) == off) { val = __uint_as_float(b.w); return true; }
+    return false;
+}
+
+template <bool CP>
 __device__ __forceinline__ int slot_lookup(const uint4 *__restrict__ stab, long long first_bucket, int sh, int d, float &val) {
     const uint4 *bk = stab + ((first_bucket + (long long)((unsigned)d >> sh)) << 2);
     const unsigned h = ((unsigned)d >> (sh - 1)) & 1u;
     const uint4 a = __ldg(bk + 2 * h), b = __ldg(bk + 2 * h + 1);
+    if (CP) {
+        const unsigned off = (unsigned)d & ((1u << sh) - 1u);
+        const unsigned meta = ~(a.z >> 16);  // stored inverted: an untouched sector (all ones) is empty
+        if (sector_match(a, b, off, meta, val)) return 1;
+        if (!(meta & 32u)) return 0;
+        const uint4 c = __ldg(bk + 2 * (1u - h)), e = __ldg(bk + 2 * (1u - h) + 1);  // the other sector of the same 64-byte line
+        if (sector_match(c, e, off, ~(c.z >> 16), val)) return 1;
+        return (meta & 64u) ? -1 : 0;
+    }
     if ((a.x & 0x7fffffffu) == (unsigned)d) { val = __uint_as_float(a.y); return 1; }
     if ((a.z & 0x7fffffffu) == (unsigned)d) { val = __uint_as_float(a.w); return 1; }
     if (b.x == (unsigned)d) { val = __uint_as_float(b.y); return 1; }
@@ -114,7 +135,7 @@ __device__ __forceinline__ int slot_lookup(const uint4 *__restrict__ stab, long 
     return ((a.z >> 31) && a.z != 0xffffffffu) ? -1 : 0;
 }
 
-template <int NT, int UNROLL, int R, bool BIG, bool MB>  // MB: a 0/1 weight mask as a bitmap (its own instantiation: registers)
+template <int NT, int UNROLL, int R, bool BIG, bool MB, bool CP>  // MB: a 0/1 weight mask as a bitmap; CP: compact slot tables (own instantiations: registers)
 struct Ms {
     static constexpr int CHUNK = NT * 4 * UNROLL;
     static constexpr int QCAP = CHUNK + NT * R;
@@ -217,7 +238,7 @@ struct Ms {
         const long long so = s.st_off[j];
         if (so >= 0) {
             if (!MS_OK(so + (long long)((unsigned)d >> s.st_sh[j]) < p.stab_len)) return false;
-            const int r = slot_lookup(p.stab, so, s.st_sh[j], d, val);
+            const int r = slot_lookup<CP>(p.stab, so, s.st_sh[j], d, val);
             if (r >= 0) { if (r) MS_CNT(15, 1); return r != 0; }
         }
         const long long beg = s.beg[j];
@@ -682,12 +703,31 @@ __global__ void __launch_bounds__(256) ms_merge_kernel(const unsigned char *__re
     if (lane == 0) atomicAdd(&ctrl->posting_count, qtot[q]);
 }
 
-template <int NT, int UNROLL, int R, int MINB, bool BIG, bool MB>
+template <int NT, int UNROLL, int R, int MINB, bool BIG, bool MB, bool CP>
 __global__ void __launch_bounds__(NT, MINB) retrieve_ms_kernel(const __grid_constant__ MsParams p) {
-    __shared__ typename Ms<NT, UNROLL, R, BIG, MB>::Sh sh;
+    __shared__ typename Ms<NT, UNROLL, R, BIG, MB, CP>::Sh sh;
     extern __shared__ __align__(16) unsigned long long ms_dyn[];
-    Ms<NT, UNROLL, R, BIG, MB> m(p, sh, ms_dyn);
+    Ms<NT, UNROLL, R, BIG, MB, CP> m(p, sh, ms_dyn);
     m.run();
+}
+
+template <int NT, int MINB, bool BIG>
+static cudaError_t launch_ms_variant(const MsParams &p, bool mb, bool cp, int grid, size_t dyn, cudaStream_t st) {
+#define BM25CU_MS_LAUNCH(MBV, CPV)                                                                                          \
+    do {                                                                                                                    \
+        if (dyn > 0) {                                                                                                      \
+            cudaError_t e_ = cudaFuncSetAttribute(retrieve_ms_kernel<NT, 4, 4, MINB, BIG, MBV, CPV>,                        \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);                   \
+            if (e_ != cudaSuccess) return e_;                                                                               \
+        }                                                                                                                   \
+        retrieve_ms_kernel<NT, 4, 4, MINB, BIG, MBV, CPV><<<grid, NT, dyn, st>>>(p);                                        \
+    } while (0)
+    if (mb && cp) BM25CU_MS_LAUNCH(true, true);
+    else if (mb) BM25CU_MS_LAUNCH(true, false);
+    else if (cp) BM25CU_MS_LAUNCH(false, true);
+    else BM25CU_MS_LAUNCH(false, false);
+#undef BM25CU_MS_LAUNCH
+    return cudaGetLastError();
 }
 
 // k > 32: one CTA per query, the parts' rows are rank-merged one after the other in shared memory
@@ -827,25 +867,16 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     const int per_sm = ix->knobs.get("MS_CTAS", 9);  // 55 registers: nine 128-thread CTAs are resident per SM
     const int grid = ix->sm_count * (per_sm > 0 ? per_sm : 9);
     const size_t dyn = p.kcap > 32 ? (size_t)2 * p.kcap * 8 : 0;
-    const bool mb = a.mask_bits != nullptr;
+    const bool mb = a.mask_bits != nullptr, cp = ix->stab_compact && p.stab != nullptr;
     if (p.kcap <= 32) {
-        if (mb) retrieve_ms_kernel<128, 4, 4, 8, false, true><<<grid, 128, 0, ix->stream>>>(p);
-        else retrieve_ms_kernel<128, 4, 4, 8, false, false><<<grid, 128, 0, ix->stream>>>(p);
+        BM25CU_CHECK((launch_ms_variant<128, 8, false>(p, mb, cp, grid, 0, ix->stream)));
     } else if (ix->knobs.get("MS_BIG_NT", 256) == 256) {
         // shared-memory top lists: CTAs of 256 threads, four per SM - twice the survivors per probe round and per merge of
         // the pending keys (k = 1000 at the MS-MARCO shape: 9.5 -> 8.7 ms)
         const int per_sm_b = ix->knobs.get("MS_CTAS", 4);
-        const int grid_b = ix->sm_count * (per_sm_b > 0 ? per_sm_b : 4);
-        if (mb) {
-            BM25CU_CHECK(cudaFuncSetAttribute(retrieve_ms_kernel<256, 4, 4, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            retrieve_ms_kernel<256, 4, 4, 4, true, true><<<grid_b, 256, dyn, ix->stream>>>(p);
-        } else {
-            BM25CU_CHECK(cudaFuncSetAttribute(retrieve_ms_kernel<256, 4, 4, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            retrieve_ms_kernel<256, 4, 4, 4, true, false><<<grid_b, 256, dyn, ix->stream>>>(p);
-        }
+        BM25CU_CHECK((launch_ms_variant<256, 4, true>(p, mb, cp, ix->sm_count * (per_sm_b > 0 ? per_sm_b : 4), dyn, ix->stream)));
     } else {
-        if (mb) retrieve_ms_kernel<128, 4, 4, 8, true, true><<<grid, 128, dyn, ix->stream>>>(p);
-        else retrieve_ms_kernel<128, 4, 4, 8, true, false><<<grid, 128, dyn, ix->stream>>>(p);
+        BM25CU_CHECK((launch_ms_variant<128, 8, true>(p, mb, cp, grid, dyn, ix->stream)));
     }
     BM25CU_CHECK(cudaGetLastError());
     if (p.kcap <= 32)

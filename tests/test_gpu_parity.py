@@ -204,6 +204,25 @@ def test_random_corpus_vs_c_oracle(k):
         np.testing.assert_array_equal(sc2, sc)
         np.testing.assert_array_equal(ids2, ids)  # deterministic tie rule: identical ids whatever the tiling
     dev.close()
+    # slot tables in the compact sector format (16-bit doc offsets, five slots per sector; chosen when the handle is made),
+    # also at a load that makes sectors lend slots and overflow to the column
+    for env in ({"BM25CU_STAB_COMPACT": "1"}, {"BM25CU_STAB_COMPACT": "1", "BM25CU_STAB_LOAD": "80"}, {"BM25CU_STAB_LOAD": "80"}):
+        old = {kk: os.environ.get(kk) for kk in env}
+        os.environ.update(env)
+        try:
+            dev_c = DeviceIndex.upload(data, indices, indptr, n_docs, nonocc=nonocc)
+        finally:
+            for kk, v in old.items():
+                if v is None:
+                    os.environ.pop(kk, None)
+                else:
+                    os.environ[kk] = v
+        for opts in ({}, {"MS_PARTCOST": 512}, {"MS_PBM": 0}):
+            with dev_c.options(**opts):
+                ids_c, sc_c = dev_c.retrieve(flat, ptr, k, shift=sh)
+            np.testing.assert_array_equal(sc_c, sc, err_msg=str((env, opts)))
+            np.testing.assert_array_equal(ids_c, ids, err_msg=str((env, opts)))
+        dev_c.close()
 
 
 def test_weight_mask_fast_path():
@@ -419,11 +438,12 @@ FULL_SIZE = [
     ("nq", "bm25+", 10, 10_000),      # configs[3]
     ("msmarco", "lucene", 10, 6_980),    # configs[2], the headline
     ("msmarco", "lucene", 1000, 6_980),  # configs[2], k = 1000
+    ("msmarco", "lucene", 10, -6_980),   # the headline with COMPACT slot tables (16-bit doc offsets; a negative batch size marks it)
 ]
 
 
 @pytest.mark.parametrize("shape,method,k,n_queries", FULL_SIZE)
-def test_full_size_against_the_oracle(shape, method, k, n_queries):
+def test_full_size_against_the_oracle(shape, method, k, n_queries, monkeypatch):
     """BASELINE.json's configurations at FULL size against the C oracle (the reference algorithm, oracle/bm25_oracle.c)
     on the same CSC: the index is built on the GPU, downloaded, and a strided sample of >= 300 queries of the batch is
     scored by the oracle on the host cores (all of the matrix, dense vector + selection, as the reference does).
@@ -436,6 +456,9 @@ def test_full_size_against_the_oracle(shape, method, k, n_queries):
 
     from bm25s_b200 import DeviceIndex, synth
 
+    if n_queries < 0:  # creation-time knob: read from the environment when the handle is made
+        monkeypatch.setenv("BM25CU_STAB_COMPACT", "1")
+        n_queries = -n_queries
     n_docs, avg_len, n_vocab, _ = synth.SHAPES[shape]
     dev_t = torch.device("cuda")
     tokens, ptr = synth.make_corpus_torch(n_docs, avg_len, n_vocab, seed=0, device=dev_t)
