@@ -502,7 +502,8 @@ def main():
 
     # ------------------------------------------------------------------ our arm
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get("BENCH_NO_SAMPLER"):  # (debugging: is the sampler's NVML polling visible in the step time?)
+        sampler.start()
     stream = torch.cuda.current_stream()
     shift_d = None if shift_h is None else torch.from_numpy(shift_h).to(device)
     work = (torch.empty((n_queries, k), dtype=torch.int32, device=device), torch.empty((n_queries, k), dtype=torch.float32, device=device))
