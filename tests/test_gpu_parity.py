@@ -358,6 +358,62 @@ def test_checked_build_finds_no_out_of_range_access():
     assert "sanitizer workload ok" in res.stdout and "libbm25cu_checked.so" in res.stdout
 
 
+def test_upload_validation_and_bad_token_ids_on_device_entry_points():
+    """(i) an uploaded CSC is validated on the device - non-monotone indptr, ids outside [0, n_docs), rows
+    that do not ascend are refused with ValueError instead of being searched; (ii) the device entry points (no host-side
+    check of the tokens) report an out-of-range token id for EVERY route - list-at-a-time kernel, streaming kernel, and
+    the dense kernel that serves queries of more than 15 tokens - and never index indptr with it; (iii) a k the
+    list-at-a-time kernel cannot take skips it altogether (no partial-result buffer) and still returns the oracle's rows."""
+    import torch
+
+    from bm25s_b200 import DeviceGroup, DeviceIndex, synth
+
+    n_docs, n_vocab = 30_000, 5_000
+    corp = synth.make_corpus(n_docs, 30, n_vocab, seed=31)
+    data, indices, indptr, _ = O.build_index(corp.to_lists(), n_vocab, "lucene")
+    # (i)
+    bad_ptr = indptr.copy()
+    bad_ptr[10], bad_ptr[11] = bad_ptr[11], bad_ptr[10] - 1 if bad_ptr[10] > 0 else 0
+    t = int(np.argmax(np.diff(indptr) >= 4))
+    swapped = indices.copy()
+    swapped[indptr[t]], swapped[indptr[t] + 1] = swapped[indptr[t] + 1], swapped[indptr[t]]
+    out_of_range = indices.copy()
+    out_of_range[indptr[t]] = n_docs + 5
+    for what, (d_, i_, p_) in {"indptr": (data, indices, bad_ptr), "unsorted": (data, swapped, indptr), "range": (data, out_of_range, indptr)}.items():
+        with pytest.raises(ValueError):
+            DeviceIndex.upload(d_, i_, p_, n_docs)
+        if what != "indptr":  # (the host-side cut of the group upload walks the columns: a broken indptr is refused before it)
+            with pytest.raises(ValueError):
+                DeviceGroup.upload(d_, i_, p_, n_docs, devices=[0, 0])
+    with pytest.raises(ValueError):
+        DeviceGroup.upload(data, indices, bad_ptr, n_docs, devices=[0, 0])
+    # (ii)
+    dev = DeviceIndex.upload(data, indices, indptr, n_docs)
+    dev_t = torch.device("cuda")
+    good = [[1, 2, 3], [7], list(range(20, 40))]
+    for bad_query in ([4, n_vocab + 3], [n_vocab], list(range(20, 39)) + [n_vocab + 1]):
+        queries = good + [bad_query]
+        flat = torch.tensor([t_ for q in queries for t_ in q], dtype=torch.int32, device=dev_t)
+        ptr = torch.tensor(np.cumsum([0] + [len(q) for q in queries]), dtype=torch.int64, device=dev_t)
+        oi = torch.empty((len(queries), 5), dtype=torch.int32, device=dev_t)
+        osc = torch.empty((len(queries), 5), dtype=torch.float32, device=dev_t)
+        for opts in ({}, {"MS": 0}, {"FORCE_GENERAL": 1}):
+            with dev.options(**opts):
+                with pytest.raises(ValueError, match="maximum token ID"):
+                    dev.retrieve_device(flat.data_ptr(), ptr.data_ptr(), len(queries), int(flat.numel()), 5, oi.data_ptr(), osc.data_ptr())
+    # the handle is still good
+    qs = synth.make_queries(20, n_vocab, seed=32)
+    ids, sc = dev.retrieve(qs.tokens, qs.ptr, 10)
+    rid, rsc = CO.retrieve(data, indices, indptr, n_docs, qs.tokens, qs.ptr, 10)
+    np.testing.assert_array_equal(sc, rsc)
+    # (iii)
+    ids, sc, st = dev.retrieve(qs.tokens, qs.ptr, 1500, with_stats=True)
+    rid, rsc = CO.retrieve(data, indices, indptr, n_docs, qs.tokens, qs.ptr, 1500)
+    np.testing.assert_array_equal(sc, rsc)
+    assert st["ms_kernel_ms"] == 0  # k > 1024: the list-at-a-time kernel (plan, parts, partial rows) is not launched at all
+    dev.close()
+
+
 def test_kth_largest_table_and_seeded_threshold():
     """The upload-time table of per-column 10th / 100th / 1000th largest scores (start value of the pruning threshold)
     equals numpy's, and results with and without the seeded threshold are identical."""
