@@ -212,3 +212,76 @@ def test_int_query_filter_equals_reference_loop():
         r._filter_int_queries([[1, 3]])
     flat, ptr = r._filter_int_queries([[0, 1, 2, 2]])
     assert flat.tolist() == [0, 2, 2] and ptr.tolist() == [0, 3]
+
+
+def test_weight_mask_packing():
+    """0/1 masks of any dtype become one bit per document (little-endian bit order inside uint32 words: bit d % 32 of word
+    d // 32, what bm25cu_index_set_mask(BM25CU_MASK_BITS) takes); anything else the exact float64 copy."""
+    from bm25s_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    keep = rng.random(1003) < 0.3
+    for dt in (bool, np.int8, np.int32, np.int64, np.uint8, np.float32, np.float64):
+        kind, words = _lib.pack_weight_mask(keep.astype(dt))
+        assert kind == _lib.MASK_BITS and words.dtype == np.uint32 and len(words) >= (1003 + 31) // 32
+        bits = (words[np.arange(1003) >> 5] >> (np.arange(1003) & 31)) & 1
+        np.testing.assert_array_equal(bits.astype(bool), keep)
+        assert not (words[1003 >> 5] >> np.uint32(1003 & 31)) & 1  # padding bits are clear
+    for m in (np.where(keep, 0.5, 1.0), np.where(keep, 2, 0), np.where(keep, np.nan, 1.0), -keep.astype(np.float64)):
+        kind, arr = _lib.pack_weight_mask(m)
+        if np.array_equal(m, -keep.astype(np.float64)):  # -0.0 and -1.0: not a 0/1 mask unless nothing is kept
+            assert kind == _lib.MASK_F64
+        assert kind == _lib.MASK_F64 and arr.dtype == np.float64
+        np.testing.assert_array_equal(arr, m.astype(np.float64))
+
+
+def test_devices_argument_and_environment(monkeypatch):
+    """BM25(devices=[...]) / BM25CU_DEVICES: the device list of the single-process multi-GPU form (parsed on the host; the
+    shards are made at the first upload / build, which needs GPUs)."""
+    from bm25s_b200 import BM25
+
+    r = BM25(devices=[2, 3])
+    assert r.devices == [2, 3] and r.device == 2
+    monkeypatch.setenv("BM25CU_DEVICES", "0, 1,2")
+    assert BM25().devices == [0, 1, 2]
+    assert BM25(devices=[5]).devices == [5]  # the argument wins
+    monkeypatch.delenv("BM25CU_DEVICES")
+    assert BM25().devices is None
+    with pytest.raises(ValueError):
+        BM25(devices=[])
+    # the residency key tells a sharded object from a single-device one
+    r1, r2 = BM25(), BM25(devices=[0, 1])
+    sc = {"data": np.zeros(1, np.float32), "indices": np.zeros(1, np.int32), "indptr": np.zeros(2, np.int64), "num_docs": 1}
+    r1.scores = r2.scores = sc
+    assert not BM25._same_key(r1._residency_key(), r2._residency_key())
+    assert BM25._same_key(r1._residency_key(), r1._residency_key())
+
+
+def test_bench_helpers_against_the_oracle():
+    """bench.py's result digest, sub-batch extraction and oracle spot check (run on the oracle's own rows; a corrupted row
+    must be reported)."""
+    import importlib.util
+
+    from bm25s_b200 import synth
+    from oracle import c_oracle as CO
+    from oracle import oracle as O
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n_docs, n_vocab, k = 20_000, 4_000, 10
+    corp = synth.make_corpus(n_docs, 30, n_vocab, seed=5)
+    data, indices, indptr, nonocc = O.build_index(corp.to_lists(), n_vocab, "bm25l")
+    qs = synth.make_queries(120, n_vocab, seed=6)
+    shift = bench.query_shifts(nonocc, qs.tokens, qs.ptr)
+    rid, rsc = CO.retrieve(data, indices, indptr, n_docs, qs.tokens, qs.ptr, k, shift=shift)
+    tok, ptr = bench.sub_batch(qs.tokens, qs.ptr, [3, 7, 100])
+    assert tok.tolist() == sum((qs.tokens[qs.ptr[q]:qs.ptr[q + 1]].tolist() for q in (3, 7, 100)), [])
+    assert ptr.tolist() == np.cumsum([0] + [int(qs.ptr[q + 1] - qs.ptr[q]) for q in (3, 7, 100)]).tolist()
+    ok = bench.oracle_parity((data, indices, indptr), qs.tokens, qs.ptr, n_docs, k, shift, rid.astype(np.int32), rsc, 60)
+    assert ok["ok"] and ok["queries"] == 60
+    bad = rsc.copy()
+    bad[0, 0] = np.nextafter(bad[0, 0], np.float32(np.inf))
+    rep = bench.oracle_parity((data, indices, indptr), qs.tokens, qs.ptr, n_docs, k, shift, rid.astype(np.int32), bad, 60)
+    assert not rep["ok"] and rep["failures"]["score_rows"] >= 1 and rep["first_bad_query"]["q"] == 0
+    assert bench.digest_of(rid, rsc) == bench.digest_of(rid.copy(), rsc.copy()) != bench.digest_of(rid, bad)
