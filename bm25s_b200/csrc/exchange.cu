@@ -7,7 +7,11 @@
 //      writes), fences them system-wide and raises a per-source flag on every peer to the call's epoch;
 //   2. runs the MERGE kernel on its own copy: a CTA per query waits until the world flags reached the epoch, then sorts
 //      the world * k pairs in shared memory (same order as bm25cu_topk_merge: score descending, id ascending).
-// Two kernels, no host round trip, no collective library call. The push runs on the caller's stream, the merge on a side
+// For k > 32 the rows are big (k = 1000: 56 MB per rank and batch) and merging ALL queries on EVERY rank would move and
+// sort everything world times: there the exchange is SLICED - rank p receives only the rows of its slice of the queries
+// (push), merges them and stores the merged rows into a "gathered" buffer on every peer (merge), and a small kernel copies
+// the gathered rows out once every rank's slice has arrived: 2/world of the all-to-all traffic, 1/world of the merge work.
+// Two kernels (three when sliced), no host round trip, no collective library call. The push runs on the caller's stream, the merge on a side
 // stream of the exchange (behind an event): waiting for the slowest shard and merging overlap the scoring kernels of the
 // caller's NEXT batch; bm25cu_exchange_check / _join make the caller's stream wait for the merge. Buffers are
 // double-buffered by epoch parity; a rank's merge of call e ends by raising a "consumed" flag on every peer, and the
@@ -21,10 +25,13 @@ namespace {
 constexpr int kMaxWorld = 16;
 constexpr size_t kFlagBytes = 512;  // unsigned int flags[2][kMaxWorld] (rows arrived), consumed[kMaxWorld] at word 64, padded
 constexpr int kConsumedWord = 64;
+constexpr int kGatheredWord = 96;   // gathered[2][kMaxWorld]: rank r's merged slice of the epoch has arrived (sliced form)
 
 struct ExchangeView {
     int32_t *ids[2];   // [world][cap]
     float *scores[2];  // [world][cap]
+    int32_t *g_ids[2];   // [cap] merged rows of all queries, every rank writes its slice (sliced form)
+    float *g_scores[2];  // [cap]
     unsigned int *flags;  // [2][kMaxWorld]
 };
 
@@ -39,8 +46,17 @@ __host__ __device__ inline ExchangeView view_of(void *base, int world, long long
         v.scores[b] = reinterpret_cast<float *>(p);
         p += (size_t)world * cap * 4;
     }
+    for (int b = 0; b < 2; ++b) {
+        v.g_ids[b] = reinterpret_cast<int32_t *>(p);
+        p += (size_t)cap * 4;
+        v.g_scores[b] = reinterpret_cast<float *>(p);
+        p += (size_t)cap * 4;
+    }
     return v;
 }
+
+// the queries rank p merges in the sliced form: [slice_lo(p), slice_lo(p + 1))
+__host__ __device__ inline int slice_lo(int n_queries, int world, int p) { return (int)((long long)n_queries * p / world); }
 
 struct PeerPtrs {
     void *p[kMaxWorld];
@@ -49,7 +65,7 @@ struct PeerPtrs {
 __global__ void __launch_bounds__(256) exchange_push_kernel(const int32_t *__restrict__ ids, const float *__restrict__ scores,
                                                             long long n, PeerPtrs peers, int rank, int world, long long cap,
                                                             int parity, unsigned int epoch, unsigned int *done_counter,
-                                                            unsigned int *err) {
+                                                            unsigned int *err, int sliced_queries, int k) {
     // every peer has merged call epoch - 2, the previous user of this parity's buffers (its merge raised consumed[peer]
     // in OUR memory); normally long true
     if (epoch > 2u && threadIdx.x < world) {
@@ -68,7 +84,10 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const int32_t *__res
         const ExchangeView v = view_of(peers.p[pr], world, cap);
         int32_t *di = v.ids[parity] + (size_t)rank * cap;
         float *ds = v.scores[parity] + (size_t)rank * cap;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        // sliced form (sliced_queries > 0): a peer gets the rows of the queries it merges, nothing else
+        const long long lo = sliced_queries > 0 ? (long long)slice_lo(sliced_queries, world, pr) * k : 0;
+        const long long hi = sliced_queries > 0 ? (long long)slice_lo(sliced_queries, world, pr + 1) * k : n;
+        for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
             di[i] = ids[i];
             ds[i] = scores[i];
         }
@@ -219,6 +238,82 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(void *local, int wo
     raise_consumed(peers, rank, world, cap, epoch, merge_counter);
 }
 
+// Sliced form, k > 32. One CTA per query of THIS rank's slice: the ranks' rows are rank-merged (select.cuh) and the merged
+// row is stored into the gathered buffer of every peer; the last CTA to finish raises gathered[rank] on every peer.
+__global__ void __launch_bounds__(256) exchange_merge_slice_kernel(void *local, int world, long long cap, int parity, unsigned int epoch,
+                                                                   int n_queries, int k, int kcap, const float *__restrict__ shift,
+                                                                   unsigned int *err, PeerPtrs peers, int rank, unsigned int *slice_counter) {
+    extern __shared__ __align__(16) unsigned long long xm[];  // cur, nxt, row: kcap keys each
+    const ExchangeView v = view_of(local, world, cap);
+    wait_for_peers(v, world, parity, epoch, err);
+    const int q = slice_lo(n_queries, world, rank) + (int)blockIdx.x;
+    if (q < slice_lo(n_queries, world, rank + 1)) {
+        const int32_t *ids = v.ids[parity];
+        const float *scores = v.scores[parity];
+        auto load = [&](int r, int j) -> unsigned long long {
+            const size_t src = (size_t)r * cap + (size_t)q * k + j;
+            const int32_t d = __ldcv(ids + src);  // written by a peer: never from a stale cache line
+            return d >= 0 ? (((unsigned long long)bm25cu::f32_key(__ldcv(scores + src)) << 32) | (unsigned int)(~d)) : 0ull;
+        };
+        const unsigned long long *top = bm25cu::block_merge_sorted_rows(world, k, kcap, xm, xm + kcap, xm + 2 * kcap, load);
+        for (int j = threadIdx.x; j < k; j += blockDim.x) {
+            const unsigned long long t = top[j];
+            int32_t d = -1;
+            float sc = __int_as_float(0xff800000);
+            if (t != 0ull) {
+                const uint32_t kk = (uint32_t)(t >> 32);
+                sc = __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk);
+                if (shift != nullptr) sc = __fadd_rn(sc, shift[q]);
+                d = (int32_t)~(unsigned int)(t & 0xffffffffu);
+            }
+            for (int pr = 0; pr < world; ++pr) {
+                const ExchangeView pv = view_of(peers.p[pr], world, cap);
+                pv.g_ids[parity][(size_t)q * k + j] = d;
+                pv.g_scores[parity][(size_t)q * k + j] = sc;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(slice_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *slice_counter = 0u;
+            __threadfence_system();
+            for (int pr = 0; pr < world; ++pr) {
+                const ExchangeView pv = view_of(peers.p[pr], world, cap);
+                volatile unsigned int *f = pv.flags + kGatheredWord + parity * kMaxWorld + rank;
+                *f = epoch;
+            }
+            __threadfence_system();
+        }
+    }
+}
+
+// Sliced form: once every rank's merged slice has arrived, the gathered rows go to the caller's arrays.
+__global__ void __launch_bounds__(256) exchange_copy_out_kernel(void *local, int world, long long cap, int parity, unsigned int epoch, long long n,
+                                                                int32_t *out_ids, float *out_scores, unsigned int *err, PeerPtrs peers,
+                                                                int rank, unsigned int *merge_counter) {
+    const ExchangeView v = view_of(local, world, cap);
+    if (threadIdx.x < world) {
+        volatile unsigned int *f = v.flags + kGatheredWord + parity * kMaxWorld + threadIdx.x;
+        unsigned long long t0 = 0, now = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(*f - epoch) < 0) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 10000000000ull) { atomicOr(err, 1u); break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        out_ids[i] = __ldcv(v.g_ids[parity] + i);
+        out_scores[i] = __ldcv(v.g_scores[parity] + i);
+    }
+    raise_consumed(peers, rank, world, cap, epoch, merge_counter);
+}
+
 }  // namespace
 
 struct bm25cu_exchange {
@@ -249,10 +344,10 @@ int bm25cu_exchange_create(int32_t device, int32_t rank, int32_t world, int64_t 
     x->rank = rank;
     x->world = world;
     x->cap = (max_elems + 3) & ~3ll;
-    x->bytes = kFlagBytes + (size_t)2 * 2 * world * x->cap * 4;
+    x->bytes = kFlagBytes + (size_t)2 * 2 * world * x->cap * 4 + (size_t)2 * 2 * x->cap * 4;
     cudaError_t e = cudaMalloc(&x->local, x->bytes);
     if (e == cudaSuccess) e = cudaMemset(x->local, 0, x->bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&x->d_counter, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_counter, 4 * sizeof(unsigned int));  // push blocks, error bits, merge / copy-out blocks, slice-merge blocks
     if (e == cudaSuccess) e = cudaMemset(x->d_counter, 0, 4 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_pushed, cudaEventDisableTiming);
@@ -315,8 +410,9 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
     for (int r = 0; r < kMaxWorld; ++r) pp.p[r] = r < x->world ? x->peer[r] : nullptr;
     int grid = (int)((n + 255) / 256);
     if (grid > 592) grid = 592;
+    const bool sliced = k > 32 && (size_t)3 * next_pow2(k) * 8 <= 200 * 1024;
     exchange_push_kernel<<<grid, 256, 0, st>>>(ids_device, scores_device, n, pp, x->rank, x->world, x->cap, parity, epoch, x->d_counter,
-                                               x->d_counter + 1);
+                                               x->d_counter + 1, sliced ? n_queries : 0, k);
     BM25CU_CHECK(cudaGetLastError());
     // the merge (and its wait for the slowest shard) runs on the side stream: the caller's stream is free for the next batch
     BM25CU_CHECK(cudaEventRecord(x->ev_pushed, st));
@@ -326,6 +422,16 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
         exchange_merge_warp_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k,
                                                                        shift_per_query_device, out_ids_device, out_scores_device,
                                                                        x->d_counter + 1, pp, x->rank, x->d_counter + 2);
+    } else if (sliced) {
+        const int kcap = next_pow2(k);
+        const size_t smem = (size_t)3 * kcap * 8;
+        const int mine = slice_lo(n_queries, x->world, x->rank + 1) - slice_lo(n_queries, x->world, x->rank);
+        BM25CU_CHECK(cudaFuncSetAttribute(exchange_merge_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        exchange_merge_slice_kernel<<<mine > 0 ? mine : 1, 256, smem, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k, kcap,
+                                                                          shift_per_query_device, x->d_counter + 1, pp, x->rank, x->d_counter + 3);
+        BM25CU_CHECK(cudaGetLastError());
+        exchange_copy_out_kernel<<<grid, 256, 0, st>>>(x->local, x->world, x->cap, parity, epoch, n, out_ids_device, out_scores_device,
+                                                       x->d_counter + 1, pp, x->rank, x->d_counter + 2);
     } else {
         const int kcap = next_pow2(k);
         const size_t smem = (size_t)3 * kcap * 8;
