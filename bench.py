@@ -49,6 +49,10 @@ def parse():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the shards' top-k rows meet - p2p: stores into peer memory over NVLink fused with the merge "
                          "(bm25cu_exchange_*), nccl: all_gather + merge kernel")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="batches in flight per GPU in the timed loop: lane 0 is the shard's handle, further lanes are views of it "
+                         "(bm25cu_index_view: own stream, workspaces and exchange, shared index), steps go to the lanes round-robin; "
+                         "1 = one batch at a time (also measured, as `one_batch_at_a_time`)")
     ap.add_argument("--local-shards", action="store_true",
                     help="N > 1: every rank generates only its own doc range (seed 1000 + rank); implied by --shape 100m")
     return ap.parse_args()
@@ -414,7 +418,8 @@ def main():
                           f"{n_queries} queries of 1+Poisson(3) tokens, k={k}, method={args.method}",
               "l2": "inputs larger than L2 (index 3.9 GB vs 126 MB L2), no flush between steps",
               "sharding": (f"doc-range x{world}" + (", every rank generates its own range" if local_shards(args, world) else ""))
-              if world > 1 else "single shard"}
+              if world > 1 else "single shard",
+              "batches_in_flight": None}
 
     import torch.distributed as dist
 
@@ -555,28 +560,60 @@ def main():
         torch.cuda.synchronize()
         exchange_check = bool(torch.equal(c_ids, merged[0]) and torch.equal(c_sc.view(torch.int32), merged[1].view(torch.int32)))
         del g_ids, g_sc, c_ids, c_sc
-    barrier()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for it in range(args.steps):
-        # the steps are enqueued back to back; per-step events split scoring from exchange + merge (+ waiting for peers)
-        ev[it][0].record()
-        step_device(q_tok, q_ptr)
-        ev[it][1].record()
-    sh.join()  # N > 1: the last merges run on the exchange's side stream; the timed region ends behind them
-    ev1.record()
-    barrier()
-    stats = sh.collect()  # one synchronisation; errors of the last call, stats of its scoring kernels
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    # lanes: lane 0 = the shard's handle on torch's current stream; further lanes = views of it on streams of their own
+    n_lanes = max(1, args.lanes) if (world == 1 or args.exchange == "p2p") else 1
+    lanes, lane_streams, lane_bufs = [sh], [stream], [(work, merged)]
+    for _ in range(n_lanes - 1):
+        ln = sh.view()
+        if world > 1:
+            ln.enable_peer_exchange(n_queries, k)
+        lw = (torch.empty_like(work[0]), torch.empty_like(work[1]))
+        lm = lw if world == 1 else (torch.empty_like(merged[0]), torch.empty_like(merged[1]))
+        lanes.append(ln)
+        lane_streams.append(torch.cuda.Stream(device))
+        lane_bufs.append((lw, lm))
+    for l in range(1, n_lanes):  # warm the views up (workspaces, stream switch)
+        for _ in range(2):
+            lanes[l].retrieve_device_enqueue(q_tok, q_ptr, k, shift=shift_d, stream=lane_streams[l], out=lane_bufs[l][1] if world > 1 else None,
+                                             work=lane_bufs[l][0])
+            lanes[l].collect()
+
+    def timed_loop(active):
+        """K steps, round-robin over the first `active` lanes, enqueued back to back; CUDA events on torch's current stream
+        around all of them (the lanes' streams fork from the first event and join before the second); max over ranks."""
+        barrier()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for l in range(1, active):
+            lane_streams[l].wait_event(ev0)
+        for it in range(args.steps):
+            l = it % active
+            ev[it][0].record(lane_streams[l])
+            lanes[l].retrieve_device_enqueue(q_tok, q_ptr, k, shift=shift_d, stream=lane_streams[l], out=lane_bufs[l][1] if world > 1 else None,
+                                             work=lane_bufs[l][0])
+            ev[it][1].record(lane_streams[l])
+        for l in range(active):
+            lanes[l].join(lane_streams[l])  # N > 1: the last merges run on the exchanges' side streams; the region ends behind them
+        for l in range(1, active):
+            e = torch.cuda.Event()
+            e.record(lane_streams[l])
+            stream.wait_event(e)
+        ev1.record(stream)
+        barrier()
+        for l in range(active):
+            lanes[l].collect()  # one synchronisation per lane; errors of its last call
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), float(np.mean([ev[i][0].elapsed_time(ev[i][1]) for i in range(args.steps)]))
+
+    ms_single, step_ms_local = timed_loop(1)  # one batch at a time: per-batch latency of the device chain
+    ms_total = timed_loop(n_lanes)[0] if n_lanes > 1 else ms_single
     ms_per_step = ms_total / args.steps
     value = n_queries / (ms_per_step / 1000.0)
-    step_ms_local = float(np.mean([ev[i][0].elapsed_time(ev[i][1]) for i in range(args.steps)]))
-    digest_device = digest_of(merged[0].cpu().numpy(), merged[1].cpu().numpy())
+    last = (args.steps - 1) % n_lanes
+    digest_device = digest_of(lane_bufs[last][1][0].cpu().numpy(), lane_bufs[last][1][1].cpu().numpy())
 
     # a few separately collected steps: the library's own CUDA events around the scoring kernels (roofline), per rank
     stats_acc = []
@@ -644,6 +681,8 @@ def main():
                 "kernel_ms": fast_ms, "ms_kernel_ms": ms_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
+    config["batches_in_flight"] = (f"{n_lanes}: steps go round-robin to {n_lanes} lanes (the shard's handle + views of it, bm25cu_index_view: own stream, "
+                                   f"workspaces and exchange, shared index); `value` = K batches / time for all K" if n_lanes > 1 else "1")
     launches_per_step = int(stats_acc[-1]["launches"])
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -653,6 +692,8 @@ def main():
                            "pinned H2D + ShardedIndex.retrieve_device (scoring kernels + " +
                            ("peer-memory exchange fused with the merge" if args.exchange == "p2p" else "all_gather + merge") + ") + D2H"},
             "gpu_launches": launches_per_step * args.steps,
+            "one_batch_at_a_time": {"value": n_queries * args.steps / (ms_single / 1000.0), "unit": UNIT, "ms_per_step": ms_single / args.steps,
+                                    "what": "the same K steps on ONE lane: a batch starts when the one before it has left the GPU"},
             "roofline": roofline, "result_digest": digest, "result_digest_device_path": digest_device,
             "n_general": int(stats_acc[-1]["n_general"]), "nnz_local": int(nnz), "index_build_s": round(build_s, 3)}
     if world > 1:

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "bm25cu_build_free", "bm25cu_index_build", "bm25cu_index_sizes", "bm25cu_index_download", "bm25cu_retrieve",
     "bm25cu_retrieve_device", "bm25cu_retrieve_device_enqueue", "bm25cu_retrieve_collect", "bm25cu_scores_dense", "bm25cu_topk_dense", "bm25cu_topk_merge",
     "bm25cu_topk_merge_device", "bm25cu_index_free", "bm25cu_index_set_option", "bm25cu_index_unset_option",
-    "bm25cu_debug_colkth", "bm25cu_debug_prof", "bm25cu_index_set_mask", "bm25cu_group_set_mask",
+    "bm25cu_debug_colkth", "bm25cu_debug_prof", "bm25cu_index_set_mask", "bm25cu_group_set_mask", "bm25cu_index_view",
     "bm25cu_exchange_create", "bm25cu_exchange_handle_size", "bm25cu_exchange_handle", "bm25cu_exchange_connect",
     "bm25cu_exchange_merge", "bm25cu_exchange_check", "bm25cu_exchange_join", "bm25cu_exchange_free",
     "bm25cu_group_upload", "bm25cu_group_build", "bm25cu_group_sizes", "bm25cu_group_shard", "bm25cu_group_set_option",
@@ -188,6 +188,15 @@ class DeviceIndex:
                     self.unset_option(k)
                 else:
                     self.set_option(k, v)
+
+    def view(self) -> "DeviceIndex":
+        """A second handle on the same resident shard (bm25cu_index_view): own stream and workspaces, shared index arrays;
+        calls on the view and on this handle may be in flight at the same time. The view keeps this handle alive."""
+        h = C.c_void_p()
+        check(lib().bm25cu_index_view(self._h, C.byref(h)))
+        v = DeviceIndex(h)
+        v._parent = self
+        return v
 
     def set_mask(self, kind: int, arr=None):
         """Resident weight mask of this shard: kind MASK_BITS (uint32 words, bit d%32 of word d//32 = keep local document

@@ -135,6 +135,7 @@ struct bm25cu_index {
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
+    bool is_view = false;          // bm25cu_index_view: the posting arrays and lookup structures belong to another handle
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,

@@ -5,13 +5,14 @@
 //   1. PUSHES its local rows (ids int32[Q][k], scores float32[Q][k]) straight into slot [rank] of a buffer that lives in
 //      the memory of EVERY peer (plain stores through pointers opened with cudaIpcOpenMemHandle: NVLink / NVSwitch peer
 //      writes), fences them system-wide and raises a per-source flag on every peer to the call's epoch;
-//   2. runs the MERGE kernel on its own copy: a CTA per query waits until the world flags reached the epoch, then sorts
-//      the world * k pairs in shared memory (same order as bm25cu_topk_merge: score descending, id ascending).
+//   2. waits until the world flags reached the epoch (a one-warp kernel of its own, exchange_wait_kernel: no kernel with a
+//      full grid ever spins) and runs the MERGE kernel on its own copy: a warp (k <= 32) or a CTA per query merges the
+//      world rows (same order as bm25cu_topk_merge: score descending, id ascending).
 // For k > 32 the rows are big (k = 1000: 56 MB per rank and batch) and merging ALL queries on EVERY rank would move and
 // sort everything world times: there the exchange is SLICED - rank p receives only the rows of its slice of the queries
 // (push), merges them and stores the merged rows into a "gathered" buffer on every peer (merge), and a small kernel copies
 // the gathered rows out once every rank's slice has arrived: 2/world of the all-to-all traffic, 1/world of the merge work.
-// Two kernels (three when sliced), no host round trip, no collective library call. The push runs on the caller's stream, the merge on a side
+// Two kernels (three when sliced) plus the one-warp waits, no host round trip, no collective library call. The push runs on the caller's stream, the merge on a side
 // stream of the exchange (behind an event): waiting for the slowest shard and merging overlap the scoring kernels of the
 // caller's NEXT batch; bm25cu_exchange_check / _join make the caller's stream wait for the merge. Buffers are
 // double-buffered by epoch parity; a rank's merge of call e ends by raising a "consumed" flag on every peer, and the
@@ -66,20 +67,6 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const int32_t *__res
                                                             long long n, PeerPtrs peers, int rank, int world, long long cap,
                                                             int parity, unsigned int epoch, unsigned int *done_counter,
                                                             unsigned int *err, int sliced_queries, int k) {
-    // every peer has merged call epoch - 2, the previous user of this parity's buffers (its merge raised consumed[peer]
-    // in OUR memory); normally long true
-    if (epoch > 2u && threadIdx.x < world) {
-        const ExchangeView mine = view_of(peers.p[rank], world, cap);
-        volatile unsigned int *c = mine.flags + kConsumedWord + threadIdx.x;
-        unsigned long long t0 = 0, now = 0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while ((int)(*c - (epoch - 2u)) < 0) {
-            __nanosleep(100);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > 10000000000ull) { atomicOr(err, 2u); break; }
-        }
-    }
-    __syncthreads();
     for (int pr = 0; pr < world; ++pr) {
         const ExchangeView v = view_of(peers.p[pr], world, cap);
         int32_t *di = v.ids[parity] + (size_t)rank * cap;
@@ -109,21 +96,24 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const int32_t *__res
     }
 }
 
-// Spin until the `world` per-source flags of this buffer parity reached the call's epoch (threads 0 .. world-1 of the
-// CTA, one flag each; 10 s without the peer's rows sets the error bit).
-__device__ __forceinline__ void wait_for_peers(const ExchangeView &v, int world, int parity, unsigned int epoch, unsigned int *err) {
+// The ONLY kernel that waits for another GPU: one warp, lane r polls the flag rank r raises in this rank's memory until it
+// reached `epoch` (10 s without it sets `errbit`). It runs in the stream ahead of the kernel that needs the peers' data,
+// so a wait never holds more than one warp of the GPU: kernels with full grids that spin can fill the SMs with waiting
+// CTAs while the scoring kernel of another batch in flight - the one whose rows the PEERS wait for - finds no slot
+// (seen with three batches in flight on two GPUs), a deadlock across GPUs no single stream order prevents.
+__global__ void __launch_bounds__(32) exchange_wait_kernel(const unsigned int *flags, int world, unsigned int epoch, unsigned int *err,
+                                                           unsigned int errbit) {
     if (threadIdx.x < world) {
-        volatile unsigned int *f = v.flags + parity * kMaxWorld + threadIdx.x;
+        const volatile unsigned int *f = flags + threadIdx.x;
         unsigned long long t0 = 0, now = 0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         while ((int)(*f - epoch) < 0) {
             __nanosleep(100);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > 10000000000ull) { atomicOr(err, 1u); break; }
+            if (now - t0 > 10000000000ull) { atomicOr(err, errbit); break; }
         }
-        __threadfence_system();
     }
-    __syncthreads();
+    __threadfence_system();
 }
 
 // End of a merge kernel: the last block to finish tells every peer that this rank is done reading the rows of `epoch`.
@@ -158,7 +148,6 @@ __global__ void __launch_bounds__(256) exchange_merge_warp_kernel(void *local, i
                                                                   int32_t *out_ids, float *out_scores, unsigned int *err,
                                                                   PeerPtrs peers, int rank, unsigned int *merge_counter) {
     const ExchangeView v = view_of(local, world, cap);
-    wait_for_peers(v, world, parity, epoch, err);
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= n_queries) { raise_consumed(peers, rank, world, cap, epoch, merge_counter); return; }
     const int32_t *ids = v.ids[parity];
@@ -212,7 +201,6 @@ __global__ void __launch_bounds__(256) exchange_merge_kernel(void *local, int wo
                                                              PeerPtrs peers, int rank, unsigned int *merge_counter) {
     extern __shared__ __align__(16) unsigned long long xm[];  // cur, nxt, row: kcap keys each
     const ExchangeView v = view_of(local, world, cap);
-    wait_for_peers(v, world, parity, epoch, err);
     const int q = blockIdx.x;
     const int32_t *ids = v.ids[parity];
     const float *scores = v.scores[parity];
@@ -245,7 +233,6 @@ __global__ void __launch_bounds__(256) exchange_merge_slice_kernel(void *local, 
                                                                    unsigned int *err, PeerPtrs peers, int rank, unsigned int *slice_counter) {
     extern __shared__ __align__(16) unsigned long long xm[];  // cur, nxt, row: kcap keys each
     const ExchangeView v = view_of(local, world, cap);
-    wait_for_peers(v, world, parity, epoch, err);
     const int q = slice_lo(n_queries, world, rank) + (int)blockIdx.x;
     if (q < slice_lo(n_queries, world, rank + 1)) {
         const int32_t *ids = v.ids[parity];
@@ -295,18 +282,6 @@ __global__ void __launch_bounds__(256) exchange_copy_out_kernel(void *local, int
                                                                 int32_t *out_ids, float *out_scores, unsigned int *err, PeerPtrs peers,
                                                                 int rank, unsigned int *merge_counter) {
     const ExchangeView v = view_of(local, world, cap);
-    if (threadIdx.x < world) {
-        volatile unsigned int *f = v.flags + kGatheredWord + parity * kMaxWorld + threadIdx.x;
-        unsigned long long t0 = 0, now = 0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while ((int)(*f - epoch) < 0) {
-            __nanosleep(100);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > 10000000000ull) { atomicOr(err, 1u); break; }
-        }
-        __threadfence_system();
-    }
-    __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         out_ids[i] = __ldcv(v.g_ids[parity] + i);
         out_scores[i] = __ldcv(v.g_scores[parity] + i);
@@ -411,6 +386,10 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
     int grid = (int)((n + 255) / 256);
     if (grid > 592) grid = 592;
     const bool sliced = k > 32 && (size_t)3 * next_pow2(k) * 8 <= 200 * 1024;
+    const ExchangeView lv = view_of(x->local, x->world, x->cap);
+    unsigned int *err = x->d_counter + 1;
+    if (epoch > 2u)  // every peer has merged call epoch - 2, the previous user of this parity's buffers (normally long true)
+        exchange_wait_kernel<<<1, 32, 0, st>>>(lv.flags + kConsumedWord, x->world, epoch - 2u, err, 2u);
     exchange_push_kernel<<<grid, 256, 0, st>>>(ids_device, scores_device, n, pp, x->rank, x->world, x->cap, parity, epoch, x->d_counter,
                                                x->d_counter + 1, sliced ? n_queries : 0, k);
     BM25CU_CHECK(cudaGetLastError());
@@ -418,6 +397,7 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
     BM25CU_CHECK(cudaEventRecord(x->ev_pushed, st));
     BM25CU_CHECK(cudaStreamWaitEvent(x->side, x->ev_pushed, 0));
     st = x->side;
+    exchange_wait_kernel<<<1, 32, 0, st>>>(lv.flags + parity * kMaxWorld, x->world, epoch, err, 1u);  // every rank's rows are here
     if (k <= 32) {
         exchange_merge_warp_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k,
                                                                        shift_per_query_device, out_ids_device, out_scores_device,
@@ -430,6 +410,7 @@ int bm25cu_exchange_merge(bm25cu_exchange *x, const int32_t *ids_device, const f
         exchange_merge_slice_kernel<<<mine > 0 ? mine : 1, 256, smem, st>>>(x->local, x->world, x->cap, parity, epoch, n_queries, k, kcap,
                                                                           shift_per_query_device, x->d_counter + 1, pp, x->rank, x->d_counter + 3);
         BM25CU_CHECK(cudaGetLastError());
+        exchange_wait_kernel<<<1, 32, 0, st>>>(lv.flags + kGatheredWord + parity * kMaxWorld, x->world, epoch, err, 1u);  // every merged slice
         exchange_copy_out_kernel<<<grid, 256, 0, st>>>(x->local, x->world, x->cap, parity, epoch, n, out_ids_device, out_scores_device,
                                                        x->d_counter + 1, pp, x->rank, x->d_counter + 2);
     } else {

@@ -573,6 +573,11 @@ static void destroy(bm25cu_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
+    if (ix->is_view) {  // a view owns its workspaces, stream and events only
+        ix->d_data = nullptr; ix->d_indices = nullptr; ix->d_indptr = nullptr; ix->d_nonocc = nullptr; ix->d_colmax = nullptr;
+        ix->d_colkth = nullptr; ix->d_btab = nullptr; ix->d_btab_off = nullptr; ix->d_btab_sh = nullptr; ix->d_pbm = nullptr;
+        ix->d_pbm_off = nullptr; ix->d_pbm_sh = nullptr; ix->d_stab = nullptr; ix->d_stab_off = nullptr; ix->d_stab_sh = nullptr;
+    }
     cudaFree(ix->d_data);
     cudaFree(ix->d_indices);
     cudaFree(ix->d_indptr);
@@ -809,6 +814,55 @@ int bm25cu_index_upload_device(const float *data, const int32_t *indices, const 
                                int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
                                int32_t doc_hi, bm25cu_index **out) {
     return upload_impl(data, indices, indptr, nnz, n_vocab, n_docs, nonocc, device, doc_lo, doc_hi, true, out);
+}
+
+// A second handle on the SAME resident shard: it shares the posting arrays and lookup structures of `src` (read-only) and
+// owns a stream, events and per-call workspaces of its own, so that calls on the view and on `src` may be in flight at
+// the same time (several batches on several streams). Free the view before `src`.
+int bm25cu_index_view(const bm25cu_index *src, bm25cu_index **out) {
+    BM25CU_REQUIRE(src != nullptr && out != nullptr, "bm25cu_index_view: null pointer");
+    *out = nullptr;
+    BM25CU_CHECK(cudaSetDevice(src->device));
+    bm25cu_index *v = new bm25cu_index();
+    v->is_view = true;
+    v->device = src->device;
+    v->n_vocab = src->n_vocab;
+    v->n_docs = src->n_docs;
+    v->doc_base = src->doc_base;
+    v->nnz = src->nnz;
+    v->d_data = src->d_data;
+    v->d_indices = src->d_indices;
+    v->d_indptr = src->d_indptr;
+    v->d_nonocc = src->d_nonocc;
+    v->d_colmax = src->d_colmax;
+    v->d_colkth = src->d_colkth;
+    v->d_btab = src->d_btab;
+    v->d_btab_off = src->d_btab_off;
+    v->d_btab_sh = src->d_btab_sh;
+    v->d_pbm = src->d_pbm;
+    v->d_pbm_off = src->d_pbm_off;
+    v->d_pbm_sh = src->d_pbm_sh;
+    v->d_stab = src->d_stab;
+    v->d_stab_off = src->d_stab_off;
+    v->d_stab_sh = src->d_stab_sh;
+    v->stab_compact = src->stab_compact;
+    v->btab_len = src->btab_len;
+    v->pbm_len = src->pbm_len;
+    v->stab_len = src->stab_len;
+    v->aux_bytes = 0;
+    v->nonneg = src->nonneg;
+    v->sm_count = src->sm_count;
+    v->max_smem_optin = src->max_smem_optin;
+    v->knobs = src->knobs;
+    cudaError_t e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&v->ev[i]);
+    if (e != cudaSuccess) {
+        set_error(std::string("bm25cu_index_view: ") + cudaGetErrorString(e));
+        destroy(v);
+        return BM25CU_ECUDA;
+    }
+    *out = v;
+    return BM25CU_OK;
 }
 
 int bm25cu_index_set_stream(bm25cu_index *ix, void *stream) {

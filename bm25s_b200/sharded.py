@@ -43,6 +43,13 @@ class ShardedIndex:
         self.n_docs = n_docs_global
         self.rank, self.world, self.device, self.group = rank, world, device, group
 
+    def view(self) -> "ShardedIndex":
+        """A second lane on the same resident shard: a view of the device handle (own stream and workspaces, shared index
+        arrays) wrapped as a ShardedIndex of its own - give it its own exchange (`enable_peer_exchange`, on every rank in the
+        same order) and its own stream, and batches on the lanes overlap: one batch's tail, its small kernels and its
+        exchange run next to the other batch's scoring."""
+        return ShardedIndex(self.dev.view(), self.n_docs, self.rank, self.world, self.device, self.group)
+
     @classmethod
     def from_csc(cls, data, indices, indptr, n_docs, nonocc=None, rank=0, world=1, device=0, group=None):
         from ._lib import DeviceIndex
@@ -216,7 +223,8 @@ class ShardedIndex:
         stats = self.dev.collect(nq, n_tok, k)
         if self.world > 1 and self._exchange is not None:
             self._exchange.check(stream)
-            stats["launches"] += 2  # push + merge
+            # push + merge (k <= 32) or push + slice merge + copy-out, and the one-warp waits ahead of them (exchange.cu)
+            stats["launches"] += (4 if k <= 32 else 6)
         elif self.world > 1:
             stats["launches"] += 1  # merge (the all_gather is NCCL's)
         return stats

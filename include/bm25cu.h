@@ -70,6 +70,12 @@ int bm25cu_index_upload_device(const float *data, const int32_t *indices, const 
                                int32_t n_vocab, int32_t n_docs, const float *nonocc, int32_t device, int32_t doc_lo,
                                int32_t doc_hi, bm25cu_index **out);
 
+/* A second handle on the SAME resident shard (no copy of the index): it shares the posting arrays and lookup structures
+ * of `src` and owns a stream, events and per-call workspaces of its own, so calls on the view and on `src` may be in
+ * flight at the same time - several batches on several streams overlap one batch's tail with the next one's start
+ * (bench.py --lanes). A view has no resident mask of its own. Free it before `src`. */
+int bm25cu_index_view(const bm25cu_index *src, bm25cu_index **out);
+
 /* Run the handle's device work on a caller-owned CUDA stream (cudaStream_t, e.g. torch's current stream) so that
  * the caller can bracket calls with its own events. Pass the stream's raw handle. */
 int bm25cu_index_set_stream(bm25cu_index *ix, void *stream);

@@ -225,6 +225,56 @@ def test_random_corpus_vs_c_oracle(k):
         dev_c.close()
 
 
+def test_views_share_the_index_and_overlap():
+    """bm25cu_index_view: handles on the same resident shard with streams and workspaces of their own - calls enqueued on
+    the handle and on two views at the same time return the rows a single call returns (k in registers and in shared
+    memory, and the streaming kernel); freeing the views leaves the parent usable."""
+    import torch
+
+    from bm25s_b200 import DeviceIndex, synth
+
+    n_docs, n_vocab = 200_000, 20_000
+    corp = synth.make_corpus(n_docs, 30, n_vocab, seed=17)
+    data, indices, indptr, nonocc = O.build_index(corp.to_lists(), n_vocab, "lucene")
+    dev = DeviceIndex.upload(data, indices, indptr, n_docs)
+    views = [dev.view(), dev.view()]
+    lanes = [dev] + views
+    dt = torch.device("cuda", 0)
+    batches = []
+    for s in range(3):
+        qs = synth.make_queries(3000, n_vocab, seed=30 + s)
+        batches.append((torch.from_numpy(qs.tokens).to(dt), torch.from_numpy(qs.ptr).to(dt), qs))
+    torch.cuda.synchronize()
+    for k in (10, 100):
+        for opts in ({}, {"MS": 0}):
+            want = []
+            for qt, qp, qs in batches:
+                with dev.options(**opts):
+                    want.append(dev.retrieve(qs.tokens, qs.ptr, k))
+            outs = [(torch.empty((3000, k), dtype=torch.int32, device=dt), torch.empty((3000, k), dtype=torch.float32, device=dt)) for _ in lanes]
+            for ln in lanes:
+                for kk, v in opts.items():
+                    ln.set_option(kk, v)
+            for rep in range(3):  # all three lanes in flight, three rounds, every lane sees every batch
+                for li, ln in enumerate(lanes):
+                    qt, qp, qs = batches[(li + rep) % 3]
+                    ln.retrieve_device_enqueue(qt.data_ptr(), qp.data_ptr(), 3000, int(qt.numel()), k, outs[li][0].data_ptr(), outs[li][1].data_ptr())
+                for li, ln in enumerate(lanes):
+                    qt, qp, qs = batches[(li + rep) % 3]
+                    ln.collect(3000, int(qt.numel()), k)
+                    np.testing.assert_array_equal(outs[li][1].cpu().numpy(), want[(li + rep) % 3][1], err_msg=f"k={k} {opts} lane {li}")
+                    np.testing.assert_array_equal(outs[li][0].cpu().numpy(), want[(li + rep) % 3][0], err_msg=f"k={k} {opts} lane {li}")
+            for ln in lanes:
+                for kk in opts:
+                    ln.unset_option(kk)
+    for v in views:
+        v.close()
+    ids, sc = dev.retrieve(batches[0][2].tokens, batches[0][2].ptr, 10)
+    rid, rsc = CO.retrieve(data, indices, indptr, n_docs, batches[0][2].tokens, batches[0][2].ptr, 10)
+    check_topk_rows(ids, sc, rid, rsc, None, what="parent after its views were freed")
+    dev.close()
+
+
 def test_weight_mask_fast_path():
     """masks with values in [0, 1] stay on the fused kernel (applied where a candidate is emitted, numpy
     order: mask before shift); results equal the C oracle's and the dense general kernel's. Other masks are routed."""
