@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the shards' top-k rows meet - p2p: stores into peer memory over NVLink fused with the merge "
                          "(bm25cu_exchange_*), nccl: all_gather + merge kernel")
-    ap.add_argument("--lanes", type=int, default=2,
+    ap.add_argument("--lanes", type=int, default=3,
                     help="batches in flight per GPU in the timed loop: lane 0 is the shard's handle, further lanes are views of it "
                          "(bm25cu_index_view: own stream, workspaces and exchange, shared index), steps go to the lanes round-robin; "
                          "1 = one batch at a time (also measured, as `one_batch_at_a_time`)")

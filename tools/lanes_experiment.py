@@ -1,5 +1,5 @@
-"""Experiment: L independent handles of the same shard on L streams, batches enqueued round-robin (no synchronisation between
-steps): what overlapping consecutive batches on one GPU buys at a given corpus size.
+"""Experiment: L handles of the same shard (the handle + views of it, bm25cu_index_view) on L streams, batches enqueued
+round-robin (no synchronisation between steps): what overlapping consecutive batches on one GPU buys at a given corpus size.
 usage: python tools/lanes_experiment.py [n_docs] [lanes...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,8 +14,9 @@ k = 10
 qt, qp = synth.make_queries_torch(n_queries, n_vocab, seed=1, device=dev)
 n_tok = int(qp[-1])
 handles, streams, outs = [], [], []
+base = DeviceIndex.build_device(tokens.data_ptr(), ptr.data_ptr(), n_docs, n_vocab, "lucene", "lucene", 1.5, 0.75, 0.5)
 for L in range(max(lanes_list)):
-    ix = DeviceIndex.build_device(tokens.data_ptr(), ptr.data_ptr(), n_docs, n_vocab, "lucene", "lucene", 1.5, 0.75, 0.5)
+    ix = base if L == 0 else base.view()
     st = torch.cuda.Stream()
     ix.set_stream(st.cuda_stream)
     handles.append(ix); streams.append(st)
