@@ -10,6 +10,7 @@ import itertools
 import json
 import logging
 import os
+import contextlib
 import threading
 from pathlib import Path
 from typing import Any, Dict, Iterable, List, NamedTuple, Tuple, Union
@@ -119,6 +120,8 @@ class BM25:
         self._mask_key = None     # what the resident device mask was made from (None: no mask resident)
         self._mask_sticky = False  # set through set_weight_mask: applies to calls that pass no mask
         self._mask_keepalive = None
+        self._lanes = None          # handles of the resident index that concurrent retrieve() calls share out (_lane)
+        self._lanes_cv = threading.Condition()
         _lib.lib()  # fail loudly, now, if the CUDA library is missing
 
     # ------------------------------------------------------------------ device residency
@@ -138,12 +141,61 @@ class BM25:
         """Drop the HBM copy of `self.scores`; the next retrieve / get_scores uploads again. Call it after editing
         `self.scores[...]` or `nonoccurrence_array` in place (swapping the arrays is detected without it)."""
         with self._dev_lock:
-            if self._dev is not None:
-                self._dev.close()
-            self._dev = None
+            self._close_dev()
             self._dev_key = None
             if not self._mask_sticky:
                 self._mask_key = None
+
+    def _close_dev(self):
+        """Free the device copy: its views first (include/bm25cu.h, bm25cu_index_view), then the handle itself."""
+        with self._lanes_cv:
+            st, self._lanes = self._lanes, None
+        if st is not None:
+            for v in st["views"]:
+                v.close()
+        if self._dev is not None:
+            self._dev.close()
+        self._dev = None
+
+    MAX_CALLS_IN_FLIGHT = 3  # retrieve() calls of different threads that may be on the GPU at the same time
+
+    @contextlib.contextmanager
+    def _lane(self, dev, base_only: bool):
+        """A handle for one retrieve call. Calls from several threads (a server) overlap on the GPU: the first takes the
+        index's own handle, the next ones views of it (same resident arrays, own stream and workspaces), at most
+        MAX_CALLS_IN_FLIGHT in all; further callers wait. A call that involves a weight mask needs the handle the mask
+        lives on (`base_only`); several devices (DeviceGroup) have one handle."""
+        if not isinstance(dev, _lib.DeviceIndex):
+            yield dev
+            return
+        with self._lanes_cv:
+            st = self._lanes
+            if st is None or st["dev"] is not dev:
+                st = self._lanes = {"dev": dev, "free": [dev], "views": []}
+            while True:
+                if base_only:
+                    if dev in st["free"]:
+                        st["free"].remove(dev)
+                        h = dev
+                        break
+                elif st["free"]:
+                    h = st["free"].pop()  # the index's own handle sits at the end: one caller at a time never makes a view
+                    break
+                elif len(st["views"]) + 1 < self.MAX_CALLS_IN_FLIGHT:
+                    h = dev.view()
+                    st["views"].append(h)
+                    break
+                self._lanes_cv.wait()
+        try:
+            yield h
+        finally:
+            with self._lanes_cv:
+                if self._lanes is st:
+                    if h is dev:
+                        st["free"].append(h)
+                    else:
+                        st["free"].insert(0, h)
+                    self._lanes_cv.notify_all()
 
     # ------------------------------------------------------------------ weight masks (bm25s/__init__.py:610-612, 833-845)
     def _check_mask(self, weight_mask):
@@ -172,12 +224,14 @@ class BM25:
         filtered / weighted by it (no per-call packing or upload). `clear_weight_mask()` removes it."""
         self._check_mask(weight_mask)
         with self._mask_lock():
-            self._load_mask(self._device_index(), weight_mask, sticky=True)
+            with self._lane(self._device_index(), base_only=True) as h:  # no call is running on the handle meanwhile
+                self._load_mask(h, weight_mask, sticky=True)
 
     def clear_weight_mask(self):
         with self._mask_lock():
             if self._dev is not None and self._mask_key is not None:
-                self._dev.set_mask(_lib.MASK_NONE)
+                with self._lane(self._dev, base_only=True) as h:
+                    h.set_mask(_lib.MASK_NONE)
             self._mask_key, self._mask_sticky, self._mask_keepalive = None, False, None
 
     def _mask_lock(self):
@@ -191,9 +245,7 @@ class BM25:
         with self._dev_lock:  # concurrent retrieve() calls: one upload
             key = self._residency_key()
             if self._dev is None or not self._same_key(self._dev_key, key):
-                if self._dev is not None:
-                    self._dev.close()
-                    self._dev = None
+                self._close_dev()
                 sc = self.scores
                 if self.devices is not None and len(self.devices) > 1:
                     self._dev = _lib.DeviceGroup.upload(sc["data"], sc["indices"], sc["indptr"], int(sc["num_docs"]),
@@ -216,7 +268,7 @@ class BM25:
         data, indices, indptr, nonocc = dev.download()
         with self._dev_lock:
             if self._dev is not None and self._dev is not dev:
-                self._dev.close()
+                self._close_dev()
             self.scores = {"data": data, "indices": indices, "indptr": indptr, "num_docs": num_docs}
             self.nonoccurrence_array = nonocc
             self._dev = dev
@@ -544,14 +596,25 @@ class BM25:
             return out + ({},) if with_stats else out
         shift = self._query_shifts(flat, ptr)
         dev = self._device_index()
-        with self._mask_lock():
-            if weight_mask is not None:
-                self._check_mask(weight_mask)
-                self._load_mask(dev, weight_mask, sticky=False)  # resident on the device: 1 bit per document for 0/1 masks
-            elif self._mask_key is not None and not self._mask_sticky:
-                dev.set_mask(_lib.MASK_NONE)  # the mask of an earlier call does not outlive it
-                self._mask_key, self._mask_keepalive = None, None
-            res = dev.retrieve(flat, ptr, k, shift=shift, mask=None, with_stats=with_stats)
+        with contextlib.ExitStack() as stack:
+            with self._mask_lock():
+                if weight_mask is not None:
+                    self._check_mask(weight_mask)
+                elif self._mask_key is not None and not self._mask_sticky:
+                    with self._lane(dev, base_only=True) as h:
+                        h.set_mask(_lib.MASK_NONE)  # the mask of an earlier call does not outlive it
+                    self._mask_key, self._mask_keepalive = None, None
+                masked = weight_mask is not None or self._mask_key is not None
+                # the handle is taken under the mask lock: while an unmasked call holds the index's own handle no other
+                # call can make a mask resident on it
+                h = stack.enter_context(self._lane(dev, base_only=masked))
+                if masked:
+                    # masked calls run one at a time, on the handle the mask is resident on (1 bit per document for 0/1 masks)
+                    if weight_mask is not None:
+                        self._load_mask(h, weight_mask, sticky=False)
+                    res = h.retrieve(flat, ptr, k, shift=shift, mask=None, with_stats=with_stats)
+            if not masked:  # no mask in force: concurrent callers overlap, each on a handle of its own
+                res = h.retrieve(flat, ptr, k, shift=shift, mask=None, with_stats=with_stats)
         ids, scores = res[0], res[1]
         out = (scores, ids.astype(np.int64))
         return out + (res[2],) if with_stats else out

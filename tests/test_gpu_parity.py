@@ -389,6 +389,56 @@ def test_bm25_weight_mask_dtypes_and_sticky_mask():
         r.retrieve(queries, k=k, weight_mask=np.ones(3))
 
 
+def test_bm25_retrieve_from_several_threads():
+    """BM25.retrieve called from several threads at once (a server): unmasked calls overlap on handles of their own (the
+    index's handle + views, at most MAX_CALLS_IN_FLIGHT), masked calls take turns on the handle the mask lives on - every
+    call returns what it returns alone, whatever runs next to it."""
+    import threading
+
+    from bm25s_b200 import BM25
+
+    g = load_golden("synth_medium")
+    corpus = lists_from_flat(g["corpus_tokens"], g["corpus_ptr"])
+    queries = lists_from_flat(g["query_tokens"], g["query_ptr"])
+    V, k = int(g["n_vocab"]), int(g["k"])
+    r = BM25(method="bm25+", backend="cuda")
+    r.index((corpus, {i: i for i in range(V)}), create_empty_token=False, show_progress=False)
+    halves = [queries[: len(queries) // 2], queries[len(queries) // 2:], queries]
+    want_plain = [r.retrieve(q, k=k) for q in halves]
+    want_mask = [r.retrieve(q, k=k, weight_mask=g["mask01"]) for q in halves]
+    want_maskf = [r.retrieve(q, k=k, weight_mask=g["maskf64"]) for q in halves]
+    np.testing.assert_array_equal(want_mask[2].scores, g["bm25plus_scores_mask01"])
+    np.testing.assert_array_equal(want_plain[2].scores, g["bm25plus_scores"])
+    failures = []
+
+    def caller(t):
+        try:
+            for it in range(12):
+                j = (t + it) % 3
+                kind = (t + it // 3) % 4 if t >= 4 else 0  # threads 0-3: unmasked only; 4-5: a mix
+                if kind in (0, 3):
+                    got, want = r.retrieve(halves[j], k=k), want_plain[j]
+                elif kind == 1:
+                    got, want = r.retrieve(halves[j], k=k, weight_mask=g["mask01"]), want_mask[j]
+                else:
+                    got, want = r.retrieve(halves[j], k=k, weight_mask=g["maskf64"]), want_maskf[j]
+                np.testing.assert_array_equal(got.scores, want.scores, err_msg=f"thread {t} call {it} kind {kind}")
+                np.testing.assert_array_equal(got.documents, want.documents, err_msg=f"thread {t} call {it} kind {kind}")
+        except BaseException as e:  # noqa: BLE001
+            failures.append(e)
+
+    pool = [threading.Thread(target=caller, args=(t,)) for t in range(6)]
+    for th in pool:
+        th.start()
+    for th in pool:
+        th.join()
+    if failures:
+        raise failures[0]
+    assert r._lanes is not None and len(r._lanes["views"]) <= BM25.MAX_CALLS_IN_FLIGHT - 1
+    r.invalidate()  # frees the views, then the handle; the next call uploads again
+    np.testing.assert_array_equal(r.retrieve(queries, k=k).scores, want_plain[2].scores)
+
+
 def test_checked_build_finds_no_out_of_range_access():
     """`make checked` (bm25s_b200/libbm25cu_checked.so: -DBM25CU_CHECKED, device-side bounds checks of every index the
     list-at-a-time kernel computes; compute-sanitizer is not available on the GPU pool): the workload of
