@@ -560,23 +560,27 @@ def main():
         torch.cuda.synchronize()
         exchange_check = bool(torch.equal(c_ids, merged[0]) and torch.equal(c_sc.view(torch.int32), merged[1].view(torch.int32)))
         del g_ids, g_sc, c_ids, c_sc
-    # lanes: lane 0 = the shard's handle on torch's current stream; further lanes = views of it on streams of their own
+    # lanes: lane 0 = the shard's handle on torch's current stream; further lanes = views of it on streams of their own.
+    # The views are made AFTER the one-batch-at-a-time measurements: the library sizes a batch's parts by the number of
+    # handles that serve the shard (1 + live views = batches the caller keeps in flight, retrieve_ms.cu).
     n_lanes = max(1, args.lanes) if (world == 1 or args.exchange == "p2p") else 1
     lanes, lane_streams, lane_bufs = [sh], [stream], [(work, merged)]
-    for _ in range(n_lanes - 1):
-        ln = sh.view()
-        if world > 1:
-            ln.enable_peer_exchange(n_queries, k)
-        lw = (torch.empty_like(work[0]), torch.empty_like(work[1]))
-        lm = lw if world == 1 else (torch.empty_like(merged[0]), torch.empty_like(merged[1]))
-        lanes.append(ln)
-        lane_streams.append(torch.cuda.Stream(device))
-        lane_bufs.append((lw, lm))
-    for l in range(1, n_lanes):  # warm the views up (workspaces, stream switch)
-        for _ in range(2):
-            lanes[l].retrieve_device_enqueue(q_tok, q_ptr, k, shift=shift_d, stream=lane_streams[l], out=lane_bufs[l][1] if world > 1 else None,
-                                             work=lane_bufs[l][0])
-            lanes[l].collect()
+
+    def make_views():
+        for _ in range(n_lanes - 1):
+            ln = sh.view()
+            if world > 1:
+                ln.enable_peer_exchange(n_queries, k)
+            lw = (torch.empty_like(work[0]), torch.empty_like(work[1]))
+            lm = lw if world == 1 else (torch.empty_like(merged[0]), torch.empty_like(merged[1]))
+            lanes.append(ln)
+            lane_streams.append(torch.cuda.Stream(device))
+            lane_bufs.append((lw, lm))
+        for l in range(n_lanes):  # warm up (workspaces of the views; lane 0 with the part sizes of n_lanes batches in flight)
+            for _ in range(2):
+                lanes[l].retrieve_device_enqueue(q_tok, q_ptr, k, shift=shift_d, stream=lane_streams[l], out=lane_bufs[l][1] if world > 1 else None,
+                                                 work=lane_bufs[l][0])
+                lanes[l].collect()
 
     def timed_loop(active):
         """K steps, round-robin over the first `active` lanes, enqueued back to back; CUDA events on torch's current stream
@@ -609,11 +613,6 @@ def main():
         return float(t.item()), float(np.mean([ev[i][0].elapsed_time(ev[i][1]) for i in range(args.steps)]))
 
     ms_single, step_ms_local = timed_loop(1)  # one batch at a time: per-batch latency of the device chain
-    ms_total = timed_loop(n_lanes)[0] if n_lanes > 1 else ms_single
-    ms_per_step = ms_total / args.steps
-    value = n_queries / (ms_per_step / 1000.0)
-    last = (args.steps - 1) % n_lanes
-    digest_device = digest_of(lane_bufs[last][1][0].cpu().numpy(), lane_bufs[last][1][1].cpu().numpy())
 
     # a few separately collected steps: the library's own CUDA events around the scoring kernels (roofline), per rank
     stats_acc = []
@@ -653,6 +652,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_qps = n_queries * args.steps / float(t.item())
     e2e_serial_qps, e2e_callers = e2e_qps, 1
+
+    # several batches in flight: the views, the timed loop over all lanes
+    if n_lanes > 1:
+        make_views()
+    ms_total = timed_loop(n_lanes)[0] if n_lanes > 1 else ms_single
+    ms_per_step = ms_total / args.steps
+    value = n_queries / (ms_per_step / 1000.0)
+    last = (args.steps - 1) % n_lanes
+    digest_device = digest_of(lane_bufs[last][1][0].cpu().numpy(), lane_bufs[last][1][1].cpu().numpy())
     if world == 1 and n_lanes > 1:
         # the same C ABI call from n_lanes host threads, one handle (the index or a view of it) each: a server with several
         # request batches in flight. Every call still copies its queries in and its rows out; K calls in all.
@@ -687,6 +695,10 @@ def main():
             if rows is not None and digest_of(np.array(rows[0]), np.array(rows[1])) != digest_of(np.array(e2e_ids), np.array(e2e_sc)):
                 raise RuntimeError("end-to-end arm: a concurrent caller returned different rows")
         e2e_qps, e2e_callers = n_queries * args.steps / e2e_par_s, n_lanes
+    if world == 1:
+        for ln in lanes[1:]:
+            ln.dev.close()  # what follows (BM25.retrieve on the same resident index) runs one call at a time again
+        del lanes[1:]
     clocks = sampler.stop()
     h2d = n_q_tokens * 4 + (n_queries + 1) * 8 + (n_queries * 4 if shift_h is not None and world == 1 else 0)
     d2h = n_queries * k * 8

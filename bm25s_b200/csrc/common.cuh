@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -136,6 +137,9 @@ struct bm25cu_index {
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
     bool is_view = false;          // bm25cu_index_view: the posting arrays and lookup structures belong to another handle
+    bm25cu_index *root = nullptr;  // a view: the handle that owns the arrays
+    std::atomic<int> n_views{0};   // live views of this handle: 1 + n_views handles serve the shard, the caller means to keep
+                                   // that many batches in flight (retrieve_ms.cu sizes its parts by it; knob IN_FLIGHT overrides)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // per-call workspaces
     bm25cu::DevBuf d_qtok, d_qptr, d_shift, d_mask, d_out_ids, d_out_scores, d_ctrl, d_general_list, d_scratch,

@@ -574,6 +574,7 @@ static void destroy(bm25cu_index *ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     if (ix->is_view) {  // a view owns its workspaces, stream and events only
+        if (ix->root) ix->root->n_views.fetch_sub(1);
         ix->d_data = nullptr; ix->d_indices = nullptr; ix->d_indptr = nullptr; ix->d_nonocc = nullptr; ix->d_colmax = nullptr;
         ix->d_colkth = nullptr; ix->d_btab = nullptr; ix->d_btab_off = nullptr; ix->d_btab_sh = nullptr; ix->d_pbm = nullptr;
         ix->d_pbm_off = nullptr; ix->d_pbm_sh = nullptr; ix->d_stab = nullptr; ix->d_stab_off = nullptr; ix->d_stab_sh = nullptr;
@@ -825,6 +826,8 @@ int bm25cu_index_view(const bm25cu_index *src, bm25cu_index **out) {
     BM25CU_CHECK(cudaSetDevice(src->device));
     bm25cu_index *v = new bm25cu_index();
     v->is_view = true;
+    v->root = src->root ? src->root : const_cast<bm25cu_index *>(src);
+    v->root->n_views.fetch_add(1);
     v->device = src->device;
     v->n_vocab = src->n_vocab;
     v->n_docs = src->n_docs;

@@ -845,7 +845,25 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     // larger top lists: every part has to fill a top list of its own before it prunes, so parts are made coarser
     // (k = 1000 at the MS-MARCO shape: 13.2 ms with 65 536, 9.5 ms with 524 288 postings per part)
     const int k_scale = p.kcap <= 32 ? 1 : (p.kcap <= 64 ? 2 : (p.kcap <= 128 ? 4 : 8));
-    const long long part_cost = (long long)ix->knobs.get("MS_PARTCOST", (small ? 32768 : 65536) * k_scale);
+    long long part_cost = (long long)(small ? 32768 : 65536) * k_scale;
+    if (p.kcap <= 32) {
+        // top lists in registers: parts proportional to the batch's work, so that the number of parts per CTA stays put
+        // (queries x postings of the shard as the measure; 32 768 .. 98 304 postings per part for one batch at a time:
+        // 1/8 .. 1/1 of the MS-MARCO shape 0.50 / 0.79 / 1.29 / 2.15 ms). With L batches in flight on views of the shard
+        // the other batches fill the GPU while one batch's last parts run, and coarser parts mean fewer thresholds
+        // re-discovered and fewer partly filled probe rounds: (L + 1) / 2 times coarser, no upper limit
+        // (profiles/round2_lanes_partcost_sweep.log; 3 lanes: 0.42 -> 0.39 / 0.70 -> 0.60 / 1.25 -> 0.97 / 2.04 -> 1.70 ms)
+        const bm25cu_index *root = ix->root ? ix->root : ix;
+        int in_flight = ix->knobs.get("IN_FLIGHT", 1 + root->n_views.load());
+        if (in_flight < 1) in_flight = 1;
+        double c = (double)a.n_queries * (double)ix->nnz / 1.75e7;
+        if (c < 32768.0) c = 32768.0;
+        if (in_flight == 1 && c > 98304.0) c = 98304.0;
+        c *= 0.5 * (in_flight + 1);
+        if (c > 1048576.0) c = 1048576.0;
+        part_cost = (long long)c;
+    }
+    part_cost = (long long)ix->knobs.get("MS_PARTCOST", (int)part_cost);
     const size_t nq = (size_t)a.n_queries;
     int rc;
     if ((rc = ix->d_ms_items.reserve(nq * (size_t)max_parts * 8))) return rc;
