@@ -843,8 +843,9 @@ int launch_retrieve_ms(bm25cu_index *ix, const RetrieveArgs &a, Ctrl *d_ctrl, un
     const int per_sm_cfg = ix->knobs.get("MS_CTAS", 9);
     const bool small = a.n_queries < 3 * ix->sm_count * per_sm_cfg || ix->nnz < 300000000ll;
     // larger top lists: every part has to fill a top list of its own before it prunes, so parts are made coarser
-    // (k = 1000 at the MS-MARCO shape: 13.2 ms with 65 536, 9.5 ms with 524 288 postings per part)
-    const int k_scale = p.kcap <= 32 ? 1 : (p.kcap <= 64 ? 2 : (p.kcap <= 128 ? 4 : 8));
+    // (k = 1000 at the MS-MARCO shape: 13.2 ms with 65 536, 9.5 ms with 524 288 postings per part; with the later kernel
+    // 8.57 ms with 524 288, 8.22 ms with 1 M and above; k = 100: 3.83 ms with 262 144, 3.60 ms with 524 288, 4.29 ms with 1 M)
+    const int k_scale = p.kcap <= 32 ? 1 : (p.kcap <= 64 ? 2 : (p.kcap <= 128 ? 8 : 16));
     long long part_cost = (long long)(small ? 32768 : 65536) * k_scale;
     if (p.kcap <= 32) {
         // top lists in registers: parts proportional to the batch's work, so that the number of parts per CTA stays put

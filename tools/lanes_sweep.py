@@ -1,6 +1,6 @@
 """Knob sweep with batches in flight: one resident shard, L lanes (the handle + views), every setting applied to all lanes with
 set_option and timed at 1 lane and at L lanes (48 batches, round-robin), rows compared with the default setting's.
-usage: python tools/lanes_sweep.py [n_docs] [lanes]"""
+usage: python tools/lanes_sweep.py [n_docs] [lanes] [k]   (SWEEP_PARTCOST=a,b,c: only those part sizes)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,7 +10,7 @@ n_docs = int(sys.argv[1]) if len(sys.argv) > 1 else n_docs_full
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device('cuda')
 tokens, ptr = synth.make_corpus_torch(n_docs, avg_len, n_vocab, seed=0, device=dev)
-k = 10
+k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 qt, qp = synth.make_queries_torch(n_queries, n_vocab, seed=1, device=dev)
 n_tok = int(qp[-1])
 base = DeviceIndex.build_device(tokens.data_ptr(), ptr.data_ptr(), n_docs, n_vocab, "lucene", "lucene", 1.5, 0.75, 0.5)
@@ -69,7 +69,7 @@ for opts in settings:
     if ref is None:
         ref = rows
     same = bool(torch.equal(rows[0], ref[0]) and torch.equal(rows[1], ref[1]) and all(torch.equal(outs[l][1], ref[1]) for l in range(L)))
-    print(f"n_docs {n_docs} {str(opts):48s} 1 lane {t1:.4f} ms   {L} lanes {tl:.4f} ms   same rows: {same}", flush=True)
+    print(f"n_docs {n_docs} k {k} {str(opts):48s} 1 lane {t1:.4f} ms   {L} lanes {tl:.4f} ms   same rows: {same}", flush=True)
     for h in handles:
         for kk in opts:
             h.unset_option(kk)
