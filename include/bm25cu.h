@@ -73,7 +73,9 @@ int bm25cu_index_upload_device(const float *data, const int32_t *indices, const 
 /* A second handle on the SAME resident shard (no copy of the index): it shares the posting arrays and lookup structures
  * of `src` and owns a stream, events and per-call workspaces of its own, so calls on the view and on `src` may be in
  * flight at the same time - several batches on several streams overlap one batch's tail with the next one's start
- * (bench.py --lanes). A view has no resident mask of its own. Free it before `src`. */
+ * (bench.py --lanes). The number of handles on a shard (1 + live views) is taken as the number of batches the caller keeps
+ * in flight, and the scoring kernel cuts a batch into coarser parts accordingly (option "IN_FLIGHT" overrides; the rows do
+ * not depend on it). A view has no resident mask of its own. Free it before `src`. */
 int bm25cu_index_view(const bm25cu_index *src, bm25cu_index **out);
 
 /* Run the handle's device work on a caller-owned CUDA stream (cudaStream_t, e.g. torch's current stream) so that
