@@ -285,3 +285,73 @@ def test_bench_helpers_against_the_oracle():
     rep = bench.oracle_parity((data, indices, indptr), qs.tokens, qs.ptr, n_docs, k, shift, rid.astype(np.int32), bad, 60)
     assert not rep["ok"] and rep["failures"]["score_rows"] >= 1 and rep["first_bad_query"]["q"] == 0
     assert bench.digest_of(rid, rsc) == bench.digest_of(rid.copy(), rsc.copy()) != bench.digest_of(rid, bad)
+
+
+def test_handle_pool_of_concurrent_retrieve_calls():
+    """BM25._lane (host logic, no GPU): one caller at a time always gets the index's own handle; concurrent callers get
+    views, at most MAX_CALLS_IN_FLIGHT handles in all; a call that needs the handle the mask lives on waits for exactly
+    that handle; handles of a device copy that was replaced are not handed out again."""
+    import threading
+    import time
+
+    from bm25s_b200 import BM25, _lib
+
+    class FakeIndex(_lib.DeviceIndex):
+        made = 0
+
+        def __init__(self):  # no library handle
+            self.closed = False
+
+        def view(self):
+            FakeIndex.made += 1
+            return FakeIndex()
+
+        def close(self):
+            self.closed = True
+
+    r = BM25(method="lucene")
+    base = FakeIndex()
+    r._dev = base
+    for _ in range(3):
+        with r._lane(base, base_only=False) as h:
+            assert h is base
+    assert FakeIndex.made == 0
+    with r._lane(base, False) as h0, r._lane(base, False) as h1, r._lane(base, False) as h2:
+        assert h0 is base and h1 is not base and h2 is not base and h1 is not h2
+        assert FakeIndex.made == 2 == BM25.MAX_CALLS_IN_FLIGHT - 1
+        got, cms = [], []
+
+        def fourth():
+            cms.append(r._lane(base, False))
+            got.append(cms[0].__enter__())
+
+        th = threading.Thread(target=fourth)
+        th.start()
+        time.sleep(0.2)
+        assert not got  # a fourth caller waits
+    th.join(5)
+    assert len(got) == 1 and FakeIndex.made == 2
+    cms[0].__exit__(None, None, None)  # the fourth caller's handle goes back
+    assert len(r._lanes["free"]) == 3 and r._lanes["free"][-1] is base
+    # base_only waits for the base handle although views are free
+    with r._lane(base, False) as h0:
+        assert h0 is base
+        got, cms = [], []
+
+        def masked():
+            cms.append(r._lane(base, True))
+            got.append(cms[0].__enter__())
+
+        th = threading.Thread(target=masked)
+        th.start()
+        time.sleep(0.2)
+        assert not got
+    th.join(5)
+    assert got == [base]
+    cms[0].__exit__(None, None, None)
+    views = list(r._lanes["views"])
+    r._close_dev()  # views first, then the handle
+    assert all(v.closed for v in views) and base.closed and r._dev is None and r._lanes is None
+    new = FakeIndex()
+    with r._lane(new, False) as h:
+        assert h is new and r._lanes["dev"] is new and r._lanes["views"] == []
