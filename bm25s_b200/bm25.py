@@ -186,7 +186,13 @@ class BM25:
                     st["views"].append(h)
                     break
                 self._lanes_cv.wait()
+            busy = 1 + len(st["views"]) - len(st["free"])  # handles in use, this one included
         try:
+            # the library sizes a batch's parts by the batches in flight; by default that is the number of handles, which
+            # stays up after a burst of callers - tell it how many calls are on the GPU right now
+            if getattr(h, "_in_flight_told", None) != busy:
+                h.set_option("IN_FLIGHT", busy)
+                h._in_flight_told = busy
             yield h
         finally:
             with self._lanes_cv:

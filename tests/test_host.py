@@ -301,6 +301,11 @@ def test_handle_pool_of_concurrent_retrieve_calls():
 
         def __init__(self):  # no library handle
             self.closed = False
+            self.told = []
+
+        def set_option(self, name, value):
+            assert name == "IN_FLIGHT"
+            self.told.append(value)
 
         def view(self):
             FakeIndex.made += 1
@@ -318,6 +323,7 @@ def test_handle_pool_of_concurrent_retrieve_calls():
     assert FakeIndex.made == 0
     with r._lane(base, False) as h0, r._lane(base, False) as h1, r._lane(base, False) as h2:
         assert h0 is base and h1 is not base and h2 is not base and h1 is not h2
+        assert base.told == [1] and h1.told == [2] and h2.told == [3]  # calls on the GPU when the handle was taken
         assert FakeIndex.made == 2 == BM25.MAX_CALLS_IN_FLIGHT - 1
         got, cms = [], []
 
