@@ -142,7 +142,7 @@ __device__ __forceinline__ unsigned long long xshfl64_xor(unsigned long long v, 
 // ~id: score descending, id ascending), sorted in the warp (rows arrive sorted by their pre-shift scores; the sort makes
 // the merge independent of that), and bitonic-merged into the running top-32 held one key per lane. The non-occurrence
 // shift of BM25L / BM25+ is added AFTER the merge, so the order - and with it the rows - do not depend on the number of
-// shards. Eight queries per CTA, one flag wait per CTA.
+// shards. Eight queries per CTA; the rows are there when the kernel starts (exchange_wait_kernel runs ahead of it).
 __global__ void __launch_bounds__(256) exchange_merge_warp_kernel(void *local, int world, long long cap, int parity, unsigned int epoch,
                                                                   int n_queries, int k, const float *__restrict__ shift,
                                                                   int32_t *out_ids, float *out_scores, unsigned int *err,
