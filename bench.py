@@ -431,6 +431,10 @@ def main():
     del tokens, ptr
     torch.cuda.empty_cache()
     nnz = dev.nnz
+    if nnz * 8 <= 126e6:  # the small shapes (SciFact): say what is true of them
+        config["l2"] = f"index {nnz * 8 / 1e6:.1f} MB fits the 126 MB L2 and is not flushed between steps (launch-bound configuration, not a bandwidth figure)"
+    elif args.shape != "msmarco" or world > 1:
+        config["l2"] = f"inputs larger than L2 (this rank's postings {nnz * 8 / 1e9:.2f} GB + lookup tables vs 126 MB L2), no flush between steps"
     q_tok_h = q_tok.cpu().numpy()
     q_ptr_h = q_ptr.cpu().numpy()
     n_q_tokens = int(q_ptr_h[-1])
